@@ -1,0 +1,149 @@
+/*
+ * selfmask_b200 — C-ABI of the B200-native SelfMask inference + evaluation hot path.
+ *
+ * Drop-in boundary.  Every entry point takes plain device pointers, sizes and a
+ * CUDA stream (passed as void* = cudaStream_t), returns 0 on success or a negative smk_status, never
+ * throws, never allocates device memory (the caller owns every buffer, including the workspace whose
+ * size it queries first) and never synchronises the stream.  One host thread per GPU/process.
+ *
+ * What each group replaces in the reference (paths under /root/reference):
+ *   smk_model_*        networks/maskformer/maskformer.py:164-251  MaskFormer.forward
+ *                      (networks/vision_transformer.py:269-304 encoder,
+ *                       networks/maskformer/transformer_decoder.py:112-150,260-297 decoder,
+ *                       maskformer.py:144-162,223 pixel decoder + mask einsum + sigmoid,
+ *                       maskformer.py:229-239,254-268 objectness MLP), reached through
+ *                      base_structure.py:18-24 BaseStructure._forward
+ *   smk_eval_batch     evaluator.pyc@L199-226 (last-layer slice, x4 bilinear, upper-bound query,
+ *                      objectness top-1) + the integer/float reductions behind
+ *                      metrics/iou.py:22-31, f_measure.py:24-81, mae.py:9, pixel_acc.py:10-14,
+ *                      s_measure.py:11-124
+ *   smk_upsample_bilinear  evaluator.pyc@L209-211  F.interpolate(scale_factor=4, 'bilinear')[..., :h, :w]
+ *   smk_mask_metrics   the same reductions for one full-resolution mask (the five metric callables)
+ *   smk_gemm_*, smk_layernorm, smk_attention, ...   single kernels, exported for unit tests
+ */
+#ifndef SELFMASK_B200_H_
+#define SELFMASK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SMK_OK = 0,
+  SMK_ERR_INVALID = -1,   /* bad argument / unsupported geometry */
+  SMK_ERR_CUDA = -2,      /* a CUDA call failed; see smk_last_error() */
+  SMK_ERR_WORKSPACE = -3, /* workspace too small */
+  SMK_ERR_UNSUPPORTED = -4
+} smk_status;
+
+/* numeric modes */
+enum { SMK_MODE_FP32 = 0,  /* validation: every contraction in fp32 on CUDA cores          */
+       SMK_MODE_BF16 = 1   /* throughput: tcgen05 bf16 operands, fp32 accumulate/residual/LN */ };
+
+typedef struct {
+  int32_t patch;        /* 16 (or 8)                                    */
+  int32_t dim;          /* 384                                          */
+  int32_t depth;        /* 12 encoder blocks                            */
+  int32_t heads;        /* 6                                            */
+  int32_t mlp_dim;      /* 1536                                         */
+  int32_t n_queries;    /* 10 / 20                                      */
+  int32_t dec_layers;   /* 6                                            */
+  int32_t dec_ffn;      /* 1536                                         */
+  int32_t scale_factor; /* pixel-decoder bilinear factor (4 for ViT-S/16) */
+  int32_t pos_grid;     /* side of the learned position grid (14)       */
+} smk_config;
+
+const char* smk_last_error(void);
+int smk_version(void);
+
+/* ---- weights: one fp32 device blob in a canonical order --------------------------------------
+ * The table maps the reference's state_dict keys (SURVEY.md §8b, 267 tensors) to blob offsets. */
+int smk_weight_count(const smk_config* cfg);
+int smk_weight_entry(const smk_config* cfg, int index, char* name, int name_cap, int64_t* offset, int64_t* numel);
+int64_t smk_weights_numel(const smk_config* cfg);
+
+/* ---- model ----------------------------------------------------------------------------------- */
+typedef struct smk_model smk_model;
+
+/* bytes of persistent device memory the model needs for repacked weights + activations at
+ * (max_batch, img_h, img_w) in `mode`. */
+int64_t smk_model_workspace_bytes(const smk_config* cfg, int mode, int max_batch, int img_h, int img_w);
+
+/* `weights` is the fp32 blob (device, must stay alive); `workspace` is caller-owned device memory.
+ * Repacks weights (bf16 copies, position-embedding resample, constant-folded decoder layer-0
+ * self-attention) on `stream`. */
+int smk_model_create(const smk_config* cfg, int mode, const float* weights, void* workspace, int64_t workspace_bytes,
+                     int max_batch, int img_h, int img_w, void* stream, smk_model** out);
+int smk_model_destroy(smk_model* m);
+
+/* x [B,3,H,W] fp32 NCHW (ImageNet-normalised).  Outputs (any may be NULL):
+ *   mask_pred  [B, L, nq, h', w'] fp32 probabilities, L = dec_layers if all_layers else 1 (last)
+ *   objectness [B, L, nq]         fp32 probabilities
+ *   features   [B, dim]           mean over queries of the last decoder layer
+ * h' = ceil(H/patch)*scale_factor. */
+int smk_model_forward(smk_model* m, const float* x, int B, int H, int W, int all_layers,
+                      float* mask_pred, float* objectness, float* features, void* stream);
+
+/* debug taps for stage-level parity tests: copies an internal activation (fp32) into `out`.
+ * what: 1 final-LN encoder tokens [B,N,D]; 2 decoder queries after the shared final norm [L,B,nq,D];
+ *       3 residual stream after the last encoder block [B,N,D] */
+int smk_model_tap(smk_model* m, int what, float* out, int64_t out_numel, void* stream);
+
+/* ---- evaluation ------------------------------------------------------------------------------ */
+#define SMK_QCOUNT_STRIDE 2      /* per query: intersection, union at threshold 0.5            */
+#define SMK_MCOUNT_STRIDE 528    /* per evaluated mask, int32: see layout below                */
+#define SMK_MSUM_STRIDE 32       /* per evaluated mask, double                                 */
+/* int32 layout of one evaluated mask:
+ *   [0,256)   histogram over foreground pixels (gt==1) of bin(p) = #{k : t_k < p}, t_k = float(k/255)
+ *   [256,512) the same over background pixels
+ *   512 tp@0.5   513 (tp+fp)@0.5   514 sum(gt)   515 tp@tau   516 (tp+fp)@tau   (tau = 2*mean(p))
+ *   517 centroid X   518 centroid Y   519 H*W   520 query index of this mask
+ * double layout:
+ *   0 sum p   1 sum |p-g|   2 tau   3 fg sum p   4 fg sum p^2   5 bg sum (1-p)   6 bg sum (1-p)^2
+ *   8+5*q+{0..4}, q = LT,RT,LB,RB: pixel count, sum p, sum p^2, sum g, sum p*g                    */
+
+/* mask_pred: probabilities at mask resolution, element (b,q,y,x) at
+ * mask_pred[b*batch_stride + q*hp*wp + y*wp + x]; objectness (b,q) at objectness[b*obj_stride + q];
+ * gt uint8 {0,1} [B,H,W] with H <= hp*up, W <= wp*up (crop, evaluator.pyc@L211).
+ * Outputs: q_counts int32 [B,nq,2]; idx int32 [B,2] = (objectness top-1, upper-bound query);
+ *          m_counts int32 [B,2,528]; m_sums double [B,2,32]  (index 0 = selected, 1 = upper bound). */
+int smk_eval_batch(const float* mask_pred, int64_t batch_stride, const float* objectness, int64_t obj_stride,
+                   const uint8_t* gt, int B, int nq, int hp, int wp, int up, int H, int W,
+                   int32_t* q_counts, int32_t* idx, int32_t* m_counts, double* m_sums, void* stream);
+
+/* one or more full-resolution masks [n,H,W] fp32 against gt uint8 [n,H,W] → m_counts [n,528], m_sums [n,32] */
+int smk_mask_metrics(const float* pred, const uint8_t* gt, int n, int H, int W,
+                     int32_t* m_counts, double* m_sums, void* stream);
+
+/* in [n,h,w] fp32 → out [n,H,W], H <= h*scale, W <= w*scale; ATen bilinear, align_corners=False */
+int smk_upsample_bilinear(const float* in, float* out, int64_t n, int h, int w, int scale, int H, int W, void* stream);
+
+/* ---- single kernels (unit tests) ------------------------------------------------------------- */
+/* epilogue flags */
+enum { SMK_EPI_NONE = 0, SMK_EPI_GELU = 1, SMK_EPI_RELU = 2, SMK_EPI_RESIDUAL = 4 /* C += existing C (fp32) */ };
+
+/* C[M,N] = A[M,K] · W[N,K]^T + bias[N], fp32 on CUDA cores.  lda/ldc in elements. */
+int smk_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
+                 int M, int N, int K, int epilogue, void* stream);
+/* bf16 tcgen05 GEMM: A [M,K] bf16 (lda), W [N,K] bf16; output bf16 (out_f32 = 0) or fp32 (1); fp32 accumulate.
+ * K % 64 == 0, N % 128 == 0. */
+int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* C, int64_t ldc,
+                  int M, int N, int K, int epilogue, int out_f32, void* stream);
+/* y = LN(x) * gamma + beta over the last dim D (fp32 statistics).  out_bf16 selects the output type. */
+int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
+                  int out_bf16, void* stream);
+/* softmax(scale * Q K^T) V for `batch` problems × `heads`, fp32 math.
+ * Q row (b,i) at q + b*q_bstride + i*ldq, head h in columns [h*dh, h*dh+dh); same for k, v, o. */
+int smk_attention(const void* q, const void* k, const void* v, void* o, int batch, int heads, int dh, int Lq, int Lk,
+                  int64_t q_bstride, int64_t ldq, int64_t k_bstride, int64_t ldk, int64_t v_bstride, int64_t ldv,
+                  int64_t o_bstride, int64_t ldo, float scale, int is_bf16, void* stream);
+/* fp32 → bf16 (round to nearest even) */
+int smk_cast_bf16(const float* in, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFMASK_B200_H_ */

@@ -1,0 +1,83 @@
+// Shared helpers for the selfmask_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/selfmask_b200.h"
+
+namespace smk {
+
+void set_error(const char* fmt, ...);
+
+#define SMK_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      smk::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SMK_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define SMK_CHECK_LAUNCH() SMK_CHECK_CUDA(cudaGetLastError())
+
+#define SMK_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      smk::set_error(__VA_ARGS__);  \
+      return SMK_ERR_INVALID;       \
+    }                               \
+  } while (0)
+
+#define SMK_PROPAGATE(expr)   \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != SMK_OK) return _s; \
+  } while (0)
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ATen bilinear source index (align_corners=False): src = max((dst+0.5)/scale - 0.5, 0)
+struct Tap {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Tap make_tap(int dst, float rscale, int n) {
+  float s = fmaxf(__fmaf_rn((float)dst + 0.5f, rscale, -0.5f), 0.0f);
+  Tap t;
+  t.i0 = min((int)s, n - 1);
+  t.i1 = min(t.i0 + 1, n - 1);
+  t.l1 = s - (float)t.i0;
+  t.l0 = 1.0f - t.l1;
+  return t;
+}
+// "nested" rounding = ATen for the evaluator's shapes (oracle/selfmask_oracle.py upsample_bilinear)
+__device__ __forceinline__ float bilerp(float a, float b, float c, float d, float lx0, float lx1, float ly0, float ly1) {
+  float top = __fmaf_rn(a, lx0, __fmul_rn(b, lx1));
+  float bot = __fmaf_rn(c, lx0, __fmul_rn(d, lx1));
+  return __fmaf_rn(top, ly0, __fmul_rn(bot, ly1));
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace smk

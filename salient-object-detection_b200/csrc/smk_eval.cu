@@ -1,0 +1,360 @@
+// Evaluation kernels: x4 bilinear upsample of probabilities fused with the per-query IoU counts, the
+// upper-bound / objectness query selection and every reduction behind IoU, F-measure (F@0.5, F-max over
+// 255 thresholds via 256-bin histograms, F-mean), MAE, pixel accuracy and S-measure.
+//
+// Reference semantics: evaluator.pyc@L199-226 and metrics/{iou,f_measure,mae,pixel_acc,s_measure}.py
+// (SURVEY.md §8a').  All integer outputs are exact; the host forms the float32 ratios from them.
+// HBM-bound byte work: the full-resolution masks [B,nq,H,W] are never written — each CTA keeps one
+// low-resolution probability plane in shared memory and re-creates full-resolution pixels on the fly.
+#include "smk_common.cuh"
+
+namespace smk {
+
+constexpr int kEvalThreads = 256;
+constexpr int kEvalWarps = kEvalThreads / 32;
+
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < kEvalWarps; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < kEvalWarps; ++i) t += red[i];   // fixed order → run-to-run deterministic
+  return t;
+}
+
+// Value of full-resolution pixel (y,x) of a plane held at low resolution in `pl` ([hp,wp]).
+struct RowTap {
+  const float* r0;
+  const float* r1;
+  float ly0, ly1;
+};
+__device__ __forceinline__ RowTap row_tap(const float* pl, int y, int hp, int wp, float rscale) {
+  Tap t = make_tap(y, rscale, hp);
+  return RowTap{pl + t.i0 * wp, pl + t.i1 * wp, t.l0, t.l1};
+}
+__device__ __forceinline__ float pixel(const RowTap& r, int x, int wp, float rscale) {
+  Tap t = make_tap(x, rscale, wp);
+  return bilerp(r.r0[t.i0], r.r0[t.i1], r.r1[t.i0], r.r1[t.i1], t.l0, t.l1, r.ly0, r.ly1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// E1: per (image, query) intersection / union at threshold 0.5  (evaluator.pyc@L113-120, iou.py:22-30)
+// grid (nq, B), 256 threads.  dynamic smem: hp*wp floats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEvalThreads)
+query_iou_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
+                 int nq, int hp, int wp, int up, int H, int W, int32_t* __restrict__ q_counts) {
+  extern __shared__ float plane[];
+  __shared__ int red[kEvalWarps];
+  const int q = blockIdx.x, b = blockIdx.y;
+  const float* src = mask_pred + (int64_t)b * batch_stride + (int64_t)q * hp * wp;
+  for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) plane[i] = src[i];
+  __syncthreads();
+  const float rscale = 1.0f / (float)up;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int inter = 0, npred = 0, ngt = 0;
+  for (int y = warp; y < H; y += kEvalWarps) {
+    RowTap r = row_tap(plane, y, hp, wp, rscale);
+    const uint8_t* grow = g + (int64_t)y * W;
+    for (int x = lane; x < W; x += 32) {
+      float v = pixel(r, x, wp, rscale);
+      int p = v > 0.5f, t = grow[x] != 0;
+      inter += p & t;
+      npred += p;
+      ngt += t;
+    }
+  }
+  inter = block_sum_int(inter, red);
+  npred = block_sum_int(npred, red);
+  ngt = block_sum_int(ngt, red);
+  if (threadIdx.x == 0) {
+    int32_t* o = q_counts + ((int64_t)b * nq + q) * SMK_QCOUNT_STRIDE;
+    o[0] = inter;
+    o[1] = npred + ngt - inter;   // |p ∪ g|
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E2: all reductions for one evaluated mask.  grid (n_masks_per_image, B).
+//   kSelect = true : mask index chosen here (blockIdx.x 0 → objectness top-1, 1 → best-IoU query)
+//   kSelect = false: blockIdx.x-th plane of `planes` as is (full-resolution masks, up = 1)
+// ------------------------------------------------------------------------------------------------
+struct MaskAcc {
+  double sp = 0, sabs = 0, fg_p = 0, fg_p2 = 0, bg_q = 0, bg_q2 = 0;
+  // region sums by inclusion-exclusion: all / left (x<X) / top (y<Y) / top-left
+  double p_all = 0, p_l = 0, p_t = 0, p_tl = 0;
+  double p2_all = 0, p2_l = 0, p2_t = 0, p2_tl = 0;
+  double pg_all = 0, pg_l = 0, pg_t = 0, pg_tl = 0;
+  int g_l = 0, g_t = 0, g_tl = 0;
+  int tp05 = 0, tpfp05 = 0;
+};
+
+template <bool kSelect, bool kSmemPlane>
+__global__ void __launch_bounds__(kEvalThreads)
+mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
+                    int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
+                    int nq, int hp, int wp, int up, int H, int W, const float* __restrict__ thresholds,
+                    int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
+  extern __shared__ float dyn[];
+  __shared__ int hist[kEvalWarps][512];
+  __shared__ float thr[256];
+  __shared__ int red_i[kEvalWarps];
+  __shared__ double red_d[kEvalWarps];
+  __shared__ int s_sel;
+  const int which = blockIdx.x, b = blockIdx.y;
+  const int n_masks = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    int sel = which;
+    if (kSelect) {
+      if (which == 0) {           // objectness top-1 (evaluator.pyc@L219-221); lowest index on ties
+        const float* ob = objectness + (int64_t)b * obj_stride;
+        float best = ob[0];
+        sel = 0;
+        for (int i = 1; i < nq; ++i)
+          if (ob[i] > best) { best = ob[i]; sel = i; }
+      } else {                    // upper bound: argmax_q I/(U+1e-7) in float32, first maximum
+        const int32_t* qc = q_counts + (int64_t)b * nq * SMK_QCOUNT_STRIDE;
+        float best = -1.0f;
+        sel = 0;
+        for (int i = 0; i < nq; ++i) {
+          float iou = __fdiv_rn((float)qc[2 * i], __fadd_rn((float)qc[2 * i + 1], 1e-7f));
+          if (iou > best) { best = iou; sel = i; }
+        }
+      }
+      idx_out[(int64_t)b * 2 + which] = sel;
+    }
+    s_sel = sel;
+  }
+  for (int i = threadIdx.x; i < kEvalWarps * 512; i += kEvalThreads) (&hist[0][0])[i] = 0;
+  if (threadIdx.x < 255) thr[threadIdx.x] = thresholds[threadIdx.x];
+  if (threadIdx.x == 255) thr[255] = 3.0e38f;
+  __syncthreads();
+  const int sel = s_sel;
+  const float* src = planes + (int64_t)b * batch_stride + (int64_t)sel * hp * wp;
+  const float* pl = src;
+  if (kSmemPlane) {
+    for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) dyn[i] = src[i];
+    pl = dyn;
+    __syncthreads();
+  }
+  const float rscale = 1.0f / (float)up;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+
+  // ---- pass A over the ground truth: area and centroid (s_measure.py:11-31) -----------------
+  int ng = 0, sxg = 0, syg = 0;
+  for (int y = warp; y < H; y += kEvalWarps) {
+    const uint8_t* grow = g + (int64_t)y * W;
+    int rowc = 0;
+    for (int x = lane; x < W; x += 32) {
+      int t = grow[x] != 0;
+      rowc += t;
+      sxg += t * x;
+    }
+    ng += rowc;
+    syg += rowc * y;
+  }
+  ng = block_sum_int(ng, red_i);
+  sxg = block_sum_int(sxg, red_i);
+  syg = block_sum_int(syg, red_i);
+  int X, Y;
+  if (ng == 0) {   // python round(cols / 2): half-to-even
+    X = (int)rint((double)W / 2.0);
+    Y = (int)rint((double)H / 2.0);
+  } else {         // torch.round(float32 ratio): half-to-even
+    X = (int)rintf(__fdiv_rn((float)sxg, (float)ng));
+    Y = (int)rintf(__fdiv_rn((float)syg, (float)ng));
+  }
+
+  // ---- pass B: histograms, counts at 0.5, moments ---------------------------------------------
+  MaskAcc a;
+  int* myhist = hist[warp];
+  for (int y = warp; y < H; y += kEvalWarps) {
+    RowTap r = row_tap(pl, y, hp, wp, rscale);
+    const uint8_t* grow = g + (int64_t)y * W;
+    const bool top = y < Y;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+      const int x = x0 + lane;
+      const bool valid = x < W;
+      float v = 0.f;
+      int t = 0;
+      if (valid) {
+        v = (up == 1) ? r.r0[x] : pixel(r, x, wp, rscale);
+        t = grow[x] != 0;
+      }
+      // bin = #{k : t_k < v}, exact float32 thresholds, strict compare (f_measure.py:65, :45)
+      int k = min(max((int)(v * 255.0f), 0), 255);
+      while (k < 255 && thr[k] < v) ++k;
+      while (k > 0 && !(thr[k - 1] < v)) --k;
+      const int key = valid ? (t ? k : 256 + k) : 1024;
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&myhist[key], __popc(peers));
+      if (valid) {
+        const int p = v > 0.5f;
+        a.tp05 += p & t;
+        a.tpfp05 += p;
+        const double dv = (double)v, dv2 = dv * dv, dg = t ? dv : 0.0;
+        a.sp += dv;
+        a.sabs += t ? 1.0 - dv : dv;
+        if (t) { a.fg_p += dv; a.fg_p2 += dv2; }
+        else   { const double w = 1.0 - dv; a.bg_q += w; a.bg_q2 += w * w; }
+        const bool left = x < X;
+        a.p_all += dv; a.p2_all += dv2; a.pg_all += dg;
+        if (left) { a.p_l += dv; a.p2_l += dv2; a.pg_l += dg; a.g_l += t; }
+        if (top)  { a.p_t += dv; a.p2_t += dv2; a.pg_t += dg; a.g_t += t; }
+        if (left && top) { a.p_tl += dv; a.p2_tl += dv2; a.pg_tl += dg; a.g_tl += t; }
+      }
+    }
+  }
+  const int64_t mrow = (int64_t)b * n_masks + which;
+  int32_t* oc = m_counts + mrow * SMK_MCOUNT_STRIDE;
+  double* os = m_sums + mrow * SMK_MSUM_STRIDE;
+
+  const double sp = block_sum_double(a.sp, red_d);
+  const double sabs = block_sum_double(a.sabs, red_d);
+  const double fg_p = block_sum_double(a.fg_p, red_d), fg_p2 = block_sum_double(a.fg_p2, red_d);
+  const double bg_q = block_sum_double(a.bg_q, red_d), bg_q2 = block_sum_double(a.bg_q2, red_d);
+  const double p_all = block_sum_double(a.p_all, red_d), p_l = block_sum_double(a.p_l, red_d);
+  const double p_t = block_sum_double(a.p_t, red_d), p_tl = block_sum_double(a.p_tl, red_d);
+  const double p2_all = block_sum_double(a.p2_all, red_d), p2_l = block_sum_double(a.p2_l, red_d);
+  const double p2_t = block_sum_double(a.p2_t, red_d), p2_tl = block_sum_double(a.p2_tl, red_d);
+  const double pg_all = block_sum_double(a.pg_all, red_d), pg_l = block_sum_double(a.pg_l, red_d);
+  const double pg_t = block_sum_double(a.pg_t, red_d), pg_tl = block_sum_double(a.pg_tl, red_d);
+  const int g_l = block_sum_int(a.g_l, red_i), g_t = block_sum_int(a.g_t, red_i), g_tl = block_sum_int(a.g_tl, red_i);
+  const int tp05 = block_sum_int(a.tp05, red_i), tpfp05 = block_sum_int(a.tpfp05, red_i);
+
+  // F-mean threshold (f_measure.py:76): 2 * mean(p) in float32
+  const int npix = H * W;
+  const float tau = 2.0f * (float)(sp / (double)npix);
+
+  // ---- pass C: counts at the adaptive threshold -----------------------------------------------
+  int tpm = 0, tpfpm = 0;
+  for (int y = warp; y < H; y += kEvalWarps) {
+    RowTap r = row_tap(pl, y, hp, wp, rscale);
+    const uint8_t* grow = g + (int64_t)y * W;
+    for (int x = lane; x < W; x += 32) {
+      float v = (up == 1) ? r.r0[x] : pixel(r, x, wp, rscale);
+      int p = v > tau, t = grow[x] != 0;
+      tpm += p & t;
+      tpfpm += p;
+    }
+  }
+  tpm = block_sum_int(tpm, red_i);
+  tpfpm = block_sum_int(tpfpm, red_i);
+
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += kEvalThreads) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalWarps; ++w) s += hist[w][i];
+    oc[i] = s;
+  }
+  if (threadIdx.x == 0) {
+    oc[512] = tp05; oc[513] = tpfp05; oc[514] = ng; oc[515] = tpm; oc[516] = tpfpm;
+    oc[517] = X; oc[518] = Y; oc[519] = npix; oc[520] = sel;
+    for (int i = 521; i < SMK_MCOUNT_STRIDE; ++i) oc[i] = 0;
+    os[0] = sp; os[1] = sabs; os[2] = (double)tau; os[3] = fg_p; os[4] = fg_p2; os[5] = bg_q; os[6] = bg_q2; os[7] = 0;
+    // quadrants LT, RT, LB, RB (s_measure.py:71-94): [:Y,:X] [:Y,X:] [Y:,:X] [Y:,X:]
+    const int Xc = min(max(X, 0), W), Yc = min(max(Y, 0), H);
+    const double n_q[4] = {(double)Xc * Yc, (double)(W - Xc) * Yc, (double)Xc * (H - Yc), (double)(W - Xc) * (H - Yc)};
+    const double sp_q[4] = {p_tl, p_t - p_tl, p_l - p_tl, p_all - p_t - p_l + p_tl};
+    const double sp2_q[4] = {p2_tl, p2_t - p2_tl, p2_l - p2_tl, p2_all - p2_t - p2_l + p2_tl};
+    const double spg_q[4] = {pg_tl, pg_t - pg_tl, pg_l - pg_tl, pg_all - pg_t - pg_l + pg_tl};
+    const double sg_q[4] = {(double)g_tl, (double)(g_t - g_tl), (double)(g_l - g_tl), (double)(ng - g_t - g_l + g_tl)};
+    for (int qd = 0; qd < 4; ++qd) {
+      os[8 + 5 * qd + 0] = n_q[qd]; os[8 + 5 * qd + 1] = sp_q[qd]; os[8 + 5 * qd + 2] = sp2_q[qd];
+      os[8 + 5 * qd + 3] = sg_q[qd]; os[8 + 5 * qd + 4] = spg_q[qd];
+    }
+    for (int i = 28; i < SMK_MSUM_STRIDE; ++i) os[i] = 0;
+  }
+}
+
+__global__ void upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int up,
+                                         int H, int W) {
+  // grid (ceil(H/8), n); 256 threads = 8 rows of one plane per CTA, lanes along x
+  const int64_t n = blockIdx.y;
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (y >= H) return;
+  const float rscale = 1.0f / (float)up;
+  RowTap r = row_tap(in + n * h * w, y, h, w, rscale);
+  float* o = out + (n * H + y) * (int64_t)W;
+  for (int x = threadIdx.x & 31; x < W; x += 32) o[x] = pixel(r, x, w, rscale);
+}
+
+static float* g_thresholds = nullptr;   // 255 float32 thresholds t_k = float(k * (1/255)) (f_measure.py:65)
+
+static int ensure_thresholds() {
+  if (g_thresholds) return SMK_OK;
+  float h[256];
+  for (int k = 0; k < 255; ++k) h[k] = (float)((double)k * (1.0 / 255.0));
+  h[255] = 3.0e38f;
+  SMK_CHECK_CUDA(cudaMalloc(&g_thresholds, sizeof(h)));   // 1 KB constant table, once per process
+  SMK_CHECK_CUDA(cudaMemcpy(g_thresholds, h, sizeof(h), cudaMemcpyHostToDevice));
+  return SMK_OK;
+}
+
+}  // namespace smk
+
+using namespace smk;
+
+extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, const float* objectness, int64_t obj_stride,
+                              const uint8_t* gt, int B, int nq, int hp, int wp, int up, int H, int W,
+                              int32_t* q_counts, int32_t* idx, int32_t* m_counts, double* m_sums, void* stream) {
+  SMK_REQUIRE(mask_pred && objectness && gt && q_counts && idx && m_counts && m_sums, "smk_eval_batch: null pointer");
+  SMK_REQUIRE(B >= 0 && nq > 0 && hp > 0 && wp > 0 && up >= 1, "smk_eval_batch: bad sizes");
+  SMK_REQUIRE(H > 0 && W > 0 && H <= hp * up && W <= wp * up, "smk_eval_batch: gt %dx%d larger than masks %dx%d x%d", H, W, hp, wp, up);
+  SMK_REQUIRE(B <= 65535, "smk_eval_batch: B > 65535");
+  if (B == 0) return SMK_OK;
+  SMK_PROPAGATE(ensure_thresholds());
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t plane_bytes = (size_t)hp * wp * sizeof(float);
+  SMK_REQUIRE(plane_bytes <= 160 * 1024, "smk_eval_batch: mask plane %dx%d does not fit shared memory", hp, wp);
+  if (plane_bytes > 48 * 1024) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
+  }
+  query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
+  SMK_CHECK_LAUNCH();
+  mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
+      mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+extern "C" int smk_mask_metrics(const float* pred, const uint8_t* gt, int n, int H, int W, int32_t* m_counts,
+                                double* m_sums, void* stream) {
+  SMK_REQUIRE(pred && gt && m_counts && m_sums, "smk_mask_metrics: null pointer");
+  SMK_REQUIRE(n >= 0 && n <= 65535 && H > 0 && W > 0, "smk_mask_metrics: bad sizes");
+  if (n == 0) return SMK_OK;
+  SMK_PROPAGATE(ensure_thresholds());
+  // one full-resolution plane per "image"; the plane is read from global memory (L1/L2), up = 1
+  mask_metrics_kernel<false, false><<<dim3(1, n), kEvalThreads, 0, (cudaStream_t)stream>>>(
+      pred, (int64_t)H * W, nullptr, 0, nullptr, gt, 1, H, W, 1, H, W, g_thresholds, nullptr, m_counts, m_sums);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+extern "C" int smk_upsample_bilinear(const float* in, float* out, int64_t n, int h, int w, int scale, int H, int W,
+                                     void* stream) {
+  SMK_REQUIRE(in && out, "smk_upsample_bilinear: null pointer");
+  SMK_REQUIRE(n >= 0 && n <= 65535 && h > 0 && w > 0 && scale >= 1 && H > 0 && W > 0 && H <= h * scale && W <= w * scale,
+              "smk_upsample_bilinear: bad sizes");
+  if (n == 0) return SMK_OK;
+  upsample_bilinear_kernel<<<dim3((H + 7) / 8, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(in, out, h, w, scale, H, W);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}

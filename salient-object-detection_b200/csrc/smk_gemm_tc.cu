@@ -1,0 +1,278 @@
+// bf16 tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T (+bias, GELU/ReLU, +residual)
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread) and
+// TMEM owner, warps 2-5 = epilogue (TMEM → registers → global).  Operands are staged by TMA into a
+// kStages-deep ring of 128-byte-swizzled shared-memory tiles; fp32 accumulators live in TMEM and are
+// double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Serves: patch-embed (vision_transformer.py:184-188), qkv / proj / fc1 / fc2 (:113,131,88-94), the
+// decoder's memory K/V projection (transformer_decoder.py:283-291 via nn.MultiheadAttention in_proj).
+#include <mutex>
+
+#include "smk_tc.cuh"
+
+namespace smk {
+
+using namespace tc;
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr int kABytes = TC_BM * TC_BK * 2;
+  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;                       // two accumulator buffers (256 or 512: powers of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+struct TcGemmParams {
+  int M, N, K;
+  const float* bias;
+  void* C;
+  int64_t ldc;
+  int epi;        // SMK_EPI_* flags
+  int out_f32;    // 0 → bf16 output, 1 → fp32 output
+  // token assembly for patch-embed: output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
+  int tok_hw;
+  const float* tok_pos;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = p.N / BN, m_blocks = (p.M + TC_BM - 1) / TC_BM;
+  const int num_tiles = n_blocks * m_blocks, k_blocks = p.K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)   // +32 B per 16-element K step → +2 in the (addr >> 4) field
+            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);              // accumulator complete → epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const int m = m_blk * TC_BM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      int64_t out_row = m;
+      const float* pos_row = nullptr;
+      if (p.tok_hw > 0) {
+        out_row = (int64_t)m + m / p.tok_hw + 1;
+        pos_row = p.tok_pos + (int64_t)(1 + m % p.tok_hw) * p.N;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int n0 = n_blk * BN + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.epi & SMK_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.epi & SMK_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (pos_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (p.out_f32) {
+            float* crow = reinterpret_cast<float*>(p.C) + out_row * p.ldc + n0;
+            if (p.epi & SMK_EPI_RESIDUAL) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(crow + j);
+                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(crow + j) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      g_encode = (PFN_encodeTiled)fn;
+  });
+  if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SMK_ERR_CUDA; }
+  SMK_REQUIRE(((uintptr_t)base % 16) == 0 && row_stride_bytes % 16 == 0, "tensor map: base/stride must be 16-byte aligned");
+  SMK_REQUIRE(box_inner * 2 == 128 && box_outer <= 256, "tensor map: box {%u,%u} unsupported", box_inner, box_outer);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SMK_ERR_CUDA; }
+  return SMK_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = (p.N / BN) * ((p.M + TC_BM - 1) / TC_BM);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, p);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements)
+int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s) {
+  SMK_REQUIRE(K % TC_BK == 0 && N % 128 == 0, "gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, N);
+  SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32, "gemm_bf16: residual epilogue needs fp32 output");
+  SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
+  SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
+  if (M == 0) return SMK_OK;
+  const int BN = (N % 256 == 0 && (int64_t)(N / 256) * ((M + 127) / 128) >= 2 * num_sms()) ? 256 : 128;
+  CUtensorMap ta, tb;
+  SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
+  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)BN));
+  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos};
+  return BN == 256 ? launch_tc<256>(ta, tb, p, s) : launch_tc<128>(ta, tb, p, s);
+}
+
+}  // namespace smk
+
+extern "C" int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                             int epilogue, int out_f32, void* stream) {
+  SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0, "smk_gemm_bf16: bad arguments");
+  return smk::gemm_bf16_tc((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, K, bias, C, ldc, M, N, K, epilogue, out_f32, 0, nullptr,
+                           (cudaStream_t)stream);
+}

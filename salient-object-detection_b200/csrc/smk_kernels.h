@@ -1,0 +1,31 @@
+// Internal (non-ABI) launcher declarations shared between the .cu files.
+#pragma once
+#include "smk_common.cuh"
+
+namespace smk {
+
+int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out, int64_t rows,
+                  int D, float eps, cudaStream_t s);
+int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s);
+int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N, int K,
+             int epi, cudaStream_t s);
+int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s);
+template <typename T, typename TK>
+int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, int dh, int Lq, int Lk, int64_t q_bs, int64_t ldq,
+              int64_t k_bs, int64_t ldk, int64_t v_bs, int64_t ldv, int64_t o_bs, int64_t ldo, float scale, cudaStream_t s);
+template <typename T>
+int im2col(const float* x, T* cols, int B, int H, int W, int P, int hp, int wp, cudaStream_t s);
+int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
+                    cudaStream_t s);
+int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);
+int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D,
+              int hp, int wp, int sf, cudaStream_t s);
+int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s);
+int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s);
+int query_mean(const float* qlast, float* out, int B, int nq, int D, cudaStream_t s);
+int pos_bicubic(const float* pos, float* out, int g, int hp, int wp, int D, cudaStream_t s);
+
+}  // namespace smk

@@ -1,0 +1,399 @@
+// Model handle + forward orchestration: MaskFormer.forward (maskformer.py:164-251) as a fixed sequence of
+// launches on the caller's stream.  No allocation, no synchronisation: everything lives in the caller's
+// workspace (see plan()).
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "smk_kernels.h"
+
+namespace smk {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- weight table: reference state_dict keys → offsets into one fp32 blob -----------
+struct WEntry {
+  std::string name;
+  int64_t offset, numel;
+};
+static const int64_t kWAlign = 64;   // floats → 256-byte aligned tensors (TMA / float4 friendly)
+
+static std::vector<WEntry> weight_table(const smk_config& c) {
+  std::vector<WEntry> t;
+  int64_t off = 0;
+  auto add = [&](const std::string& n, int64_t numel) {
+    t.push_back({n, off, numel});
+    off += align_up(numel, kWAlign);
+  };
+  const int64_t D = c.dim, P = c.patch, F = c.mlp_dim, FD = c.dec_ffn;
+  add("query_embed", (int64_t)c.n_queries * D);
+  add("encoder.cls_token", D);
+  add("encoder.pos_embed", ((int64_t)c.pos_grid * c.pos_grid + 1) * D);
+  add("encoder.patch_embed.proj.weight", D * 3 * P * P);
+  add("encoder.patch_embed.proj.bias", D);
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    add(p + "norm1.weight", D); add(p + "norm1.bias", D);
+    add(p + "attn.qkv.weight", 3 * D * D); add(p + "attn.qkv.bias", 3 * D);
+    add(p + "attn.proj.weight", D * D); add(p + "attn.proj.bias", D);
+    add(p + "norm2.weight", D); add(p + "norm2.bias", D);
+    add(p + "mlp.fc1.weight", F * D); add(p + "mlp.fc1.bias", F);
+    add(p + "mlp.fc2.weight", D * F); add(p + "mlp.fc2.bias", D);
+  }
+  add("encoder.norm.weight", D); add("encoder.norm.bias", D);
+  for (int i = 0; i < c.dec_layers; ++i) {
+    const std::string p = "decoder.layers." + std::to_string(i) + ".";
+    for (const char* a : {"self_attn", "multihead_attn"}) {
+      add(p + a + ".in_proj_weight", 3 * D * D); add(p + a + ".in_proj_bias", 3 * D);
+      add(p + a + ".out_proj.weight", D * D); add(p + a + ".out_proj.bias", D);
+    }
+    add(p + "linear1.weight", FD * D); add(p + "linear1.bias", FD);
+    add(p + "linear2.weight", D * FD); add(p + "linear2.bias", D);
+    for (const char* n : {"norm1", "norm2", "norm3"}) { add(p + n + ".weight", D); add(p + n + ".bias", D); }
+  }
+  add("decoder.norm.weight", D); add("decoder.norm.bias", D);
+  add("ffn.layers.0.weight", D * D); add("ffn.layers.0.bias", D);
+  add("ffn.layers.1.weight", D * D); add("ffn.layers.1.bias", D);
+  add("ffn.layers.2.weight", D); add("ffn.layers.2.bias", 1);
+  return t;
+}
+static int64_t table_numel(const std::vector<WEntry>& t) { return t.empty() ? 0 : t.back().offset + align_up(t.back().numel, kWAlign); }
+
+static int check_config(const smk_config* c) {
+  SMK_REQUIRE(c != nullptr, "null config");
+  SMK_REQUIRE(c->dim > 0 && c->dim % 128 == 0 && c->dim <= 512, "dim=%d unsupported (multiple of 128, <= 512)", c->dim);
+  SMK_REQUIRE(c->heads > 0 && c->dim == c->heads * 64, "heads=%d: head dim must be 64", c->heads);
+  SMK_REQUIRE(c->patch > 0 && (3 * c->patch * c->patch) % 64 == 0, "patch=%d unsupported", c->patch);
+  SMK_REQUIRE(c->mlp_dim % 128 == 0 && c->dec_ffn % 128 == 0, "mlp_dim/dec_ffn must be multiples of 128");
+  SMK_REQUIRE(c->depth > 0 && c->dec_layers > 0 && c->n_queries > 0 && c->n_queries <= 64, "bad depth / layers / n_queries");
+  SMK_REQUIRE(c->scale_factor >= 1 && c->scale_factor <= 8 && c->pos_grid > 0, "bad scale_factor / pos_grid");
+  return SMK_OK;
+}
+
+struct BlockW { int64_t n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b; };
+struct DecW { int64_t saw, sab, saow, saob, caw, cab, caow, caob, l1w, l1b, l2w, l2b, n1w, n1b, n2w, n2b, n3w, n3b; };
+
+}  // namespace smk
+
+using namespace smk;
+
+struct smk_model {
+  smk_config cfg;
+  int mode, max_batch, H, W, hp, wp, hw, N;
+  const float* w;                 // fp32 blob (caller-owned)
+  int64_t o_query, o_cls, o_pos, o_pew, o_peb, o_enw, o_enb, o_dnw, o_dnb, o_f0w, o_f0b, o_f1w, o_f1b, o_f2w, o_f2b;
+  std::vector<BlockW> blk;
+  std::vector<DecW> dec;
+  // workspace
+  float* pos;                     // [N, D] position embedding at this geometry
+  float *kvw32, *kvb;             // decoder memory K/V projection, all layers concatenated: [L*2D, D], [L*2D]
+  __nv_bfloat16 *wb, *kvwb;       // bf16 copies (bf16 mode)
+  float* X;                       // [B*N, D] residual stream (fp32)
+  void *Xn, *QKV, *AO, *Hm, *KV;  // activations in the mode's GEMM input type
+  float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
+  __nv_bfloat16* tokb;            // bf16 copy (bf16 mode)
+  float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
+  int last_B;
+};
+
+namespace smk {
+
+struct Plan {
+  int64_t bytes = 0;
+  uint8_t* base = nullptr;
+  template <typename T>
+  T* take(int64_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + bytes) : nullptr;
+    bytes += align_up(n * (int64_t)sizeof(T), 256);
+    return p;
+  }
+};
+
+// Single source of truth for the workspace layout (sizing pass: m.base == nullptr).
+static void plan(smk_model& m, Plan& pl) {
+  const smk_config& c = m.cfg;
+  const int64_t D = c.dim, B = m.max_batch, N = m.N, M = B * N, L = c.dec_layers, nq = c.n_queries;
+  const bool bf = m.mode == SMK_MODE_BF16;
+  const int64_t esz = bf ? 2 : 4;
+  const int64_t wnumel = table_numel(weight_table(c));
+  m.pos = pl.take<float>(N * D);
+  m.kvw32 = pl.take<float>(L * 2 * D * D);
+  m.kvb = pl.take<float>(L * 2 * D);
+  m.wb = bf ? pl.take<__nv_bfloat16>(wnumel) : nullptr;
+  m.kvwb = bf ? pl.take<__nv_bfloat16>(L * 2 * D * D) : nullptr;
+  m.X = pl.take<float>(M * D);
+  m.Xn = pl.take<uint8_t>(M * D * esz);
+  m.QKV = pl.take<uint8_t>(M * 3 * D * 4);          // fp32-sized: doubles as the fp32 patch-embed output
+  m.AO = pl.take<uint8_t>(M * D * esz);
+  m.Hm = pl.take<uint8_t>(M * (int64_t)c.mlp_dim * esz);   // doubles as the im2col buffer (3*P*P <= 2*mlp_dim)
+  m.KV = pl.take<uint8_t>(M * L * 2 * D * esz);
+  m.tok32 = pl.take<float>(M * D);
+  m.tokb = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
+  const int64_t R = B * nq;
+  m.tgt = pl.take<float>(R * D);
+  m.qin = pl.take<float>(R * D);
+  m.dqk = pl.take<float>(R * 2 * D);
+  m.dv = pl.take<float>(R * D);
+  m.dao = pl.take<float>(R * D);
+  m.t2 = pl.take<float>(R * D);
+  m.ffh = pl.take<float>(R * c.dec_ffn);
+  m.queries = pl.take<float>(L * R * D);
+  m.oh1 = pl.take<float>(L * R * D);
+  m.oh2 = pl.take<float>(L * R * D);
+  m.otmp = pl.take<float>(L * R);
+}
+
+static int64_t find(const std::vector<WEntry>& t, const std::string& n) {
+  for (const auto& e : t)
+    if (e.name == n) return e.offset;
+  return -1;
+}
+
+}  // namespace smk
+
+extern "C" const char* smk_last_error(void) { return smk::g_err; }
+extern "C" int smk_version(void) { return 100; }
+
+extern "C" int smk_weight_count(const smk_config* cfg) {
+  if (check_config(cfg) != SMK_OK) return SMK_ERR_INVALID;
+  return (int)weight_table(*cfg).size();
+}
+extern "C" int smk_weight_entry(const smk_config* cfg, int index, char* name, int name_cap, int64_t* offset, int64_t* numel) {
+  SMK_PROPAGATE(check_config(cfg));
+  const auto t = weight_table(*cfg);
+  SMK_REQUIRE(index >= 0 && index < (int)t.size() && name && name_cap > 0 && offset && numel, "smk_weight_entry: bad arguments");
+  snprintf(name, name_cap, "%s", t[index].name.c_str());
+  *offset = t[index].offset;
+  *numel = t[index].numel;
+  return SMK_OK;
+}
+extern "C" int64_t smk_weights_numel(const smk_config* cfg) {
+  if (check_config(cfg) != SMK_OK) return SMK_ERR_INVALID;
+  return table_numel(weight_table(*cfg));
+}
+
+static int geometry(smk_model& m, const smk_config* cfg, int mode, int max_batch, int H, int W) {
+  SMK_PROPAGATE(check_config(cfg));
+  SMK_REQUIRE(mode == SMK_MODE_FP32 || mode == SMK_MODE_BF16, "mode %d unknown", mode);
+  SMK_REQUIRE(max_batch > 0 && max_batch <= 65535 && H > 0 && W > 0, "bad batch / image size");
+  m.cfg = *cfg;
+  m.mode = mode;
+  m.max_batch = max_batch;
+  m.H = H;
+  m.W = W;
+  m.hp = (H + cfg->patch - 1) / cfg->patch;
+  m.wp = (W + cfg->patch - 1) / cfg->patch;
+  m.hw = m.hp * m.wp;
+  m.N = m.hw + 1;
+  SMK_REQUIRE(3 * cfg->patch * cfg->patch <= 2 * cfg->mlp_dim, "patch too large for the im2col alias");
+  return SMK_OK;
+}
+
+extern "C" int64_t smk_model_workspace_bytes(const smk_config* cfg, int mode, int max_batch, int img_h, int img_w) {
+  smk_model m{};
+  if (geometry(m, cfg, mode, max_batch, img_h, img_w) != SMK_OK) return SMK_ERR_INVALID;
+  Plan pl;
+  plan(m, pl);
+  return pl.bytes;
+}
+
+extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* weights, void* workspace, int64_t workspace_bytes,
+                                int max_batch, int img_h, int img_w, void* stream, smk_model** out) {
+  SMK_REQUIRE(weights && workspace && out, "smk_model_create: null pointer");
+  SMK_REQUIRE(((uintptr_t)weights % 256) == 0 && ((uintptr_t)workspace % 256) == 0, "weights/workspace must be 256-byte aligned");
+  smk_model* m = new smk_model();
+  int st = geometry(*m, cfg, mode, max_batch, img_h, img_w);
+  if (st != SMK_OK) { delete m; return st; }
+  Plan pl;
+  pl.base = reinterpret_cast<uint8_t*>(workspace);
+  plan(*m, pl);
+  if (pl.bytes > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes, got %lld", (long long)pl.bytes, (long long)workspace_bytes);
+    delete m;
+    return SMK_ERR_WORKSPACE;
+  }
+  m->w = weights;
+  m->last_B = 0;
+  const auto t = weight_table(*cfg);
+  auto f = [&](const std::string& n) { return find(t, n); };
+  m->o_query = f("query_embed"); m->o_cls = f("encoder.cls_token"); m->o_pos = f("encoder.pos_embed");
+  m->o_pew = f("encoder.patch_embed.proj.weight"); m->o_peb = f("encoder.patch_embed.proj.bias");
+  m->o_enw = f("encoder.norm.weight"); m->o_enb = f("encoder.norm.bias");
+  m->o_dnw = f("decoder.norm.weight"); m->o_dnb = f("decoder.norm.bias");
+  m->o_f0w = f("ffn.layers.0.weight"); m->o_f0b = f("ffn.layers.0.bias");
+  m->o_f1w = f("ffn.layers.1.weight"); m->o_f1b = f("ffn.layers.1.bias");
+  m->o_f2w = f("ffn.layers.2.weight"); m->o_f2b = f("ffn.layers.2.bias");
+  for (int i = 0; i < cfg->depth; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    m->blk.push_back({f(p + "norm1.weight"), f(p + "norm1.bias"), f(p + "attn.qkv.weight"), f(p + "attn.qkv.bias"),
+                      f(p + "attn.proj.weight"), f(p + "attn.proj.bias"), f(p + "norm2.weight"), f(p + "norm2.bias"),
+                      f(p + "mlp.fc1.weight"), f(p + "mlp.fc1.bias"), f(p + "mlp.fc2.weight"), f(p + "mlp.fc2.bias")});
+  }
+  for (int i = 0; i < cfg->dec_layers; ++i) {
+    const std::string p = "decoder.layers." + std::to_string(i) + ".";
+    m->dec.push_back({f(p + "self_attn.in_proj_weight"), f(p + "self_attn.in_proj_bias"), f(p + "self_attn.out_proj.weight"),
+                      f(p + "self_attn.out_proj.bias"), f(p + "multihead_attn.in_proj_weight"), f(p + "multihead_attn.in_proj_bias"),
+                      f(p + "multihead_attn.out_proj.weight"), f(p + "multihead_attn.out_proj.bias"), f(p + "linear1.weight"),
+                      f(p + "linear1.bias"), f(p + "linear2.weight"), f(p + "linear2.bias"), f(p + "norm1.weight"), f(p + "norm1.bias"),
+                      f(p + "norm2.weight"), f(p + "norm2.bias"), f(p + "norm3.weight"), f(p + "norm3.bias")});
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t D = cfg->dim;
+  auto fail = [&](int code) { delete m; return code; };
+  // position embedding at this geometry (identity copy or bicubic resample, vision_transformer.py:377-401)
+  if (m->hw == cfg->pos_grid * cfg->pos_grid) {
+    if (cudaMemcpyAsync(m->pos, weights + m->o_pos, (size_t)m->N * D * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+      set_error("pos copy failed");
+      return fail(SMK_ERR_CUDA);
+    }
+  } else if ((st = pos_bicubic(weights + m->o_pos, m->pos, cfg->pos_grid, m->hp, m->wp, (int)D, s)) != SMK_OK) {
+    return fail(st);
+  }
+  // decoder memory K/V projection weights of all layers, concatenated: rows [D,3D) of each multihead_attn.in_proj
+  for (int l = 0; l < cfg->dec_layers; ++l) {
+    cudaError_t e1 = cudaMemcpyAsync(m->kvw32 + (int64_t)l * 2 * D * D, weights + m->dec[l].caw + D * D, (size_t)2 * D * D * 4,
+                                     cudaMemcpyDeviceToDevice, s);
+    cudaError_t e2 = cudaMemcpyAsync(m->kvb + (int64_t)l * 2 * D, weights + m->dec[l].cab + D, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, s);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("kv weight copy failed"); return fail(SMK_ERR_CUDA); }
+  }
+  if (mode == SMK_MODE_BF16) {
+    if ((st = cast_bf16(weights, m->wb, table_numel(t), s)) != SMK_OK) return fail(st);
+    if ((st = cast_bf16(m->kvw32, m->kvwb, (int64_t)cfg->dec_layers * 2 * D * D, s)) != SMK_OK) return fail(st);
+  }
+  *out = m;
+  return SMK_OK;
+}
+
+extern "C" int smk_model_destroy(smk_model* m) {
+  delete m;
+  return SMK_OK;
+}
+
+extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int W, int all_layers, float* mask_pred,
+                                 float* objectness, float* features, void* stream) {
+  SMK_REQUIRE(m && x, "smk_model_forward: null pointer");
+  SMK_REQUIRE(B >= 0 && B <= m->max_batch, "batch %d exceeds max_batch %d", B, m->max_batch);
+  SMK_REQUIRE(H == m->H && W == m->W, "image %dx%d does not match the model geometry %dx%d", H, W, m->H, m->W);
+  if (B == 0) return SMK_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const smk_config& c = m->cfg;
+  const int D = c.dim, N = m->N, hw = m->hw, M = B * N, F = c.mlp_dim, L = c.dec_layers, nq = c.n_queries, R = B * nq;
+  const int Kpe = 3 * c.patch * c.patch;
+  const bool bf = m->mode == SMK_MODE_BF16;
+  const float* w = m->w;
+  const __nv_bfloat16* wb = m->wb;
+  const float scale = 0.125f;   // head_dim^-0.5, head_dim = 64
+  m->last_B = B;
+
+  // ---- encoder ------------------------------------------------------------------------------------
+  if (bf) {
+    __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
+    SMK_PROPAGATE(im2col<__nv_bfloat16>(x, Hm, B, H, W, c.patch, m->hp, m->wp, s));
+    SMK_PROPAGATE(gemm_bf16_tc(Hm, Kpe, wb + m->o_pew, Kpe, w + m->o_peb, m->X, D, B * hw, D, Kpe, SMK_EPI_NONE, 1, hw, m->pos, s));
+    SMK_PROPAGATE(assemble_tokens(nullptr, w + m->o_cls, m->pos, m->X, B, hw, D, true, s));
+    for (int i = 0; i < c.depth; ++i) {
+      const BlockW& b = m->blk[i];
+      SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
+      SMK_PROPAGATE((attention<__nv_bfloat16, __nv_bfloat16>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D,
+                                                             (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
+      SMK_PROPAGATE(gemm_bf16_tc(AO, D, wb + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+      SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, 0, 0, nullptr, s));
+      SMK_PROPAGATE(gemm_bf16_tc(Hm, F, wb + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+    }
+    SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tokb, m->tok32, nullptr, M, D, 1e-6f, s));
+    SMK_PROPAGATE(gemm_bf16_tc(m->tokb, D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
+  } else {
+    float *Xn = (float*)m->Xn, *QKV = (float*)m->QKV, *AO = (float*)m->AO, *Hm = (float*)m->Hm;
+    SMK_PROPAGATE(im2col<float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, s));
+    SMK_PROPAGATE(gemm_f32(Hm, Kpe, w + m->o_pew, Kpe, w + m->o_peb, QKV, D, B * hw, D, Kpe, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(assemble_tokens(QKV, w + m->o_cls, m->pos, m->X, B, hw, D, false, s));
+    for (int i = 0; i < c.depth; ++i) {
+      const BlockW& b = m->blk[i];
+      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(gemm_f32(Xn, D, w + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, s));
+      SMK_PROPAGATE((attention<float, float>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D,
+                                             3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
+      SMK_PROPAGATE(gemm_f32(AO, D, w + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, s));
+      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(gemm_f32(Xn, D, w + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, s));
+      SMK_PROPAGATE(gemm_f32(Hm, F, w + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, s));
+    }
+    SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tok32, nullptr, M, D, 1e-6f, s));
+    SMK_PROPAGATE(gemm_f32(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
+  }
+
+  // ---- decoder (transformer_decoder.py:260-297, post-norm; fp32 on CUDA cores in both modes) ------------
+  const float* qpos = w + m->o_query;
+  const int64_t ldkv = (int64_t)L * 2 * D;
+  SMK_CHECK_CUDA(cudaMemsetAsync(m->tgt, 0, (size_t)R * D * 4, s));
+  for (int l = 0; l < L; ++l) {
+    const DecW& d = m->dec[l];
+    // self-attention: q = k = tgt + query_pos, v = tgt
+    SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
+    SMK_PROPAGATE(gemm_f32(m->qin, D, w + d.saw, D, w + d.sab, m->dqk, 2 * D, R, 2 * D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.saw + (int64_t)2 * D * D, D, w + d.sab + 2 * D, m->dv, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE((attention<float, float>(m->dqk, m->dqk + D, m->dv, m->dao, B, c.heads, 64, nq, nq, (int64_t)nq * 2 * D, 2 * D,
+                                           (int64_t)nq * 2 * D, 2 * D, (int64_t)nq * D, D, (int64_t)nq * D, D, scale, s)));
+    SMK_PROPAGATE(gemm_f32(m->dao, D, w + d.saow, D, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n1w, w + d.n1b, m->tgt, nullptr, R, D, 1e-5f, s));
+    // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
+    SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
+    SMK_PROPAGATE(gemm_f32(m->qin, D, w + d.caw, D, w + d.cab, m->dqk, D, R, D, D, SMK_EPI_NONE, s));
+    if (bf) {
+      const __nv_bfloat16* kv = (const __nv_bfloat16*)m->KV + ldkv /*skip cls row*/ + (int64_t)l * 2 * D;
+      SMK_PROPAGATE((attention<float, __nv_bfloat16>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv,
+                                                     ldkv, (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
+    } else {
+      const float* kv = (const float*)m->KV + ldkv + (int64_t)l * 2 * D;
+      SMK_PROPAGATE((attention<float, float>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv, ldkv,
+                                             (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
+    }
+    SMK_PROPAGATE(gemm_f32(m->dao, D, w + d.caow, D, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
+    // FFN
+    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.l1w, D, w + d.l1b, m->ffh, c.dec_ffn, R, c.dec_ffn, D, SMK_EPI_RELU, s));
+    SMK_PROPAGATE(gemm_f32(m->ffh, c.dec_ffn, w + d.l2w, c.dec_ffn, w + d.l2b, m->t2, D, R, D, c.dec_ffn, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n3w, w + d.n3b, m->tgt, nullptr, R, D, 1e-5f, s));
+    // shared final norm on every layer's output (transformer_decoder.py:138-145)
+    SMK_PROPAGATE(layernorm_f32(m->tgt, nullptr, w + m->o_dnw, w + m->o_dnb, m->queries + (int64_t)l * R * D, nullptr, R, D, 1e-5f, s));
+  }
+
+  // ---- heads ----------------------------------------------------------------------------------------
+  const int Lout = all_layers ? L : 1, layer0 = all_layers ? 0 : L - 1;
+  if (mask_pred)
+    SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, nullptr, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
+  if (objectness) {
+    const float* qsrc = m->queries + (int64_t)layer0 * R * D;
+    const int rows = Lout * R;
+    SMK_PROPAGATE(gemm_f32(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
+    SMK_PROPAGATE(gemm_f32(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
+    SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
+    SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));
+  }
+  if (features) SMK_PROPAGATE(query_mean(m->queries + (int64_t)(L - 1) * R * D, features, B, nq, D, s));
+  return SMK_OK;
+}
+
+extern "C" int smk_model_tap(smk_model* m, int what, float* out, int64_t out_numel, void* stream) {
+  SMK_REQUIRE(m && out && m->last_B > 0, "smk_model_tap: no forward pass to tap");
+  const int64_t B = m->last_B, D = m->cfg.dim;
+  const float* src = nullptr;
+  int64_t n = 0;
+  if (what == 1) { src = m->tok32; n = B * m->N * D; }
+  else if (what == 2) { src = m->queries; n = (int64_t)m->cfg.dec_layers * B * m->cfg.n_queries * D; }
+  else if (what == 3) { src = m->X; n = B * m->N * D; }
+  SMK_REQUIRE(src != nullptr, "smk_model_tap: unknown tap %d", what);
+  SMK_REQUIRE(out_numel >= n, "smk_model_tap: output too small (%lld < %lld)", (long long)out_numel, (long long)n);
+  SMK_CHECK_CUDA(cudaMemcpyAsync(out, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SMK_OK;
+}

@@ -1,0 +1,542 @@
+// CUDA-core kernels: LayerNorm, fp32 GEMM (validation mode + the high-precision decoder tail), generic
+// softmax attention, patch im2col, token assembly, residual+LayerNorm, mask head (contraction at patch
+// resolution → bilinear → sigmoid), objectness tail, casts.  Memory-bound ones are vectorised, one warp
+// per row with shuffle reductions.
+#include "smk_common.cuh"
+
+namespace smk {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (vision_transformer.py:165,169,299 eps 1e-6; transformer_decoder.py eps 1e-5).
+// One warp per row; the row lives in registers (D <= 1024, D % 128 == 0); optional residual input and
+// optional second (fp32) output so that bf16-mode callers get both copies in one pass.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut, int kChunks>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
+                 int64_t rows, int D, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const float4* rr = res ? reinterpret_cast<const float4*>(res + row * D) : nullptr;
+  float4 v[kChunks];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    v[c] = xr[lane + 32 * c];
+    if (rr) {
+      float4 r = rr[lane + 32 * c];
+      v[c].x += r.x; v[c].y += r.y; v[c].z += r.z; v[c].w += r.w;
+    }
+    s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+  }
+  if (sum_out) {   // the pre-norm residual stream (x + res), needed by post-norm callers
+    float4* so = reinterpret_cast<float4*>(sum_out + row * D);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) so[lane + 32 * c] = v[c];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+    ss += (a * a + b * b) + (cc * cc + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int i = lane + 32 * c;
+    float4 g = g4[i], b = b4[i], o;
+    o.x = (v[c].x - mean) * rstd * g.x + b.x;
+    o.y = (v[c].y - mean) * rstd * g.y + b.y;
+    o.z = (v[c].z - mean) * rstd * g.z + b.z;
+    o.w = (v[c].w - mean) * rstd * g.w + b.w;
+    if (y32) reinterpret_cast<float4*>(y32 + row * D)[i] = o;
+    if (y) {
+      if constexpr (sizeof(TOut) == 4) {
+        reinterpret_cast<float4*>(y + row * D)[i] = o;
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(y + row * D)[i] = pk;
+      }
+    }
+  }
+}
+
+template <typename TOut>
+static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
+                            float* sum_out, int64_t rows, int D, float eps, cudaStream_t s) {
+  SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
+  if (rows == 0) return SMK_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  switch (D / 128) {
+#define SMK_LN_CASE(c) \
+  case c: layernorm_kernel<TOut, c><<<grid, 256, 0, s>>>(x, res, gamma, beta, y, y32, sum_out, rows, D, eps); break;
+    SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
+#undef SMK_LN_CASE
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out,
+                  int64_t rows, int D, float eps, cudaStream_t s) {
+  return launch_layernorm<float>(x, res, gamma, beta, y, nullptr, sum_out, rows, D, eps, s);
+}
+int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s) {
+  return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, rows, D, eps, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 GEMM  C[M,N] = A[M,K] · W[N,K]^T + bias  (both operands K-contiguous = nn.Linear layout)
+// 64x64x16 tiles, 256 threads, 4x4 micro-tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
+                const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int epi) {
+  __shared__ float As[GBK][GBM + 4];
+  __shared__ float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;     // loader: row within the tile, k offset
+  const int ty = tid >> 4, tx = tid & 15;          // compute: 16x16 threads, 4x4 outputs each
+  const int am = m0 + lr, wn = n0 + lr;
+  const float* ap = A + (int64_t)min(am, M - 1) * lda + lk;
+  const float* wp = W + (int64_t)min(wn, N - 1) * ldw + lk;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += GBK) {
+    float4 a = *reinterpret_cast<const float4*>(ap + k0);
+    float4 w = *reinterpret_cast<const float4*>(wp + k0);
+    if (am >= M) a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wn >= N) w = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+    Bs[lk + 0][lr] = w.x; Bs[lk + 1][lr] = w.y; Bs[lk + 2][lr] = w.z; Bs[lk + 3][lr] = w.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (epi & SMK_EPI_GELU) v = gelu_erf(v);
+      if (epi & SMK_EPI_RELU) v = fmaxf(v, 0.f);
+      float* c = C + (int64_t)m * ldc + n;
+      if (epi & SMK_EPI_RESIDUAL) v += *c;
+      *c = v;
+    }
+  }
+}
+
+int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N,
+             int K, int epi, cudaStream_t s) {
+  SMK_REQUIRE(K % GBK == 0 && lda % 4 == 0 && ldw % 4 == 0, "gemm_f32: K=%d lda=%lld ldw=%lld must be multiples of 16/4/4", K,
+              (long long)lda, (long long)ldw);
+  SMK_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_f32: operands must be 16-byte aligned");
+  if (M == 0 || N == 0) return SMK_OK;
+  dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+  gemm_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic multi-head softmax attention, fp32 math, online softmax over 64-key tiles.
+// vision_transformer.py:122-130 (scale after QK^T) and nn.MultiheadAttention (scale on q) — identical
+// here because scale = 2^-3 is exact.  grid (ceil(Lq/32), heads, batch), 128 threads, dh = 64.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_ROWS = 32, ATT_KT = 64, ATT_DH = 64, ATT_RPW = ATT_ROWS / 4;
+
+template <typename T, typename TK>
+__global__ void __launch_bounds__(128)
+attention_kernel(const T* __restrict__ q, const TK* __restrict__ k, const TK* __restrict__ v, T* __restrict__ o, int Lq, int Lk,
+                 int64_t q_bs, int64_t ldq, int64_t k_bs, int64_t ldk, int64_t v_bs, int64_t ldv, int64_t o_bs, int64_t ldo,
+                 float scale) {
+  __shared__ float qs[ATT_ROWS][ATT_DH];
+  __shared__ float ks[ATT_KT][ATT_DH + 1];
+  __shared__ float vs[ATT_KT][ATT_DH];
+  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * ATT_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qb = q + b * q_bs + h * ATT_DH;
+  const TK* kb = k + b * k_bs + h * ATT_DH;
+  const TK* vb = v + b * v_bs + h * ATT_DH;
+  for (int i = threadIdx.x; i < ATT_ROWS * ATT_DH; i += 128) {
+    const int r = i >> 6, d = i & 63;
+    qs[r][d] = (r0 + r < Lq) ? to_float(qb[(int64_t)(r0 + r) * ldq + d]) * scale : 0.f;
+  }
+  float m[ATT_RPW], l[ATT_RPW], a0[ATT_RPW], a1[ATT_RPW];
+#pragma unroll
+  for (int i = 0; i < ATT_RPW; ++i) { m[i] = -INFINITY; l[i] = 0.f; a0[i] = 0.f; a1[i] = 0.f; }
+  for (int kt = 0; kt < Lk; kt += ATT_KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ATT_KT * ATT_DH; i += 128) {
+      const int r = i >> 6, d = i & 63;
+      const bool ok = kt + r < Lk;
+      ks[r][d] = ok ? to_float(kb[(int64_t)(kt + r) * ldk + d]) : 0.f;
+      vs[r][d] = ok ? to_float(vb[(int64_t)(kt + r) * ldv + d]) : 0.f;
+    }
+    __syncthreads();
+    const bool ok0 = kt + lane < Lk, ok1 = kt + lane + 32 < Lk;
+#pragma unroll
+    for (int i = 0; i < ATT_RPW; ++i) {
+      const float* qr = qs[warp * ATT_RPW + i];
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < ATT_DH; ++d) {
+        const float qv = qr[d];
+        s0 = fmaf(qv, ks[lane][d], s0);
+        s1 = fmaf(qv, ks[lane + 32][d], s1);
+      }
+      s0 = ok0 ? s0 : -INFINITY;
+      s1 = ok1 ? s1 : -INFINITY;
+      const float mn = fmaxf(m[i], warp_max(fmaxf(s0, s1)));   // finite: every tile holds >= 1 valid key
+      const float corr = expf(m[i] - mn);
+      const float p0 = expf(s0 - mn), p1 = expf(s1 - mn);
+      l[i] = l[i] * corr + (p0 + p1);
+      float c0 = a0[i] * corr, c1 = a1[i] * corr;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p0, j);
+        c0 = fmaf(pj, vs[j][lane], c0);
+        c1 = fmaf(pj, vs[j][lane + 32], c1);
+      }
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p1, j);
+        c0 = fmaf(pj, vs[j + 32][lane], c0);
+        c1 = fmaf(pj, vs[j + 32][lane + 32], c1);
+      }
+      a0[i] = c0; a1[i] = c1; m[i] = mn;
+    }
+  }
+  T* ob = o + b * o_bs + h * ATT_DH;
+#pragma unroll
+  for (int i = 0; i < ATT_RPW; ++i) {
+    const int r = r0 + warp * ATT_RPW + i;
+    if (r >= Lq) continue;
+    const float inv = 1.0f / warp_sum(l[i]);
+    ob[(int64_t)r * ldo + lane] = from_float<T>(a0[i] * inv);
+    ob[(int64_t)r * ldo + lane + 32] = from_float<T>(a1[i] * inv);
+  }
+}
+
+template <typename T, typename TK>
+int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, int dh, int Lq, int Lk, int64_t q_bs, int64_t ldq,
+              int64_t k_bs, int64_t ldk, int64_t v_bs, int64_t ldv, int64_t o_bs, int64_t ldo, float scale, cudaStream_t s) {
+  SMK_REQUIRE(dh == ATT_DH, "attention: head dim %d != 64", dh);
+  SMK_REQUIRE(Lq > 0 && Lk > 0 && batch <= 65535 && heads <= 65535, "attention: bad sizes");
+  if (batch == 0) return SMK_OK;
+  dim3 grid((Lq + ATT_ROWS - 1) / ATT_ROWS, heads, batch);
+  attention_kernel<T, TK><<<grid, 128, 0, s>>>(q, k, v, o, Lq, Lk, q_bs, ldq, k_bs, ldk, v_bs, ldv, o_bs, ldo, scale);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+#define SMK_ATT_INST(T, TK)                                                                                                      \
+  template int attention<T, TK>(const T*, const TK*, const TK*, T*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, \
+                                int64_t, int64_t, int64_t, int64_t, float, cudaStream_t);
+SMK_ATT_INST(float, float)
+SMK_ATT_INST(__nv_bfloat16, __nv_bfloat16)
+SMK_ATT_INST(float, __nv_bfloat16)
+#undef SMK_ATT_INST
+
+// ------------------------------------------------------------------------------------------------
+// Patch im2col (vision_transformer.py:184-188 conv k=s=P as a GEMM; :260-267 zero pad right/bottom):
+// cols[b*hw + py*wp + px][c*P*P + ky*P + kx] = x[b,c,py*P+ky,px*P+kx]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp) {
+  // grid (hp*wp, B); one CTA per patch; thread → (c, ky, kx) with kx fastest (coalesced 64-byte runs)
+  const int patch = blockIdx.x, b = blockIdx.y;
+  const int py = patch / wp, px = patch % wp;
+  const int K = 3 * P * P;
+  T* dst = cols + ((int64_t)b * hp * wp + patch) * K;
+  const float* src = x + (int64_t)b * 3 * H * W;
+  for (int i = threadIdx.x; i < K; i += 256) {
+    const int c = i / (P * P), r = i % (P * P), ky = r / P, kx = r % P;
+    const int yy = py * P + ky, xx = px * P + kx;
+    const float v = (yy < H && xx < W) ? src[((int64_t)c * H + yy) * W + xx] : 0.f;
+    dst[i] = from_float<T>(v);
+  }
+}
+template <typename T>
+int im2col(const float* x, T* cols, int B, int H, int W, int P, int hp, int wp, cudaStream_t s) {
+  if (B == 0) return SMK_OK;
+  SMK_REQUIRE(B <= 65535, "im2col: batch too large");
+  im2col_kernel<T><<<dim3(hp * wp, B), 256, 0, s>>>(x, cols, H, W, P, hp, wp);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+template int im2col<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+template int im2col<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
+
+// tokens[b,0,:] = cls + pos[0];  tokens[b,1+p,:] = patch_out[b*hw+p,:] + pos[1+p]   (vision_transformer.py:276-280)
+__global__ void __launch_bounds__(128)
+assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
+                       float* __restrict__ tokens, int hw, int D) {
+  const int t = blockIdx.x, b = blockIdx.y;   // t in [0, hw]; a grid of (1, B) writes the cls rows only
+  const float* src = (t == 0) ? cls : patch_out + ((int64_t)b * hw + t - 1) * D;
+  float* dst = tokens + ((int64_t)b * (hw + 1) + t) * D;
+  for (int d = threadIdx.x; d < D; d += 128) dst[d] = src[d] + pos[(int64_t)t * D + d];
+}
+int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
+                    cudaStream_t s) {
+  if (B == 0) return SMK_OK;
+  assemble_tokens_kernel<<<dim3(cls_only ? 1 : hw + 1, B), 128, 0, s>>>(patch_out, cls, pos, tokens, hw, D);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// out[r, :] = a[r, :] + pos[r % period, :]   (query_pos broadcast over the batch, transformer_decoder.py:257-258)
+__global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ pos, float* __restrict__ out,
+                                int64_t rows, int D, int period) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  const int64_t r = i / D;
+  const int d = (int)(i % D);
+  out[i] = (a ? a[i] : 0.f) + pos[(int64_t)(r % period) * D + d];
+}
+int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s) {
+  if (rows == 0) return SMK_OK;
+  add_rows_kernel<<<(unsigned)((rows * D + 255) / 256), 256, 0, s>>>(a, pos, out, rows, D, period);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + i) = pk;
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return SMK_OK;
+  SMK_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 8) == 0, "cast_bf16: misaligned");
+  cast_bf16_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(in, out, n);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mask head (maskformer.py:144-162, :223): logits at patch resolution = queries · memory^T, then the
+// pixel decoder's bilinear xsf applied to the nq-channel logits (bilinear is linear and per-channel, so
+// it commutes with the contraction — SURVEY.md K12), sigmoid, store mask_pred[b,l,q,:,:].
+// grid (L, B), 256 threads.  dynamic smem: nq*D (queries) + nq*hw (logits) floats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const float* __restrict__ tokens /*[B,N,D] final LN*/,
+                 float* __restrict__ mask_pred /*[B,L,nq,hp*sf,wp*sf]*/, float* __restrict__ logits_out, int B, int nq, int D,
+                 int hp, int wp, int sf, int layer0) {
+  extern __shared__ float sm[];
+  float* qs = sm;                 // [nq][D]
+  float* lg = sm + nq * D;        // [nq][hw]
+  const int l = blockIdx.x, b = blockIdx.y, L = gridDim.x;
+  const int hw = hp * wp, N = hw + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* qsrc = queries + (((int64_t)(layer0 + l) * B + b) * nq) * D;
+  for (int i = threadIdx.x; i < nq * D; i += 256) qs[i] = qsrc[i];
+  __syncthreads();
+  const float* mem = tokens + ((int64_t)b * N + 1) * D;   // skip the cls token (maskformer.py:104)
+  const int per_lane = D / 32;                            // D = 384 → 12
+  for (int n = warp; n < hw; n += 8) {
+    float mv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mv[j] = (j < per_lane) ? mem[(int64_t)n * D + lane + 32 * j] : 0.f;
+    for (int qi = 0; qi < nq; ++qi) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < per_lane) s = fmaf(mv[j], qs[qi * D + lane + 32 * j], s);
+      s = warp_sum(s);
+      if (lane == 0) lg[qi * hw + n] = s;
+    }
+  }
+  __syncthreads();
+  const int Ho = hp * sf, Wo = wp * sf;
+  const float rscale = 1.0f / (float)sf;
+  float* out = mask_pred + (((int64_t)b * L + l) * nq) * Ho * Wo;
+  float* lout = logits_out ? logits_out + (((int64_t)b * L + l) * nq) * Ho * Wo : nullptr;
+  for (int row = warp; row < nq * Ho; row += 8) {
+    const int qi = row / Ho, y = row % Ho;
+    const float* pl = lg + qi * hw;
+    Tap ty = make_tap(y, rscale, hp);
+    const float* r0 = pl + ty.i0 * wp;
+    const float* r1 = pl + ty.i1 * wp;
+    for (int x = lane; x < Wo; x += 32) {
+      Tap tx = make_tap(x, rscale, wp);
+      const float z = bilerp(r0[tx.i0], r0[tx.i1], r1[tx.i0], r1[tx.i1], tx.l0, tx.l1, ty.l0, ty.l1);
+      out[(int64_t)row * Wo + x] = sigmoidf_(z);
+      if (lout) lout[(int64_t)row * Wo + x] = z;
+    }
+  }
+}
+int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq,
+              int D, int hp, int wp, int sf, cudaStream_t s) {
+  if (B == 0) return SMK_OK;
+  SMK_REQUIRE(D % 32 == 0 && D <= 512 && B <= 65535, "mask_head: D=%d unsupported", D);
+  const size_t smem = ((size_t)nq * D + (size_t)nq * hp * wp) * sizeof(float);
+  SMK_REQUIRE(smem <= 200 * 1024, "mask_head: %zu bytes of shared memory needed", smem);
+  if (smem > 48 * 1024) SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mask_head_kernel<<<dim3(L, B), 256, smem, s>>>(queries, tokens, mask_pred, logits_out, B, nq, D, hp, wp, sf, layer0);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// objectness tail: out[r] = sigmoid(dot(h[r,:], w) + b)   (last Linear(384→1) of maskformer.py:254-268 + :239)
+__global__ void __launch_bounds__(256)
+rowdot_sigmoid_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, int64_t rows, int D) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s = fmaf(h[row * D + d], w[d], s);
+  s = warp_sum(s);
+  if (lane == 0) out[row] = sigmoidf_(s + bias[0]);
+}
+int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s) {
+  if (rows == 0) return SMK_OK;
+  rowdot_sigmoid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h, w, bias, out, rows, D);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// objectness comes out as [L,B,nq]; the interface wants [B,L,nq] (maskformer.py:238 permute)
+__global__ void permute_lb_kernel(const float* __restrict__ in, float* __restrict__ out, int L, int B, int n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)L * B * n) return;
+  const int e = (int)(i % n);
+  const int64_t lb = i / n;
+  const int b = (int)(lb % B), l = (int)(lb / B);
+  out[((int64_t)b * L + l) * n + e] = in[i];
+}
+int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s) {
+  const int64_t tot = (int64_t)L * B * n;
+  if (tot == 0) return SMK_OK;
+  permute_lb_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(in, out, L, B, n);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// features[b,:] = mean_q queries_last[b,q,:]   (maskformer.py:203)
+__global__ void query_mean_kernel(const float* __restrict__ qlast, float* __restrict__ out, int nq, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int qi = 0; qi < nq; ++qi) s += qlast[((int64_t)b * nq + qi) * D + d];
+    out[(int64_t)b * D + d] = s / (float)nq;
+  }
+}
+int query_mean(const float* qlast, float* out, int B, int nq, int D, cudaStream_t s) {
+  if (B == 0) return SMK_OK;
+  query_mean_kernel<<<B, 128, 0, s>>>(qlast, out, nq, D);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// Bicubic resample of the learned position grid (vision_transformer.py:377-401; ATen upsample_bicubic2d,
+// align_corners=False, A = -0.75), run once per image geometry at model creation.
+__device__ __forceinline__ float cubic1(float x) { return ((-0.75f + 2.f) * x - (-0.75f + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { return ((-0.75f * x - 5.f * -0.75f) * x + 8.f * -0.75f) * x - 4.f * -0.75f; }
+__global__ void pos_bicubic_kernel(const float* __restrict__ pos /*[1+g*g, D]*/, float* __restrict__ out /*[1+hp*wp, D]*/,
+                                   int g, int hp, int wp, int D) {
+  const int t = blockIdx.x;   // output token
+  if (t == 0) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = pos[d];
+    return;
+  }
+  const int oy = (t - 1) / wp, ox = (t - 1) % wp;
+  const float sy = (float)g / (float)hp, sx = (float)g / (float)wp;
+  const float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+  const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+  const float ty = fy - (float)iy, tx = fx - (float)ix;
+  float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+  float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int yy = min(max(iy - 1 + i, 0), g - 1);
+      float r = 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int xx = min(max(ix - 1 + j, 0), g - 1);
+        r += wx[j] * pos[(int64_t)(1 + yy * g + xx) * D + d];
+      }
+      acc += wy[i] * r;
+    }
+    out[(int64_t)t * D + d] = acc;
+  }
+}
+int pos_bicubic(const float* pos, float* out, int g, int hp, int wp, int D, cudaStream_t s) {
+  pos_bicubic_kernel<<<1 + hp * wp, 128, 0, s>>>(pos, out, g, hp, wp, D);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+}  // namespace smk
+
+using namespace smk;
+
+extern "C" int smk_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int M, int N,
+                            int K, int epilogue, void* stream) {
+  SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0, "smk_gemm_f32: bad arguments");
+  return gemm_f32(A, lda, W, K, bias, C, ldc, M, N, K, epilogue, (cudaStream_t)stream);
+}
+
+extern "C" int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
+                             int out_bf16, void* stream) {
+  SMK_REQUIRE(x && gamma && beta && y && rows >= 0, "smk_layernorm: bad arguments");
+  if (out_bf16) return layernorm_bf16(x, nullptr, gamma, beta, (__nv_bfloat16*)y, nullptr, nullptr, rows, D, eps, (cudaStream_t)stream);
+  return layernorm_f32(x, nullptr, gamma, beta, (float*)y, nullptr, rows, D, eps, (cudaStream_t)stream);
+}
+
+extern "C" int smk_attention(const void* q, const void* k, const void* v, void* o, int batch, int heads, int dh, int Lq, int Lk,
+                             int64_t q_bstride, int64_t ldq, int64_t k_bstride, int64_t ldk, int64_t v_bstride, int64_t ldv,
+                             int64_t o_bstride, int64_t ldo, float scale, int is_bf16, void* stream) {
+  SMK_REQUIRE(q && k && v && o, "smk_attention: null pointer");
+  if (is_bf16)
+    return attention<__nv_bfloat16, __nv_bfloat16>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)o, batch,
+                                    heads, dh, Lq, Lk, q_bstride, ldq, k_bstride, ldk, v_bstride, ldv, o_bstride, ldo, scale,
+                                    (cudaStream_t)stream);
+  return attention<float, float>((const float*)q, (const float*)k, (const float*)v, (float*)o, batch, heads, dh, Lq, Lk, q_bstride, ldq,
+                          k_bstride, ldk, v_bstride, ldv, o_bstride, ldo, scale, (cudaStream_t)stream);
+}
+
+extern "C" int smk_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
+  SMK_REQUIRE(in && out && n >= 0, "smk_cast_bf16: bad arguments");
+  return cast_bf16(in, (__nv_bfloat16*)out, n, (cudaStream_t)stream);
+}

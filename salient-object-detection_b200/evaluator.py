@@ -1,0 +1,123 @@
+"""Batched GPU evaluator with the reference `Evaluator` call surface.
+
+Reference: `evaluator.pyc` (source not shipped): `Evaluator(network, arch, dir_dataset,
+visualizer, debug)` and `__call__(dataset_name, dir_ckpt, img_size, scale_factor, batch_size, device,
+cost_type) -> dict` of 14 averages + `{dir_ckpt}/metrics_{dataset_name}.txt`.
+
+What changes is *where* the work happens: instead of ≥16 device→host syncs per image, one
+`smk_eval_batch` call per batch does the x4 upsample, the per-query IoU counts, the query selection and
+all metric reductions on the GPU; the host only turns integer counts into ratios and keeps the running
+means in dataset order (bit-compatible with `AverageMeter`).
+"""
+import os
+from typing import Callable, Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+from .metrics import METRIC_KEYS, finalize, running_mean
+
+
+class BatchRecords:
+    """Per-image integer / float records of an evaluated batch (device tensors)."""
+
+    def __init__(self, B: int, nq: int, device):
+        self.q_counts = torch.empty(B, nq, _lib.QCOUNT_STRIDE, dtype=torch.int32, device=device)
+        self.idx = torch.empty(B, 2, dtype=torch.int32, device=device)
+        self.m_counts = torch.empty(B, 2, _lib.MCOUNT_STRIDE, dtype=torch.int32, device=device)
+        self.m_sums = torch.empty(B, 2, _lib.MSUM_STRIDE, dtype=torch.float64, device=device)
+
+
+def eval_batch(mask_pred: torch.Tensor, objectness: torch.Tensor, gt: torch.Tensor, up: int = 4,
+               out: Optional[BatchRecords] = None) -> BatchRecords:
+    """evaluator.pyc@L199-226 for a whole batch.
+
+    mask_pred: b x (L x) nq x h' x w' probabilities (5-D → last layer, @L199-205); objectness: b x (L x) nq (x 1);
+    gt: b x 1 x H x W (or b x H x W) {0,1}, any integer/bool dtype.  Returns device-side records.
+    """
+    _lib.require_cuda(mask_pred, "mask_pred", torch.float32)
+    if mask_pred.ndim == 5:
+        mask_pred, objectness = mask_pred[:, -1], objectness[:, -1]
+    objectness = objectness.reshape(objectness.shape[0], -1).float()
+    B, nq, hp, wp = mask_pred.shape
+    if mask_pred.stride()[1:] != (hp * wp, wp, 1) or objectness.stride(1) != 1:
+        mask_pred, objectness = mask_pred.contiguous(), objectness.contiguous()
+    g = gt.reshape(B, gt.shape[-2], gt.shape[-1])
+    if g.dtype != torch.uint8:
+        g = (g != 0).to(torch.uint8)
+    g = g.to(mask_pred.device).contiguous()
+    H, W = g.shape[-2:]
+    rec = out or BatchRecords(B, nq, mask_pred.device)
+    with torch.cuda.device(mask_pred.device):
+        check(lib().smk_eval_batch(ptr(mask_pred), mask_pred.stride(0), ptr(objectness), objectness.stride(0), ptr(g),
+                                   B, nq, hp, wp, up, H, W, ptr(rec.q_counts), ptr(rec.idx), ptr(rec.m_counts), ptr(rec.m_sums),
+                                   stream_ptr()), "smk_eval_batch")
+    return rec
+
+
+def summarize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, float]:
+    """[n_img,2,528] / [n_img,2,32] records in dataset order → the reference's 14-key result
+    (evaluator.pyc@L294-308)."""
+    vals = finalize(m_counts, m_sums)
+    res = {k: running_mean(vals[k][:, 0]) for k in METRIC_KEYS}
+    res.update({k + "_ub": running_mean(vals[k][:, 1]) for k in METRIC_KEYS})
+    return res
+
+
+_TXT_HEADER = ("iou,pixel_acc,f_score,f_max,f_mean,mae,s_measure,miou_ub,pixel_acc_ub,f_score_ub,f_max_ub,f_mean_ub,"
+               "mae_ub,s_measure_ub")
+
+
+class Evaluator:
+    """Same constructor and call signature as the reference Evaluator (evaluator.pyc@L18-32, @L164-174).
+
+    `dataset` may be passed instead of relying on the reference's dataset layer (out of scope, SURVEY.md
+    §2.1 #12): any iterable of dicts {'x': b x 3 x H x W float32, 'm': b x 1 x H x W {0,1}} or a callable
+    `(dataset_name, batch_size) -> iterable`.
+    """
+
+    def __init__(self, network: Callable, arch: str = "vit_small", dir_dataset: Optional[str] = None, visualizer=None,
+                 debug: bool = False, dataset=None):
+        if dir_dataset is not None:
+            assert os.path.exists(dir_dataset), f"{dir_dataset} does not exist"
+        self.model, self.arch, self.dir_dataset, self.visualizer, self.debug = network, arch, dir_dataset, visualizer, debug
+        self.dataset = dataset
+        self.records = None
+
+    def _batches(self, dataset_name: str, batch_size: int) -> Iterable[dict]:
+        if self.dataset is None:
+            raise _lib.SmkError("pass dataset=... (an iterable of {'x','m'} batches); the reference's directory readers "
+                                "are outside the B200 hot path")
+        return self.dataset(dataset_name, batch_size) if callable(self.dataset) else self.dataset
+
+    @torch.no_grad()
+    def __call__(self, dataset_name: str, dir_ckpt: Optional[str] = None, img_size: Optional[int] = None, scale_factor: int = 2,
+                 batch_size: int = 1, device: torch.device = torch.device("cuda:0"), cost_type: str = "iou") -> dict:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.SmkError("the B200 evaluator runs on CUDA devices only")
+        recs = []
+        for dict_data in self._batches(dataset_name, batch_size):
+            x = dict_data["x"].to(device, non_blocking=True)
+            gt = dict_data["m"].to(device, non_blocking=True)
+            out = self.model(x, encoder_only=False, skip_decoder=False)     # BaseStructure._forward contract
+            rec = eval_batch(out["mask_pred"], out["objectness"], gt, up=4)
+            recs.append(rec)
+            if self.debug:
+                break
+        if not recs:
+            raise _lib.SmkError("empty dataset")
+        m_counts = torch.cat([r.m_counts for r in recs]).cpu().numpy()       # one sync for the whole sweep
+        m_sums = torch.cat([r.m_sums for r in recs]).cpu().numpy()
+        self.records = {"m_counts": m_counts, "m_sums": m_sums,
+                        "idx": torch.cat([r.idx for r in recs]).cpu().numpy(),
+                        "q_counts": torch.cat([r.q_counts for r in recs]).cpu().numpy()}
+        res = summarize(m_counts, m_sums)
+        if dir_ckpt is not None:
+            os.makedirs(dir_ckpt, exist_ok=True)
+            with open(f"{dir_ckpt}/metrics_{dataset_name}.txt", "w") as f:
+                f.write(_TXT_HEADER + "\n")
+                f.write(",".join(str(res[k]) for k in METRIC_KEYS) + "," + ",".join(str(res[k + "_ub"]) for k in METRIC_KEYS))
+        return res

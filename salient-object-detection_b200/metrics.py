@@ -1,0 +1,222 @@
+"""Metric finalisation on the host + drop-in replacements for the reference's five metric callables.
+
+The GPU produces exact integer counts / 256-bin histograms and double-precision moment sums per image
+(`smk_eval_batch`, `smk_mask_metrics`); this module turns them into the reference's float32 values with the
+same operation order as `metrics/iou.py:22-31`, `f_measure.py:24-81`, `mae.py:9`, `pixel_acc.py:10-14`,
+`s_measure.py:11-124` and averages them like `metrics/average_meter.py:12-16`.  Pure numpy, vectorised
+over images; no pixel ever reaches the host.
+"""
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+F32 = np.float32
+EPS = F32(1e-7)
+METRIC_KEYS = ("iou", "pixel_accuarcy", "f_score", "f_max", "f_mean", "mae", "s_measure")   # [sic] evaluator.pyc@L294-308
+
+
+def iou_from_counts(inter, union):
+    """iou.py:31 — int64 / (int64 + 1e-7) in float32."""
+    return (np.asarray(inter).astype(F32) / (np.asarray(union).astype(F32) + EPS)).astype(F32)
+
+
+def f_from_counts(tp, tp_fp, tp_fn, beta_square: float = 0.3):
+    """f_measure.py:24-50; the reference squares beta_square once more (:49,80) → weight 0.09."""
+    tp = np.asarray(tp).astype(F32)
+    prec = tp / (np.asarray(tp_fp).astype(F32) + EPS)
+    rec = tp / (np.asarray(tp_fn).astype(F32) + EPS)
+    b2 = beta_square ** 2
+    return ((F32(1 + b2) * prec * rec) / (F32(b2) * prec + rec + EPS)).astype(F32)
+
+
+def counts_above_thresholds(hist: np.ndarray) -> np.ndarray:
+    """hist[..., 256] over bin(p) = #{k : t_k < p}  →  count(p > t_k) for k = 0..254 = Σ_{b>k} hist[b]."""
+    total = hist.sum(axis=-1, keepdims=True, dtype=np.int64)
+    return (total - np.cumsum(hist, axis=-1, dtype=np.int64))[..., :255]
+
+
+def s_measure_from_sums(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
+    """s_measure.py:108-124 from moment sums (float64).  counts [...,528] int, sums [...,32] float64."""
+    counts = np.asarray(counts)
+    sums = np.asarray(sums, np.float64)
+    out = np.empty(counts.shape[:-1], np.float64)
+    flat_c, flat_s, flat_o = counts.reshape(-1, counts.shape[-1]), sums.reshape(-1, sums.shape[-1]), out.reshape(-1)
+    for i in range(flat_c.shape[0]):
+        c, s = flat_c[i], flat_s[i]
+        n, G = float(c[519]), float(c[514])
+        mean_p = s[0] / n
+        if G == 0:
+            flat_o[i] = 1.0 - mean_p
+            continue
+        if G == n:
+            flat_o[i] = mean_p
+            continue
+        with np.errstate(all="ignore"):
+            def obj(sum1, sum2, cnt):                      # s_measure.py:54-60, unbiased std
+                mu = sum1 / cnt
+                var = (sum2 - cnt * mu * mu) / (cnt - 1) if cnt > 1 else float("nan")
+                sd = math.sqrt(max(var, 0.0)) if not math.isnan(var) else float("nan")
+                return 2.0 * mu / (mu * mu + 1.0 + sd + 1e-20)
+            u = G / n
+            s_obj = u * obj(s[3], s[4], G) + (1 - u) * obj(s[5], s[6], n - G)
+            X, Y = float(c[517]), float(c[518])
+            hw = n
+            # widths are not in the record: recover W, H from quadrant pixel counts is unnecessary — the
+            # weights only need X*Y/area etc., and (W-X)*Y = N_RT, X*(H-Y) = N_LB
+            q = s[8:28].reshape(4, 5)
+            w1 = F32(F32(X) * F32(Y)) / F32(hw)
+            w2 = F32(q[1, 0]) / F32(hw)
+            w3 = F32(q[2, 0]) / F32(hw)
+            w4 = F32(1) - w1 - w2 - w3
+            Q = []
+            for k in range(4):
+                N, sp, sp2, sg, spg = q[k]
+                if N == 0:
+                    Q.append(float("nan"))
+                    continue
+                x, y = sp / N, sg / N
+                den = N - 1 + 1e-20
+                sx2 = (sp2 - N * x * x) / den
+                sy2 = (sg - N * y * y) / den
+                sxy = (spg - N * x * y) / den
+                a = 4 * x * y * sxy
+                b = (x * x + y * y) * (sx2 + sy2)
+                if (y == 0.0 or y == 1.0) and not math.isnan(a):
+                    a = 0.0                                  # (g - ȳ) ≡ 0 → the reference's σxy is an exact zero
+                if a != 0:
+                    Q.append(a / (b + 1e-20))
+                elif a == 0 and b == 0:
+                    Q.append(1.0)
+                else:
+                    Q.append(0.0)
+            s_reg = float(w1) * Q[0] + float(w2) * Q[1] + float(w3) * Q[2] + float(w4) * Q[3]
+            val = alpha * s_obj + (1 - alpha) * s_reg
+        flat_o[i] = 0.0 if val < 0 else val
+    return out
+
+
+def finalize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, np.ndarray]:
+    """Per-mask metric values from the GPU records.  m_counts [...,528] int32, m_sums [...,32] float64.
+    Returns float32 arrays of shape [...] (s_measure float64, like the reference's python float)."""
+    c = np.asarray(m_counts).astype(np.int64)
+    s = np.asarray(m_sums, np.float64)
+    tp05, tpfp05, G, tpm, tpfpm, n = c[..., 512], c[..., 513], c[..., 514], c[..., 515], c[..., 516], c[..., 519]
+    union = tpfp05 + G - tp05
+    fg_above = counts_above_thresholds(c[..., 0:256])
+    all_above = fg_above + counts_above_thresholds(c[..., 256:512])
+    f_k = f_from_counts(fg_above, all_above, G[..., None])
+    wrong = tpfp05 + G - 2 * tp05
+    return {
+        "iou": iou_from_counts(tp05, union),
+        "pixel_accuarcy": ((n - wrong).astype(F32) / n.astype(F32)).astype(F32),
+        "f_score": f_from_counts(tp05, tpfp05, G),
+        "f_max": f_k.max(axis=-1),
+        "f_mean": f_from_counts(tpm, tpfpm, G),
+        "mae": (s[..., 1] / n).astype(F32),
+        "s_measure": s_measure_from_sums(c, s),
+    }
+
+
+def running_mean(vals: np.ndarray) -> float:
+    """AverageMeter (average_meter.py:12-16): sequential accumulation in the dtype of the values
+    (float32 for the tensor-valued metrics, float64 for S-measure's python floats), dataset order."""
+    vals = np.asarray(vals)
+    if vals.size == 0:
+        return 0.0
+    return float(np.add.accumulate(vals, dtype=vals.dtype)[-1] / vals.dtype.type(len(vals)))
+
+
+class AverageMeter:
+    """metrics/average_meter.py:1-16, unchanged semantics."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n: int):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+# ---- drop-in metric callables (same names, arguments and return types as metrics/*.py) ---------------
+
+def _device_record(pred_mask: torch.Tensor, gt_mask: torch.Tensor):
+    """Run the GPU reduction for [H,W] or [B,H,W] masks; returns (counts [n,528], sums [n,32]) on the host."""
+    _lib.require_cuda(pred_mask, "pred_mask")
+    if pred_mask.shape != gt_mask.shape:
+        raise AssertionError(f"{pred_mask.shape} != {gt_mask.shape}")
+    p = pred_mask.detach().to(torch.float32).reshape(-1, *pred_mask.shape[-2:]).contiguous()
+    g = (gt_mask.detach().reshape(p.shape) != 0).to(torch.uint8).to(p.device).contiguous()
+    n, H, W = p.shape
+    counts = torch.empty(n, _lib.MCOUNT_STRIDE, dtype=torch.int32, device=p.device)
+    sums = torch.empty(n, _lib.MSUM_STRIDE, dtype=torch.float64, device=p.device)
+    with torch.cuda.device(p.device):
+        check(lib().smk_mask_metrics(ptr(p), ptr(g), n, H, W, ptr(counts), ptr(sums), stream_ptr()), "smk_mask_metrics")
+    return counts.cpu().numpy(), sums.cpu().numpy()
+
+
+def _shape_like(pred_mask, arr):
+    t = torch.from_numpy(np.asarray(arr))
+    return t.reshape(pred_mask.shape[:-2]) if pred_mask.ndim > 2 else t.reshape(())
+
+
+def compute_iou(pred_mask, gt_mask, threshold: Optional[float] = 0.5, eps: float = 1e-7):
+    """metrics/iou.py:6-32 (threshold 0.5 or boolean input)."""
+    if threshold is None or pred_mask.dtype == torch.bool:
+        pred_mask = pred_mask.to(torch.float32)       # {0,1} > 0.5 reproduces the boolean mask
+    elif threshold != 0.5:
+        raise _lib.SmkError("only threshold=0.5 is implemented on the GPU path")
+    c, s = _device_record(pred_mask, gt_mask)
+    return _shape_like(pred_mask, finalize(c, s)["iou"])
+
+
+class FMeasure:
+    """metrics/f_measure.py:4-92."""
+
+    def __init__(self, default_thres: float = 0.5, beta_square: float = 0.3, n_bins: int = 255, eps: float = 1e-7):
+        if default_thres != 0.5 or n_bins != 255 or beta_square != 0.3 or eps != 1e-7:
+            raise _lib.SmkError("only the reference defaults are implemented on the GPU path")
+
+    def __call__(self, pred_mask: torch.Tensor, gt_mask: torch.Tensor) -> dict:
+        """pred_mask, gt_mask: (H x W), as documented by the reference (:83-92); returns 0-d CPU tensors."""
+        if pred_mask.ndim != 2:
+            raise _lib.SmkError("FMeasure expects (H x W) masks")
+        c, s = _device_record(pred_mask, gt_mask)
+        f = finalize(c, s)
+        return {k: torch.from_numpy(np.asarray(f[src])).reshape(())
+                for k, src in (("f_measure", "f_score"), ("f_max", "f_max"), ("f_mean", "f_mean"))}
+
+
+def compute_mae(pred_mask: torch.Tensor, gt_mask: torch.Tensor) -> torch.Tensor:
+    """metrics/mae.py:4-9."""
+    c, s = _device_record(pred_mask, gt_mask)
+    return _shape_like(pred_mask, finalize(c, s)["mae"])
+
+
+def compute_pixel_accuracy(pred_mask: torch.Tensor, gt_mask: torch.Tensor, threshold: Optional[float] = 0.5) -> torch.Tensor:
+    """metrics/pixel_acc.py:5-14."""
+    if threshold is None:
+        pred_mask = pred_mask.to(torch.float32)
+    c, s = _device_record(pred_mask, gt_mask)
+    return _shape_like(pred_mask, finalize(c, s)["pixel_accuarcy"])
+
+
+class SMeasure:
+    """metrics/s_measure.py:6-124 (returns a python float; unlike the reference it does not mutate gt_mask)."""
+
+    def __init__(self, alpha: float = 0.5):
+        self.alpha = alpha
+
+    def __call__(self, pred_mask: torch.Tensor, gt_mask: torch.Tensor) -> float:
+        assert pred_mask.shape == gt_mask.shape
+        c, s = _device_record(pred_mask, gt_mask >= 0.5)
+        return float(s_measure_from_sums(c, s, self.alpha).reshape(-1)[0])

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference model interface for the B200 path.
+
+`SelfMaskB200` keeps the constructor keywords, attributes and `forward` contract of
+`networks/maskformer/maskformer.py:11-72,164-251` (MaskFormer) so it can stand in for it behind
+`BaseStructure._forward` (base_structure.py:18-24) and `Evaluator(network=...)`:
+
+    model(x, encoder_only=False, skip_decoder=False) -> {"mask_pred", "objectness", "features"}
+
+All arithmetic happens in libselfmask_b200.so (hand-written sm_100a CUDA); torch only owns device memory
+and the stream.
+"""
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import SmkConfig, SmkError, check, lib, ptr, stream_ptr
+
+_MODES = {"fp32": _lib.SMK_MODE_FP32, "bf16": _lib.SMK_MODE_BF16}
+
+
+def weight_table(cfg: SmkConfig):
+    """[(state_dict key, offset, numel)] of the canonical fp32 weight blob (from the C library)."""
+    n = lib().smk_weight_count(C.byref(cfg))
+    if n <= 0:
+        check(n, "smk_weight_count")
+    out, buf = [], C.create_string_buffer(256)
+    off, num = C.c_int64(), C.c_int64()
+    for i in range(n):
+        check(lib().smk_weight_entry(C.byref(cfg), i, buf, 256, C.byref(off), C.byref(num)), "smk_weight_entry")
+        out.append((buf.value.decode(), off.value, num.value))
+    return out
+
+
+class SelfMaskB200(torch.nn.Module):
+    """Drop-in for the reference `MaskFormer` (vit_small / dino, use_binary_classifier=True).
+
+    Extra keywords (not in the reference): `mode` ("bf16" throughput | "fp32" validation),
+    `return_intermediate` False gives the legal fast variant of the interface — 4-D `mask_pred` with 3-D
+    `objectness` (evaluator.pyc@L199-205), `max_batch` sizes the workspace.
+    """
+
+    def __init__(self, n_queries: int = 20, arch: str = "vit_small", patch_size: int = 16, training_method: str = "dino",
+                 n_decoder_layers: int = 6, normalize_before: bool = False, return_intermediate: bool = True,
+                 learnable_pixel_decoder: bool = False, lateral_connection: bool = False, scale_factor: int = 4,
+                 abs_2d_pe_init: bool = False, use_binary_classifier: bool = True, mode: str = "bf16", max_batch: int = 64,
+                 device: Optional[torch.device] = None):
+        super().__init__()
+        if arch != "vit_small" or training_method != "dino":
+            raise SmkError("only arch='vit_small', training_method='dino' is on the B200 path (SURVEY.md §8)")
+        if normalize_before or lateral_connection or learnable_pixel_decoder:
+            raise SmkError("normalize_before / lateral_connection / learnable_pixel_decoder are not on the path")
+        if not use_binary_classifier:
+            raise SmkError("use_binary_classifier=False is not on the path (the evaluator requires objectness)")
+        if mode not in _MODES:
+            raise SmkError(f"mode must be one of {sorted(_MODES)}")
+        self.arch, self.use_binary_classifier = arch, True
+        self.lateral_connection, self.learnable_pixel_decoder = False, False
+        self.scale_factor, self.return_intermediate, self.mode = scale_factor, return_intermediate, mode
+        self.cfg = SmkConfig(patch=patch_size, dim=384, depth=12, heads=6, mlp_dim=1536, n_queries=n_queries,
+                             dec_layers=n_decoder_layers, dec_ffn=1536, scale_factor=scale_factor,
+                             pos_grid=224 // patch_size)
+        # attributes the reference callers read (maskformer.py:32-34,107,184-185)
+        self.encoder = SimpleNamespace(patch_size=patch_size, depth=12, n_embs=384, n_heads=6, mlp_ratio=4)
+        self.max_batch = max_batch
+        self._table = None
+        self._blob = None          # fp32 weights, one device tensor in the library's canonical order
+        self._handles = {}         # (H, W) -> (handle, workspace tensor)
+        self._device = torch.device(device) if device is not None else None
+        self._loaded = False
+
+    # ---- nn.Module protocol used by the reference (evaluator.pyc@L358-360, app.py:178-187) ----------
+    def to(self, device=None, *a, **k):
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise SmkError("SelfMaskB200 only runs on CUDA devices")
+            if self._blob is not None and self._blob.device != device:
+                self._release()
+                self._blob = self._blob.to(device)
+            self._device = device
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def table(self):
+        if self._table is None:
+            self._table = weight_table(self.cfg)
+        return self._table
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Accepts the reference's raw state_dict or a checkpoint dict with a 'model' entry."""
+        if "model" in state_dict and "query_embed" not in state_dict:
+            state_dict = state_dict["model"]
+        dev = self._device or torch.device("cuda", torch.cuda.current_device())
+        table = self.table()
+        names = {n for n, _, _ in table}
+        missing = sorted(names - set(state_dict.keys()))
+        unexpected = sorted(set(state_dict.keys()) - names)
+        if strict and (missing or unexpected):
+            raise SmkError(f"load_state_dict: missing {missing[:5]}{'...' if len(missing) > 5 else ''}, "
+                           f"unexpected {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}")
+        total = lib().smk_weights_numel(C.byref(self.cfg))
+        host = torch.zeros(total, dtype=torch.float32)
+        for name, off, numel in table:
+            if name not in state_dict:
+                continue
+            t = state_dict[name].detach().to("cpu", torch.float32).reshape(-1)
+            if t.numel() != numel:
+                raise SmkError(f"load_state_dict: {name} has {t.numel()} elements, expected {numel}")
+            host[off:off + numel] = t
+        self._release()
+        self._blob = host.to(dev)
+        self._device = dev
+        self._loaded = True
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def state_dict(self, *a, **k):
+        if self._blob is None:
+            return {}
+        return {n: self._blob[o:o + m].clone() for n, o, m in self.table()}
+
+    def _release(self):
+        for ent in self._handles.values():
+            lib().smk_model_destroy(ent[0])
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _handle(self, B: int, H: int, W: int):
+        if not self._loaded:
+            raise SmkError("weights not loaded: call load_state_dict first")
+        key = (H, W)
+        ent = self._handles.get(key)
+        if ent is not None and ent[2] >= B:
+            return ent[0]
+        if ent is not None:
+            lib().smk_model_destroy(ent[0])
+        cap = max(B, self.max_batch)
+        mode = _MODES[self.mode]
+        nbytes = lib().smk_model_workspace_bytes(C.byref(self.cfg), mode, cap, H, W)
+        if nbytes <= 0:
+            check(int(nbytes), "smk_model_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self._blob.device)
+        handle = C.c_void_p()
+        check(lib().smk_model_create(C.byref(self.cfg), mode, ptr(self._blob), ptr(ws), nbytes, cap, H, W, stream_ptr(),
+                                     C.byref(handle)), "smk_model_create")
+        self._handles[key] = (handle, ws, cap)
+        return handle
+
+    # ---- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, encoder_only: bool = False, skip_decoder: bool = False) -> Dict[str, torch.Tensor]:
+        """x: b x 3 x H x W float32 on the GPU (maskformer.py:164).  `skip_decoder` is accepted and ignored,
+        as in the reference (:118-135)."""
+        if x.ndim != 4 or x.shape[1] != 3:
+            raise SmkError(f"expected b x 3 x H x W, got {tuple(x.shape)}")
+        _lib.require_cuda(x, "x")
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        cfg = self.cfg
+        hp, wp = -(-H // cfg.patch), -(-W // cfg.patch)
+        with torch.cuda.device(x.device):
+            handle = self._handle(B, H, W)
+            L = cfg.dec_layers if (self.return_intermediate and not encoder_only) else 1
+            ho, wo = hp * cfg.scale_factor, wp * cfg.scale_factor
+            if encoder_only:
+                check(lib().smk_model_forward(handle, ptr(x), B, H, W, 0, None, None, None, stream_ptr()), "smk_model_forward")
+                tok = torch.empty(B, hp * wp + 1, cfg.dim, dtype=torch.float32, device=x.device)
+                check(lib().smk_model_tap(handle, 1, ptr(tok), tok.numel(), stream_ptr()), "smk_model_tap")
+                # maskformer.py:183-189 (the reference `.view`s a b x D x hw tensor; here: b x h x w x D tokens)
+                return {"patch_tokens": tok[:, 1:, :].reshape(B, hp, wp, cfg.dim)}
+            mask_pred = torch.empty(B, L, cfg.n_queries, ho, wo, dtype=torch.float32, device=x.device)
+            objectness = torch.empty(B, L, cfg.n_queries, dtype=torch.float32, device=x.device)
+            features = torch.empty(B, cfg.dim, dtype=torch.float32, device=x.device)
+            check(lib().smk_model_forward(handle, ptr(x), B, H, W, 1 if L > 1 else 0, ptr(mask_pred), ptr(objectness),
+                                          ptr(features), stream_ptr()), "smk_model_forward")
+        if self.return_intermediate:
+            return {"objectness": objectness.unsqueeze(-1), "mask_pred": mask_pred, "features": features}
+        return {"objectness": objectness[:, 0].unsqueeze(-1), "mask_pred": mask_pred[:, 0], "features": features}
+
+    def tap(self, what: int, B: int, H: int, W: int) -> torch.Tensor:
+        """Stage-level parity hook: 1 final-LN tokens, 2 decoder queries [L,B,nq,D], 3 residual stream."""
+        cfg = self.cfg
+        handle = self._handles[(H, W)][0]
+        N = (-(-H // cfg.patch)) * (-(-W // cfg.patch)) + 1
+        shape = (cfg.dec_layers, B, cfg.n_queries, cfg.dim) if what == 2 else (B, N, cfg.dim)
+        out = torch.empty(shape, dtype=torch.float32, device=self._blob.device)
+        check(lib().smk_model_tap(handle, what, ptr(out), out.numel(), stream_ptr()), "smk_model_tap")
+        return out
+
+
+def get_model(arch: str, configs=None, **kwargs) -> SelfMaskB200:
+    """Mirror of `utils/misc.py:163-188 get_model(arch="maskformer", configs=Namespace)`."""
+    if arch != "maskformer":
+        raise SmkError(f"{arch} is not on the B200 path; only arch='maskformer'")
+    assert configs is not None
+    return SelfMaskB200(n_queries=configs.n_queries, n_decoder_layers=configs.n_decoder_layers,
+                        learnable_pixel_decoder=configs.learnable_pixel_decoder,
+                        lateral_connection=configs.lateral_connection,
+                        return_intermediate=configs.loss_every_decoder_layer, scale_factor=configs.scale_factor,
+                        abs_2d_pe_init=configs.abs_2d_pe_init, use_binary_classifier=configs.use_binary_classifier,
+                        arch=configs.arch, training_method=configs.training_method, patch_size=configs.patch_size, **kwargs)

@@ -1,0 +1,145 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the weight table matches the
+reference state_dict schema, and the host-side finalisation reproduces the reference's metric values from
+GPU-format records (emulated in numpy).  No compute call touches a GPU here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import selfmask_b200 as S
+from oracle import selfmask_oracle as O
+from selfmask_b200 import metrics as M
+from tests.helpers import numpy_record
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(nq=20):
+    return S.SmkConfig(patch=16, dim=384, depth=12, heads=6, mlp_dim=1536, n_queries=nq, dec_layers=6, dec_ffn=1536,
+                       scale_factor=4, pos_grid=14)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "selfmask_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(smk_[a-z0-9_]+)\s*\(", header))
+    from selfmask_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = S.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.smk_version() >= 100
+
+
+def test_weight_table_matches_reference_schema():
+    for nq in (10, 20):
+        cfg = O.make_config(n_queries=nq)
+        schema = O.state_dict_schema(cfg)
+        table = S.weight_table(_cfg(nq))
+        assert [n for n, _, _ in table] == [n for n, _, _ in schema]
+        assert len(table) == 267
+        for (n, off, numel), (_, shape, _) in zip(table, schema):
+            assert numel == int(np.prod(shape)), n
+            assert off % 64 == 0
+        offs = [o for _, o, _ in table]
+        assert offs == sorted(offs)
+        assert S.lib().smk_weights_numel(C.byref(_cfg(nq))) >= table[-1][1] + table[-1][2]
+
+
+def test_bad_config_is_rejected_with_message():
+    cfg = _cfg()
+    cfg.dim = 100
+    assert S.lib().smk_weight_count(C.byref(cfg)) < 0
+    assert b"dim" in S.lib().smk_last_error()
+
+
+def test_no_cpu_fallback():
+    model = S.SelfMaskB200(n_queries=20)
+    with pytest.raises(S.SmkError):
+        model.to("cpu")
+    with pytest.raises(S.SmkError):
+        model(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(S.SmkError):
+        S.compute_iou(torch.zeros(4, 4), torch.zeros(4, 4))
+
+
+def test_finalize_reproduces_reference_metrics(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    recs = [numpy_record(p, gt) for p, gt in zip(g["preds"], g["gts"])]
+    counts, sums = np.stack([r[0] for r in recs]), np.stack([r[1] for r in recs])
+    f = M.finalize(counts, sums)
+    # integer-derived metrics: bit-exact against the reference's own outputs
+    assert np.array_equal(f["iou"], g["iou"])
+    assert np.array_equal(f["f_score"], g["f_measure"])
+    assert np.array_equal(f["f_max"], g["f_max"])
+    assert np.array_equal(f["pixel_accuarcy"], g["pixel_acc"])
+    fg_above = M.counts_above_thresholds(counts[:, 0:256].astype(np.int64))
+    all_above = fg_above + M.counts_above_thresholds(counts[:, 256:512].astype(np.int64))
+    assert np.array_equal(M.f_from_counts(fg_above, all_above, counts[:, 514][:, None].astype(np.int64)), g["fmax_vec"])
+    # float reductions (different summation order than torch's float32 kernels): tolerance 2e-6 / 2e-5
+    np.testing.assert_allclose(f["mae"], g["mae"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(f["f_mean"], g["f_mean"], rtol=0, atol=1e-6)
+    a, b = f["s_measure"], g["s_measure"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=0, atol=2e-5)
+
+
+def test_histogram_counts_equal_direct_threshold_counts():
+    rng = np.random.default_rng(0)
+    thr = O.fmax_thresholds()
+    p = rng.random((37, 53), dtype=np.float32)
+    p.flat[:255] = thr                      # every threshold value itself must land in the right bin
+    gt = rng.random((37, 53)) > 0.6
+    counts, _ = numpy_record(p, gt)
+    f = O.f_measure_all(p, gt)
+    assert np.array_equal(M.counts_above_thresholds(counts[0:256].astype(np.int64)), f["tp_k"])
+    assert np.array_equal(M.counts_above_thresholds((counts[0:256] + counts[256:512]).astype(np.int64)), f["tpfp_k"])
+
+
+def test_running_mean_is_the_sequential_average_meter():
+    rng = np.random.default_rng(1)
+    vals = rng.random(1000).astype(np.float32)
+    m = S.AverageMeter()
+    for v in vals:
+        m.update(np.asarray(v), 1)           # 0-d float32 arrays, like `tensor.numpy()` in the reference
+    assert M.running_mean(vals) == float(m.avg)
+    vals64 = rng.random(100)
+    m = S.AverageMeter()
+    for v in vals64:
+        m.update(float(v), 1)
+    assert M.running_mean(vals64) == float(m.avg)
+
+
+def test_summarize_matches_reference_evaluator(golden_dir):
+    """Host half of the evaluator: records built (in numpy) from the oracle's full-resolution masks must give
+    the reference Evaluator's 14 averages."""
+    ref = json.load(open(os.path.join(golden_dir, "evaluator.json")))
+    cfg = O.make_config(n_queries=20)
+    sd = O.synth_state_dict(cfg, seed=0)
+    n, h, w = ref["n_img"], ref["h"], ref["w"]
+    xs = O.normalize_images(O.synth_images_u8(n, h, w, seed=ref["image_seed"]))
+    gts = O.synth_gt(n, h, w, seed=ref["gt_seed"], edge_every=ref["edge_every"])
+    counts, sums = np.zeros((n, 2, 528), np.int32), np.zeros((n, 2, 32))
+    with torch.no_grad():
+        out = O.model_forward(sd, xs, cfg)
+    full = O.upsample_bilinear(out["mask_pred"][:, -1].numpy(), 4)
+    ob = out["objectness"][:, -1, :, 0].numpy()
+    for i in range(n):
+        inter, union = O.iou_counts(full[i], np.broadcast_to(gts[i, 0], full[i].shape))
+        sel, ub = int(np.argmax(ob[i])), int(np.argmax(O.iou_from_counts(inter, union)))
+        for j, q in enumerate((sel, ub)):
+            counts[i, j], sums[i, j] = numpy_record(full[i, q], gts[i, 0])
+    res = S.summarize(counts, sums)
+    for k, v in ref["result"].items():
+        assert abs(res[k] - v) <= 2e-5 * max(1.0, abs(v)), (k, res[k], v)
+
+
+def test_shard_range_covers_everything():
+    for n, w in [(5019, 8), (7, 8), (256, 1), (0, 4), (9, 2)]:
+        spans = [S.shard_range(n, r, w) for r in range(w)]
+        covered = [i for a, b in spans for i in range(a, b)]
+        assert covered == list(range(n))
