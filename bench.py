@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the SelfMask inference + evaluation hot path (BASELINE.json metric: images/s at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU path (oracle port)
+
+A step = one pass of the hot path over one batch of synthetic images per GPU: model forward (encoder, decoder,
+mask head, objectness; all 6 decoder layers' masks, as the reference computes them) + the fused evaluation
+(x4 upsample, per-query IoU, query selection, IoU / F-measure / MAE / pixel-acc / S-measure reductions) and, at
+N > 1, the one collective on the path (all-reduce of the per-image count rows).  Workload = BASELINE.json
+configs[2]: nq 20, 224x224, batch 256 per GPU (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--nq", type=int, default=20)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="images in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [s.strip() for s in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_images_per_s(n_img, size, nq, batch, steps=1, warmup=0):
+    """The reference algorithm on the host cores: oracle port (torch CPU fp32 model + the reference's metric
+    semantics, per-image loop like evaluator.pyc).  Returns (images/s, cores, description)."""
+    from oracle import selfmask_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.make_config(n_queries=nq)
+    sd = O.synth_state_dict(cfg, seed=0)
+    xs = O.normalize_images(O.synth_images_u8(n_img, size, size, seed=1234))
+    gts = O.synth_gt(n_img, size, size, seed=4321)
+    batches = [(xs[i:i + batch], gts[i:i + batch]) for i in range(0, n_img, batch)]
+
+    def one_pass():
+        with torch.no_grad():
+            O.evaluate(lambda x: O.model_forward(sd, x, cfg), batches)
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = time.perf_counter() - t0
+    return n_img * steps / dt, cores, dt / steps
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the reference is Python/PyTorch and
+    cannot travel to the GPU box, so this is the oracle port; kind = "port").  Rank 0 only."""
+    if rank != 0:
+        return
+    sample = min(args.cpu_sample, 16)
+    ips, cores, sec = cpu_reference_images_per_s(sample, args.size, args.nq, batch=8, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": f"SelfMask nq{args.nq} {args.size}x{args.size} images/sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, sample_images_per_step=sample),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} images/step (batches of 8): oracle model forward + reference metric loop, torch CPU fp32, "
+                                       f"{cores} threads"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, **extra):
+    c = {"workload": f"SelfMask nq{args.nq} ViT-S/16 inference+metrics, batch {args.batch}/GPU at {args.size}x{args.size} "
+                     f"(BASELINE.json configs[2]), batch-sharded, count all-reduce",
+         "per_gpu_batch": args.batch, "image": [args.size, args.size], "n_queries": args.nq, "numeric_mode": args.mode,
+         "mask_layers": 6, "l2": "inputs larger than L2 (x is 154 MB/step at batch 256; activations ~1 GB)"}
+    c.update(extra)
+    return c
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    import selfmask_b200 as S
+    from selfmask_b200 import synthetic as Y
+    from selfmask_b200._lib import lib
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU reference arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+
+    model = S.SelfMaskB200(n_queries=args.nq, mode=args.mode, max_batch=B, return_intermediate=True).to(dev)
+    model.load_state_dict(Y.synth_state_dict(model.table(), seed=0))
+    uniq = min(B, 32)
+    x_host = Y.normalize_images(Y.synth_images_u8(uniq, args.size, args.size, seed=1234 + rank)).repeat((B + uniq - 1) // uniq, 1, 1, 1)[:B]
+    g_host = torch.from_numpy(Y.synth_gt(uniq, args.size, args.size, seed=4321 + rank)).repeat((B + uniq - 1) // uniq, 1, 1, 1)[:B]
+    x_host, g_host = x_host.contiguous().pin_memory(), g_host.contiguous().pin_memory()
+    x, g = x_host.to(dev), g_host.to(dev)
+    n_total = B * world
+    start_row = rank * B
+    rec = S.BatchRecords(B, args.nq, dev)
+
+    def step():
+        out = model(x)
+        S.eval_batch(out["mask_pred"], out["objectness"], g, up=4, out=rec)
+        if world > 1:
+            return S.allreduce_records(rec.m_counts, rec.m_sums, start_row, n_total)
+        return rec.m_counts, rec.m_sums
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib().smk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        counts, sums = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib().smk_launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_total * K / (ms / 1e3)
+    res = S.summarize(counts.cpu().numpy(), sums.cpu().numpy())        # metric of the last step (sanity; outside the timed region)
+
+    # ---- end to end through the public API: pinned host batches → Evaluator.__call__ → 14 averages ----------
+    def e2e_pass():
+        batches = ({"x": x_host, "m": g_host} for _ in range(K))
+        ev = S.Evaluator(network=model, dataset=batches)
+        r = ev(dataset_name="synthetic", dir_ckpt=None, batch_size=B, device=dev)
+        if world > 1:      # same collective as the step: every rank's per-image rows → identical averages everywhere
+            c = torch.from_numpy(ev.records["m_counts"]).to(dev)
+            s_ = torch.from_numpy(ev.records["m_sums"]).to(dev)
+            fc, fs = S.allreduce_records(c, s_, rank * B * K, world * B * K)
+            r = S.summarize(fc.cpu().numpy(), fs.cpu().numpy())
+        return r
+    e2e_pass()                                   # warm-up (allocator, page-locked paths)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_res = e2e_pass()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * K / float(dt.item())
+    h2d = x_host.numel() * 4 + g_host.numel()
+    d2h = B * 2 * (528 * 4 + 32 * 8) + B * 2 * 4 + B * args.nq * 2 * 4
+
+    # ---- per-stage device time with CUDA events on the launching stream (roofline block) -------------------------
+    pk = peaks()
+    lib().smk_prof_enable(1)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
+    ms_c, work_c, n_c = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
+    lib().smk_prof_read(ms_c, work_c, n_c)
+    lib().smk_prof_enable(0)
+    names = ["gemm_tcgen05", "attention_simt", "gemm_f32_simt", "layernorm", "eval_metrics", "mask_head", "other", "attention_tcgen05"]
+    tensor_cats = {0, 1, 2, 7}
+    stages, total_ms = {}, sum(ms_c)
+    for i, nme in enumerate(names):
+        if n_c[i] == 0:
+            continue
+        sec = ms_c[i] / 1e3
+        ach = work_c[i] / sec / (1e12 if i in tensor_cats else 1e9) if sec > 0 else 0.0
+        stages[nme] = {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] // prof_steps, "share": ms_c[i] / total_ms if total_ms else 0,
+                       "achieved": ach, "unit": "TFLOP/s" if i in tensor_cats else "GB/s",
+                       "frac_of_peak": ach / (pk["tensor"] if i in tensor_cats else pk["hbm"])}
+    dom = max(range(8), key=lambda i: ms_c[i])
+    dom_tensor = dom in tensor_cats
+    ach = stages[names[dom]]["achieved"]
+    roofline = {"kernel": names[dom], "bound": "tensor" if dom_tensor else "hbm", "achieved": ach,
+                "peak": pk["tensor"] if dom_tensor else pk["hbm"], "unit": "TFLOP/s" if dom_tensor else "GB/s",
+                "frac": ach / (pk["tensor"] if dom_tensor else pk["hbm"]), "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json ({pk['src']}; sustained bf16 for a kernel timed inside a long step)",
+                "avg_launch_ms": ms_c[dom] / max(n_c[dom], 1), "stages": stages}
+
+    if rank == 0:
+        line = {"metric": f"SelfMask nq{args.nq} {args.size}x{args.size} images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args),
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "sanity": {"iou": res["iou"], "f_max": res["f_max"], "e2e_iou": e2e_res["iou"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            ips, cores, sec = cpu_reference_images_per_s(args.cpu_sample, args.size, args.nq, batch=8)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} images (batches of 8) of the same workload: oracle model forward + the reference's "
+                                              f"per-image metric loop, torch CPU fp32, {cores} threads, {sec:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

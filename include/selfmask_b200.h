@@ -59,6 +59,15 @@ typedef struct {
 const char* smk_last_error(void);
 int smk_version(void);
 
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t smk_launch_count(void);
+/* per-category device timing with CUDA events on the launching stream.  enable: 1 start recording (resets), 0 stop.
+ * smk_prof_read synchronises the recorded events and fills ms[8], work[8] (algorithmic FLOPs or bytes), launches[8];
+ * categories: 0 tcgen05 GEMM, 1 CUDA-core attention, 2 fp32 GEMM, 3 LayerNorm, 4 evaluation, 5 mask head, 6 other,
+ * 7 tcgen05 attention. */
+int smk_prof_enable(int enable);
+int smk_prof_read(double* ms, double* work, int64_t* launches);
+
 /* ---- weights: one fp32 device blob in a canonical order --------------------------------------
  * The table maps the reference's state_dict keys (SURVEY.md §8b, 267 tensors) to blob offsets. */
 int smk_weight_count(const smk_config* cfg);
@@ -91,6 +100,8 @@ int smk_model_forward(smk_model* m, const float* x, int B, int H, int W, int all
  * what: 1 final-LN encoder tokens [B,N,D]; 2 decoder queries after the shared final norm [L,B,nq,D];
  *       3 residual stream after the last encoder block [B,N,D] */
 int smk_model_tap(smk_model* m, int what, float* out, int64_t out_numel, void* stream);
+/* when set (non-NULL), the next forward passes also store the pre-sigmoid mask logits, same shape as mask_pred */
+int smk_model_debug_logits(smk_model* m, float* logits);
 
 /* ---- evaluation ------------------------------------------------------------------------------ */
 #define SMK_QCOUNT_STRIDE 2      /* per query: intersection, union at threshold 0.5            */

@@ -30,6 +30,10 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "smk_last_error": (C.c_char_p, []),
     "smk_version": (_I, []),
+    "smk_launch_count": (_L, []),
+    "smk_prof_enable": (_I, [_I]),
+    "smk_prof_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)]),
+    "smk_model_debug_logits": (_I, [_P, _P]),
     "smk_weight_count": (_I, [C.POINTER(SmkConfig)]),
     "smk_weight_entry": (_I, [C.POINTER(SmkConfig), _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_L)]),
     "smk_weights_numel": (_L, [C.POINTER(SmkConfig)]),

@@ -19,12 +19,21 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def source_hash():
+    """Content hash of every source the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "selfmask_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "selfmask_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    stamp = LIB + ".srchash"
+    return not (os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash())
 
 
 def build(force=False, verbose=False):
@@ -55,6 +64,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    with open(LIB + ".srchash", "w") as f:
+        f.write(source_hash())
     return LIB
 
 

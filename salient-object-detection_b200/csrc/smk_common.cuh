@@ -10,6 +10,17 @@
 namespace smk {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional per-category device timing (CUDA events on the launching stream), for bench.py's roofline block.
+enum ProfCat { PROF_GEMM_TC = 0, PROF_ATTENTION = 1, PROF_GEMM_F32 = 2, PROF_LAYERNORM = 3, PROF_EVAL = 4, PROF_MASK_HEAD = 5,
+               PROF_OTHER = 6, PROF_ATTENTION_TC = 7, PROF_NUM = 8 };
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(int cat, double work, cudaStream_t s);   // work = algorithmic FLOPs (tensor categories) or bytes (memory ones)
+  ~ProfScope();
+};
 
 #define SMK_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -20,7 +31,11 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define SMK_CHECK_LAUNCH() SMK_CHECK_CUDA(cudaGetLastError())
+#define SMK_CHECK_LAUNCH()       \
+  do {                           \
+    smk::count_launch();         \
+    SMK_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 #define SMK_REQUIRE(cond, ...)      \
   do {                              \

@@ -209,7 +209,7 @@ mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, cons
         a.tpfp05 += p;
         const double dv = (double)v, dv2 = dv * dv, dg = t ? dv : 0.0;
         a.sp += dv;
-        a.sabs += t ? 1.0 - dv : dv;
+        a.sabs += fabs(dv - (t ? 1.0 : 0.0));
         if (t) { a.fg_p += dv; a.fg_p2 += dv2; }
         else   { const double w = 1.0 - dv; a.bg_q += w; a.bg_q2 += w * w; }
         const bool left = x < X;
@@ -327,10 +327,17 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
-  query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
+  {
+    // algorithmic bytes "as if materialised" (SURVEY.md §8d): every full-resolution mask pixel (fp32) + the GT plane
+    ProfScope prof(PROF_EVAL, (double)B * ((double)nq * H * W * 4.0 + (double)H * W), s);
+    query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
+  }
   SMK_CHECK_LAUNCH();
-  mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
-      mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
+  {
+    ProfScope prof(PROF_EVAL, (double)B * 2.0 * ((double)H * W * 4.0 + (double)H * W), s);
+    mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
+        mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }

@@ -247,7 +247,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmP
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM - 1) / TC_BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, p);
+  {
+    ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
+    gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, p);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }

@@ -19,6 +19,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- event profiler -----------------------------------------------------------------------------
+static const int kProfMaxEvents = 16384;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;      // start/end pairs
+static std::vector<int> g_prof_cat;
+static int g_prof_used = 0;
+static double g_prof_work[PROF_NUM];
+static long long g_prof_launches[PROF_NUM];
+
+ProfScope::ProfScope(int cat, double work, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  g_prof_work[cat] += work;
+  g_prof_launches[cat] += 1;
+  if (g_prof_used >= kProfMaxEvents) return;
+  if ((int)g_prof_ev.size() < 2 * (g_prof_used + 1)) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof_ev.push_back(a);
+    g_prof_ev.push_back(b);
+    g_prof_cat.push_back(cat);
+  }
+  slot = g_prof_used++;
+  g_prof_cat[slot] = cat;
+  cudaEventRecord(g_prof_ev[2 * slot], stream);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], stream);
+}
+
 // ---- weight table: reference state_dict keys → offsets into one fp32 blob -----------
 struct WEntry {
   std::string name;
@@ -101,6 +133,7 @@ struct smk_model {
   float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
   __nv_bfloat16* tokb;            // bf16 copy (bf16 mode)
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
+  float* debug_logits;
   int last_B;
 };
 
@@ -161,6 +194,26 @@ static int64_t find(const std::vector<WEntry>& t, const std::string& n) {
 
 extern "C" const char* smk_last_error(void) { return smk::g_err; }
 extern "C" int smk_version(void) { return 100; }
+extern "C" int64_t smk_launch_count(void) { return smk::g_launches; }
+extern "C" int smk_prof_enable(int enable) {
+  g_prof_on = enable != 0;
+  if (g_prof_on) {
+    g_prof_used = 0;
+    for (int i = 0; i < PROF_NUM; ++i) { g_prof_work[i] = 0; g_prof_launches[i] = 0; }
+  }
+  return SMK_OK;
+}
+extern "C" int smk_prof_read(double* ms, double* work, int64_t* launches) {
+  SMK_REQUIRE(ms && work && launches, "smk_prof_read: null pointer");
+  for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; work[i] = g_prof_work[i]; launches[i] = g_prof_launches[i]; }
+  for (int i = 0; i < g_prof_used; ++i) {
+    SMK_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+    float t = 0.f;
+    SMK_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    ms[g_prof_cat[i]] += t;
+  }
+  return SMK_OK;
+}
 
 extern "C" int smk_weight_count(const smk_config* cfg) {
   if (check_config(cfg) != SMK_OK) return SMK_ERR_INVALID;
@@ -222,6 +275,7 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
   }
   m->w = weights;
   m->last_B = 0;
+  m->debug_logits = nullptr;
   const auto t = weight_table(*cfg);
   auto f = [&](const std::string& n) { return find(t, n); };
   m->o_query = f("query_embed"); m->o_cls = f("encoder.cls_token"); m->o_pos = f("encoder.pos_embed");
@@ -371,7 +425,7 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
   // ---- heads ----------------------------------------------------------------------------------------
   const int Lout = all_layers ? L : 1, layer0 = all_layers ? 0 : L - 1;
   if (mask_pred)
-    SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, nullptr, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
+    SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
   if (objectness) {
     const float* qsrc = m->queries + (int64_t)layer0 * R * D;
     const int rows = Lout * R;
@@ -381,6 +435,12 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
     SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));
   }
   if (features) SMK_PROPAGATE(query_mean(m->queries + (int64_t)(L - 1) * R * D, features, B, nq, D, s));
+  return SMK_OK;
+}
+
+extern "C" int smk_model_debug_logits(smk_model* m, float* logits) {
+  SMK_REQUIRE(m != nullptr, "smk_model_debug_logits: null model");
+  m->debug_logits = logits;
   return SMK_OK;
 }
 

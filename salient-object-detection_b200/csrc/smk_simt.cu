@@ -76,6 +76,7 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
   case c: layernorm_kernel<TOut, c><<<grid, 256, 0, s>>>(x, res, gamma, beta, y, y32, sum_out, rows, D, eps); break;
@@ -163,7 +164,10 @@ int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
   SMK_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_f32: operands must be 16-byte aligned");
   if (M == 0 || N == 0) return SMK_OK;
   dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
-  gemm_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi);
+  {
+    ProfScope prof(PROF_GEMM_F32, 2.0 * M * N * K, s);
+    gemm_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -255,7 +259,10 @@ int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, 
   SMK_REQUIRE(Lq > 0 && Lk > 0 && batch <= 65535 && heads <= 65535, "attention: bad sizes");
   if (batch == 0) return SMK_OK;
   dim3 grid((Lq + ATT_ROWS - 1) / ATT_ROWS, heads, batch);
-  attention_kernel<T, TK><<<grid, 128, 0, s>>>(q, k, v, o, Lq, Lk, q_bs, ldq, k_bs, ldk, v_bs, ldv, o_bs, ldo, scale);
+  {
+    ProfScope prof(PROF_ATTENTION, 4.0 * Lq * Lk * dh * heads * batch, s);
+    attention_kernel<T, TK><<<grid, 128, 0, s>>>(q, k, v, o, Lq, Lk, q_bs, ldq, k_bs, ldk, v_bs, ldv, o_bs, ldo, scale);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -291,7 +298,10 @@ template <typename T>
 int im2col(const float* x, T* cols, int B, int H, int W, int P, int hp, int wp, cudaStream_t s) {
   if (B == 0) return SMK_OK;
   SMK_REQUIRE(B <= 65535, "im2col: batch too large");
-  im2col_kernel<T><<<dim3(hp * wp, B), 256, 0, s>>>(x, cols, H, W, P, hp, wp);
+  {
+    ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * (4.0 + sizeof(T)), s);
+    im2col_kernel<T><<<dim3(hp * wp, B), 256, 0, s>>>(x, cols, H, W, P, hp, wp);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -310,7 +320,10 @@ assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restr
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
                     cudaStream_t s) {
   if (B == 0) return SMK_OK;
-  assemble_tokens_kernel<<<dim3(cls_only ? 1 : hw + 1, B), 128, 0, s>>>(patch_out, cls, pos, tokens, hw, D);
+  {
+    ProfScope prof(PROF_OTHER, (double)B * (cls_only ? 1 : hw + 1) * D * 8.0, s);
+    assemble_tokens_kernel<<<dim3(cls_only ? 1 : hw + 1, B), 128, 0, s>>>(patch_out, cls, pos, tokens, hw, D);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -326,7 +339,10 @@ __global__ void add_rows_kernel(const float* __restrict__ a, const float* __rest
 }
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s) {
   if (rows == 0) return SMK_OK;
-  add_rows_kernel<<<(unsigned)((rows * D + 255) / 256), 256, 0, s>>>(a, pos, out, rows, D, period);
+  {
+    ProfScope prof(PROF_OTHER, (double)rows * D * 8.0, s);
+    add_rows_kernel<<<(unsigned)((rows * D + 255) / 256), 256, 0, s>>>(a, pos, out, rows, D, period);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -347,7 +363,10 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
   if (n == 0) return SMK_OK;
   SMK_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 8) == 0, "cast_bf16: misaligned");
-  cast_bf16_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(in, out, n);
+  {
+    ProfScope prof(PROF_OTHER, (double)n * 6.0, s);
+    cast_bf16_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(in, out, n);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -412,7 +431,11 @@ int mask_head(const float* queries, const float* tokens, float* mask_pred, float
   const size_t smem = ((size_t)nq * D + (size_t)nq * hp * wp) * sizeof(float);
   SMK_REQUIRE(smem <= 200 * 1024, "mask_head: %zu bytes of shared memory needed", smem);
   if (smem > 48 * 1024) SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mask_head_kernel<<<dim3(L, B), 256, smem, s>>>(queries, tokens, mask_pred, logits_out, B, nq, D, hp, wp, sf, layer0);
+  {
+    // algorithmic bytes: read tokens + queries, write the [nq, hp*sf, wp*sf] probability planes
+    ProfScope prof(PROF_MASK_HEAD, (double)B * L * ((double)(hp * wp + nq) * D + (double)nq * hp * sf * wp * sf) * 4.0, s);
+    mask_head_kernel<<<dim3(L, B), 256, smem, s>>>(queries, tokens, mask_pred, logits_out, B, nq, D, hp, wp, sf, layer0);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -431,7 +454,10 @@ rowdot_sigmoid_kernel(const float* __restrict__ h, const float* __restrict__ w, 
 }
 int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s) {
   if (rows == 0) return SMK_OK;
-  rowdot_sigmoid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h, w, bias, out, rows, D);
+  {
+    ProfScope prof(PROF_OTHER, (double)rows * D * 4.0, s);
+    rowdot_sigmoid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h, w, bias, out, rows, D);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -448,7 +474,10 @@ __global__ void permute_lb_kernel(const float* __restrict__ in, float* __restric
 int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s) {
   const int64_t tot = (int64_t)L * B * n;
   if (tot == 0) return SMK_OK;
-  permute_lb_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(in, out, L, B, n);
+  {
+    ProfScope prof(PROF_OTHER, (double)tot * 8.0, s);
+    permute_lb_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(in, out, L, B, n);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
@@ -464,7 +493,10 @@ __global__ void query_mean_kernel(const float* __restrict__ qlast, float* __rest
 }
 int query_mean(const float* qlast, float* out, int B, int nq, int D, cudaStream_t s) {
   if (B == 0) return SMK_OK;
-  query_mean_kernel<<<B, 128, 0, s>>>(qlast, out, nq, D);
+  {
+    ProfScope prof(PROF_OTHER, (double)B * (nq + 1) * D * 4.0, s);
+    query_mean_kernel<<<B, 128, 0, s>>>(qlast, out, nq, D);
+  }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }

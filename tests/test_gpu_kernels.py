@@ -1,0 +1,191 @@
+"""GPU parity tests of single kernels through the C-ABI: CUDA path vs the CPU oracle / golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import selfmask_b200 as S  # noqa: E402
+from oracle import selfmask_oracle as O  # noqa: E402
+from selfmask_b200 import metrics as M  # noqa: E402
+from selfmask_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
+from tests.gpu_util import DEV, dev, gemm_bf16, gemm_f32  # noqa: E402
+from tests.helpers import numpy_record  # noqa: E402
+
+
+def test_upsample_bit_exact_with_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "upsample.npz"))
+    for src, ref in (("probs", "probs4"), ("odd", "odd4")):
+        x = dev(g[src][0])
+        n, h, w = x.shape
+        out = torch.empty(n, h * 4, w * 4, dtype=torch.float32, device=DEV)
+        check(lib().smk_upsample_bilinear(ptr(x), ptr(out), n, h, w, 4, h * 4, w * 4, stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), g[ref][0]), src
+    # crop [..., :H, :W] (evaluator.pyc@L211) and scale 1 (identity)
+    x = dev(g["odd"][0])
+    out = torch.empty(2, 200, 180, dtype=torch.float32, device=DEV)
+    check(lib().smk_upsample_bilinear(ptr(x), ptr(out), 2, 52, 48, 4, 200, 180, stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), g["odd4"][0][:, :200, :180])
+    out1 = torch.empty_like(x)
+    check(lib().smk_upsample_bilinear(ptr(x), ptr(out1), 2, 52, 48, 1, 52, 48, stream_ptr()))
+    assert torch.equal(out1, x)
+
+
+def test_mask_metrics_counts_bit_exact_and_values_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    preds, gts = g["preds"], g["gts"]
+    n, H, W = preds.shape
+    counts = torch.empty(n, 528, dtype=torch.int32, device=DEV)
+    sums = torch.empty(n, 32, dtype=torch.float64, device=DEV)
+    check(lib().smk_mask_metrics(ptr(dev(preds)), ptr(dev(gts.astype(np.uint8))), n, H, W, ptr(counts), ptr(sums), stream_ptr()))
+    counts, sums = counts.cpu().numpy(), sums.cpu().numpy()
+    for i in range(n):
+        c_ref, s_ref = numpy_record(preds[i], gts[i])
+        assert np.array_equal(counts[i, :515], c_ref[:515]), i           # histograms, counts@0.5, sum(gt): bit-exact
+        assert np.array_equal(counts[i, 517:520], c_ref[517:520]), i     # centroid, pixel count
+        assert abs(float(sums[i, 2]) - float(s_ref[2])) <= 1.2e-7, i      # tau = 2*mean(p) (fp32)
+        if sums[i, 2] == s_ref[2]:
+            assert np.array_equal(counts[i, 515:517], c_ref[515:517]), i
+        np.testing.assert_allclose(sums[i], s_ref, rtol=1e-12, atol=1e-9)
+    f = M.finalize(counts, sums)
+    assert np.array_equal(f["iou"], g["iou"])
+    assert np.array_equal(f["f_score"], g["f_measure"])
+    assert np.array_equal(f["f_max"], g["f_max"])
+    assert np.array_equal(f["pixel_accuarcy"], g["pixel_acc"])
+    np.testing.assert_allclose(f["mae"], g["mae"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(f["f_mean"], g["f_mean"], rtol=0, atol=1e-6)
+    a, b = f["s_measure"], g["s_measure"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=0, atol=2e-5)
+
+
+def test_metric_callables_are_drop_in(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for i in (0, 3, 7, 8):
+        p, gt = dev(g["preds"][i]), dev(g["gts"][i].astype(np.int64))
+        assert S.compute_iou(p, gt).numpy() == g["iou"][i]
+        f = S.FMeasure()(p, gt)
+        assert f["f_measure"].numpy() == g["f_measure"][i] and f["f_max"].numpy() == g["f_max"][i]
+        assert abs(float(f["f_mean"]) - float(g["f_mean"][i])) <= 1e-6
+        assert abs(float(S.compute_mae(p, gt)) - float(g["mae"][i])) <= 2e-6
+        assert S.compute_pixel_accuracy(p, gt).numpy() == g["pixel_acc"][i]
+        assert abs(S.SMeasure()(pred_mask=p, gt_mask=gt.float()) - float(g["s_measure"][i])) <= 2e-5
+
+
+@pytest.mark.parametrize("B,nq,hp,wp,H,W", [(3, 20, 56, 56, 224, 224), (2, 10, 56, 56, 224, 224), (1, 20, 52, 48, 200, 180),
+                                            (1, 20, 96, 96, 384, 384), (1, 3, 5, 7, 20, 28)])
+def test_eval_batch_counts_bit_exact_vs_oracle(B, nq, hp, wp, H, W):
+    rng = np.random.default_rng(B * 1000 + nq + hp)
+    yy, xx = np.mgrid[0:hp, 0:wp].astype(np.float32)
+    logits = rng.normal(0, 4, (B, nq, hp, wp)).astype(np.float32)
+    for b in range(B):
+        for q in range(nq):
+            logits[b, q] += 12 * np.exp(-((yy - rng.uniform(0, hp)) ** 2 + (xx - rng.uniform(0, wp)) ** 2) / (2 * rng.uniform(3, 15) ** 2)) - 5
+    probs = (1 / (1 + np.exp(-logits))).astype(np.float32)
+    obj = rng.random((B, nq)).astype(np.float32)
+    gt = O.synth_gt(B, H, W, seed=B + nq, edge_every=2 if B > 1 else 0)
+    rec = S.eval_batch(dev(probs), dev(obj), dev(gt), up=4)
+    torch.cuda.synchronize()
+    qc, idx = rec.q_counts.cpu().numpy(), rec.idx.cpu().numpy()
+    mc, ms = rec.m_counts.cpu().numpy(), rec.m_sums.cpu().numpy()
+    full = O.upsample_bilinear(probs, 4)[..., :H, :W]
+    for b in range(B):
+        inter, union = O.iou_counts(full[b], np.broadcast_to(gt[b, 0], full[b].shape))
+        assert np.array_equal(qc[b, :, 0], inter) and np.array_equal(qc[b, :, 1], union), b
+        sel, ub = int(np.argmax(obj[b])), int(np.argmax(O.iou_from_counts(inter, union)))
+        assert tuple(idx[b]) == (sel, ub), (b, idx[b], sel, ub)
+        for j, q in enumerate((sel, ub)):
+            c_ref, s_ref = numpy_record(full[b, q], gt[b, 0])
+            assert np.array_equal(mc[b, j, :515], c_ref[:515]), (b, j)
+            assert np.array_equal(mc[b, j, 517:520], c_ref[517:520]), (b, j)
+            assert mc[b, j, 520] == q
+            if ms[b, j, 2] == s_ref[2]:
+                assert np.array_equal(mc[b, j, 515:517], c_ref[515:517]), (b, j)
+            np.testing.assert_allclose(ms[b, j], s_ref, rtol=1e-12, atol=1e-9)
+    # and the metric values against the oracle's direct (non-histogram) restatement
+    vals = M.finalize(mc, ms)
+    for b in range(B):
+        for j in range(2):
+            m = O.image_metrics(full[b, int(mc[b, j, 520])], gt[b, 0])
+            for k in ("iou", "f_score", "f_max", "pixel_accuarcy"):
+                assert vals[k][b, j] == m[k], (k, b, j)
+            assert abs(float(vals["mae"][b, j]) - float(m["mae"])) <= 2e-6
+            sa, sb = float(vals["s_measure"][b, j]), m["s_measure"]
+            assert (np.isnan(sa) and np.isnan(sb)) or abs(sa - sb) <= 2e-5
+
+
+def test_layernorm_matches_torch():
+    torch.manual_seed(0)
+    x = torch.randn(1000, 384, device=DEV) * 3 + 1
+    g, b = torch.randn(384, device=DEV), torch.randn(384, device=DEV)
+    ref = torch.nn.functional.layer_norm(x, (384,), g, b, 1e-6)
+    y = torch.empty_like(x)
+    check(lib().smk_layernorm(ptr(x), ptr(g), ptr(b), ptr(y), 1000, 384, 1e-6, 0, stream_ptr()))
+    assert (y - ref).abs().max().item() <= 2e-5
+    yb = torch.empty(1000, 384, dtype=torch.bfloat16, device=DEV)
+    check(lib().smk_layernorm(ptr(x), ptr(g), ptr(b), ptr(yb), 1000, 384, 1e-6, 1, stream_ptr()))
+    assert torch.equal(yb, y.to(torch.bfloat16)) or (yb.float() - ref).abs().max().item() <= 0.05
+
+
+@pytest.mark.parametrize("M_,N,K,epi", [(197, 384, 384, 0), (1000, 1152, 384, 0), (333, 1536, 384, 1), (130, 384, 1536, 4),
+                                        (64, 128, 768, 2), (5, 384, 384, 0)])
+def test_gemm_f32_matches_torch(M_, N, K, epi):
+    torch.manual_seed(1)
+    A, W, bias = torch.randn(M_, K, device=DEV), torch.randn(N, K, device=DEV) * 0.05, torch.randn(N, device=DEV)
+    C0 = torch.randn(M_, N, device=DEV)
+    ref = (A.double() @ W.double().t() + bias.double())
+    if epi & 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi & 2:
+        ref = torch.relu(ref)
+    if epi & 4:
+        ref = ref + C0.double()
+    out = gemm_f32(A, W, bias, epi, C_init=C0 if epi & 4 else None)
+    assert (out.double() - ref).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("M_,N,K,epi,f32", [(128, 128, 64, 0, True), (128, 128, 384, 0, True), (197, 384, 384, 0, False),
+                                            (1000, 1152, 384, 0, False), (333, 1536, 384, 1, False), (130, 384, 1536, 4, True),
+                                            (50432, 1536, 384, 1, False), (50432, 384, 1536, 4, True), (40000, 4608, 384, 0, False),
+                                            (64, 256, 768, 2, True)])
+def test_gemm_bf16_tcgen05_matches_torch(M_, N, K, epi, f32):
+    torch.manual_seed(2)
+    A = torch.randn(M_, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    C0 = torch.randn(M_, N, device=DEV) if epi & 4 else None
+    out = gemm_bf16(A, W, bias, epi, out_f32=f32, C_init=C0)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias          # fp32 accumulate of the same bf16 operands
+    if epi & 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi & 2:
+        ref = torch.relu(ref)
+    if epi & 4:
+        ref = ref + C0
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-3 if f32 else 0.02 * max(1.0, ref.abs().max().item())     # bf16 output rounding: 2^-8 relative
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("is_bf16", [False, True])
+@pytest.mark.parametrize("Lq,Lk", [(197, 197), (20, 196), (20, 20), (577, 577)])
+def test_attention_matches_torch(Lq, Lk, is_bf16):
+    torch.manual_seed(3)
+    B, H, dh = 2, 6, 64
+    dt = torch.bfloat16 if is_bf16 else torch.float32
+    q = torch.randn(B, Lq, H * dh, device=DEV).to(dt)
+    k = torch.randn(B, Lk, H * dh, device=DEV).to(dt)
+    v = torch.randn(B, Lk, H * dh, device=DEV).to(dt)
+    o = torch.empty(B, Lq, H * dh, device=DEV, dtype=dt)
+    check(lib().smk_attention(ptr(q), ptr(k), ptr(v), ptr(o), B, H, dh, Lq, Lk, Lq * H * dh, H * dh, Lk * H * dh, H * dh,
+                              Lk * H * dh, H * dh, Lq * H * dh, H * dh, 0.125, 1 if is_bf16 else 0, stream_ptr()))
+    qh = q.float().view(B, Lq, H, dh).transpose(1, 2)
+    kh = k.float().view(B, Lk, H, dh).transpose(1, 2)
+    vh = v.float().view(B, Lk, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B, Lq, H * dh)
+    assert (o.float() - ref).abs().max().item() <= (0.02 if is_bf16 else 2e-5)

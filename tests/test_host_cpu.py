@@ -143,3 +143,13 @@ def test_shard_range_covers_everything():
         spans = [S.shard_range(n, r, w) for r in range(w)]
         covered = [i for a, b in spans for i in range(a, b)]
         assert covered == list(range(n))
+
+
+def test_package_synthetic_generators_match_the_oracle():
+    from selfmask_b200 import synthetic as Y
+    cfg = O.make_config(n_queries=20)
+    a, b = O.synth_state_dict(cfg, seed=3), Y.synth_state_dict(S.weight_table(_cfg(20)), seed=3)
+    assert list(a) == list(b)
+    assert all(a[k].shape == b[k].shape and torch.equal(a[k], b[k]) for k in a)
+    assert np.array_equal(O.synth_images_u8(2, 64, 48, 5), Y.synth_images_u8(2, 64, 48, 5))
+    assert np.array_equal(O.synth_gt(7, 64, 48, 6, edge_every=3), Y.synth_gt(7, 64, 48, 6, edge_every=3))
