@@ -151,6 +151,9 @@ int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y
 int smk_attention(const void* q, const void* k, const void* v, void* o, int batch, int heads, int dh, int Lq, int Lk,
                   int64_t q_bstride, int64_t ldq, int64_t k_bstride, int64_t ldk, int64_t v_bstride, int64_t ldv,
                   int64_t o_bstride, int64_t ldo, float scale, int is_bf16, void* stream);
+/* tcgen05 fused self-attention on the fused-QKV layout: qkv [B*N, 3*heads*64] bf16 (q|k|v), out [B*N, heads*64] bf16;
+ * N <= 256 tokens per image (one key tile). */
+int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
 /* fp32 → bf16 (round to nearest even) */
 int smk_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 

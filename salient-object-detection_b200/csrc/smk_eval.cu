@@ -323,7 +323,7 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
   cudaStream_t s = (cudaStream_t)stream;
   const size_t plane_bytes = (size_t)hp * wp * sizeof(float);
   SMK_REQUIRE(plane_bytes <= 160 * 1024, "smk_eval_batch: mask plane %dx%d does not fit shared memory", hp, wp);
-  if (plane_bytes > 48 * 1024) {
+  if (plane_bytes > 24 * 1024) {   // static (17.5 KB) + dynamic shared memory beyond the 48 KB default needs the opt-in
     SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }

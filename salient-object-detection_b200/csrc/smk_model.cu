@@ -357,8 +357,12 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
       const BlockW& b = m->blk[i];
       SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
-      SMK_PROPAGATE((attention<__nv_bfloat16, __nv_bfloat16>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D,
-                                                             (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
+      if (N <= 256) {
+        SMK_PROPAGATE(attention_tc(QKV, AO, B, N, c.heads, scale, s));
+      } else {   // longer sequences (384x384 → 577 tokens): CUDA-core online-softmax kernel
+        SMK_PROPAGATE((attention<__nv_bfloat16, __nv_bfloat16>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D,
+                                                               (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
+      }
       SMK_PROPAGATE(gemm_bf16_tc(AO, D, wb + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
       SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, 0, 0, nullptr, s));

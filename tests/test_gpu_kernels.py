@@ -41,7 +41,8 @@ def test_mask_metrics_counts_bit_exact_and_values_match_reference(golden_dir):
     n, H, W = preds.shape
     counts = torch.empty(n, 528, dtype=torch.int32, device=DEV)
     sums = torch.empty(n, 32, dtype=torch.float64, device=DEV)
-    check(lib().smk_mask_metrics(ptr(dev(preds)), ptr(dev(gts.astype(np.uint8))), n, H, W, ptr(counts), ptr(sums), stream_ptr()))
+    d_pred, d_gt = dev(preds), dev(gts.astype(np.uint8))     # keep references: the call is asynchronous
+    check(lib().smk_mask_metrics(ptr(d_pred), ptr(d_gt), n, H, W, ptr(counts), ptr(sums), stream_ptr()))
     counts, sums = counts.cpu().numpy(), sums.cpu().numpy()
     for i in range(n):
         c_ref, s_ref = numpy_record(preds[i], gts[i])
@@ -189,3 +190,18 @@ def test_attention_matches_torch(Lq, Lk, is_bf16):
     vh = v.float().view(B, Lk, H, dh).transpose(1, 2)
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B, Lq, H * dh)
     assert (o.float() - ref).abs().max().item() <= (0.02 if is_bf16 else 2e-5)
+
+
+@pytest.mark.parametrize("B,N", [(1, 197), (3, 197), (2, 64), (2, 256), (5, 130), (64, 197)])
+def test_attention_tcgen05_matches_torch(B, N):
+    torch.manual_seed(4)
+    H, dh = 6, 64
+    D = H * dh
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 1.5).to(torch.bfloat16)
+    out = torch.zeros(B * N, D, device=DEV, dtype=torch.bfloat16)
+    check(lib().smk_attention_tc(ptr(qkv), ptr(out), B, N, H, 0.125, stream_ptr()), "smk_attention_tc")
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, N, H, dh).transpose(1, 2) for t in qkv.view(B, N, 3 * D).split(D, dim=-1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, D)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.03, err

@@ -26,9 +26,15 @@ REPORT = {}
 
 
 def _report(key, value):
-    REPORT[key] = value
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+    path = os.path.join(ROOT, "gpurun_out", "parity_report.json")
+    if not REPORT and os.path.exists(path):
+        try:
+            REPORT.update(json.load(open(path)))
+        except Exception:
+            pass
+    REPORT[key] = value
+    with open(path, "w") as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
