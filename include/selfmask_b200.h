@@ -154,6 +154,14 @@ int smk_attention(const void* q, const void* k, const void* v, void* o, int batc
 /* tcgen05 fused self-attention on the fused-QKV layout: qkv [B*N, 3*heads*64] bf16 (q|k|v), out [B*N, heads*64] bf16;
  * N <= 256 tokens per image (one key tile). */
 int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
+/* general form: q [B*Lq, ldq], k / v [kv_total_rows, ld] bf16 (head h at columns [h*64, h*64+64) of each pointer); image b's
+ * queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0; out [B*Lq, ldo] fp32 (out_f32) or bf16. */
+int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_total_rows,
+                             int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk, int heads,
+                             float scale, void* stream);
+/* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
+ * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */
+int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream);
 /* fp32 → bf16 (round to nearest even) */
 int smk_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 

@@ -1,7 +1,9 @@
 // bf16 tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T (+bias, GELU/ReLU, +residual)
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread) and
-// TMEM owner, warps 2-5 = epilogue (TMEM → registers → global).  Operands are staged by TMA into a
+// TMEM owner, warps 2-9 = epilogue (two warpgroups, each owning half of the tile's columns; TMEM → registers →
+// global).  With K = 384 the MMA time of a tile is only 12 cycles per accumulator column, so the epilogue must
+// stay under ~12 instructions per output element: hence 8 epilogue warps and the MUFU-light GELU below.  Operands are staged by TMA into a
 // kStages-deep ring of 128-byte-swizzled shared-memory tiles; fp32 accumulators live in TMEM and are
 // double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Serves: patch-embed (vision_transformer.py:184-188), qkv / proj / fc1 / fc2 (:113,131,88-94), the
@@ -14,15 +16,30 @@ namespace smk {
 
 using namespace tc;
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+
+// exact-GELU (vision_transformer.py:78 nn.GELU, erf form) evaluated as  0.5x(1 + erf(|x|/√2)·sign x)  with
+// erf(z) = 1 − 2^(−p(z)), p a degree-5 fit on [0,4]: max abs error 1.9e-5 = 0.06 bf16 ulp of the result
+// (the bf16-mode output is rounded to bf16 right after).  10 FMA-pipe instructions + one MUFU.EX2; the fp32
+// validation mode keeps erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.0f);
+  float p = fmaf(z, 0.00164591f, -0.02243328f);
+  p = fmaf(z, p, 0.13533017f);
+  p = fmaf(z, p, 0.92796782f);
+  p = fmaf(z, p, 1.62590536f);
+  const float t = exp2f(-(z * p));               // 1 − erf(z)
+  const float hx = 0.5f * x, ax = fabsf(hx);
+  return fmaf(-ax, t, hx + ax);                  // hx + |hx|·erf(z)
+}
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr int kStages = (BN == 128) ? 6 : (BN == 192 ? 5 : 4);
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;                       // two accumulator buffers (256 or 512: powers of two)
+  static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -58,7 +75,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -112,8 +129,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: warps 2..9; lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
     const int quarter = warp & 3;
+    const int col_half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -130,7 +148,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -148,7 +166,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (p.epi & SMK_EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
           }
           if (p.epi & SMK_EPI_RELU) {
 #pragma unroll
@@ -263,12 +281,14 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
   if (M == 0) return SMK_OK;
-  const int BN = (N % 256 == 0 && (int64_t)(N / 256) * ((M + 127) / 128) >= 2 * num_sms()) ? 256 : 128;
+  // wider tiles relieve shared-memory bandwidth (A+B bytes per MMA cycle: 128 B at BN=128, 107 at 192, 96 at 256)
+  const int64_t mb = (M + 127) / 128;
+  const int BN = (N % 256 == 0 && (N / 256) * mb >= num_sms()) ? 256 : ((N % 192 == 0 && (N / 192) * mb >= num_sms()) ? 192 : 128);
   CUtensorMap ta, tb;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)BN));
   TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos};
-  return BN == 256 ? launch_tc<256>(ta, tb, p, s) : launch_tc<128>(ta, tb, p, s);
+  return BN == 256 ? launch_tc<256>(ta, tb, p, s) : (BN == 192 ? launch_tc<192>(ta, tb, p, s) : launch_tc<128>(ta, tb, p, s));
 }
 
 }  // namespace smk

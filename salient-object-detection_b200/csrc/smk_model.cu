@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -112,6 +113,8 @@ static int check_config(const smk_config* c) {
 
 struct BlockW { int64_t n1w, n1b, qkvw, qkvb, pw, pb, n2w, n2b, f1w, f1b, f2w, f2b; };
 struct DecW { int64_t saw, sab, saow, saob, caw, cab, caow, caob, l1w, l1b, l2w, l2b, n1w, n1b, n2w, n2b, n3w, n3b; };
+// bf16x3-split copies ([N, 3K] = [hi | lo | hi]) of the decoder-tail weights (bf16 mode)
+struct Dec3 { __nv_bfloat16 *saw, *saow, *caqw, *caow, *l1w, *l2w; };
 
 }  // namespace smk
 
@@ -133,6 +136,8 @@ struct smk_model {
   float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
   __nv_bfloat16* tokb;            // bf16 copy (bf16 mode)
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
+  std::vector<Dec3> dec3;         // bf16 mode only
+  __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *dqk_b, *dv_b, *cq_b;
   float* debug_logits;
   int last_B;
 };
@@ -182,6 +187,26 @@ static void plan(smk_model& m, Plan& pl) {
   m.oh1 = pl.take<float>(L * R * D);
   m.oh2 = pl.take<float>(L * R * D);
   m.otmp = pl.take<float>(L * R);
+  if (bf) {
+    const int64_t FD = c.dec_ffn;
+    m.dec3.resize(L);
+    for (int l = 0; l < L; ++l) {
+      m.dec3[l].saw = pl.take<__nv_bfloat16>(3 * D * 3 * D);
+      m.dec3[l].saow = pl.take<__nv_bfloat16>(D * 3 * D);
+      m.dec3[l].caqw = pl.take<__nv_bfloat16>(D * 3 * D);
+      m.dec3[l].caow = pl.take<__nv_bfloat16>(D * 3 * D);
+      m.dec3[l].l1w = pl.take<__nv_bfloat16>(FD * 3 * D);
+      m.dec3[l].l2w = pl.take<__nv_bfloat16>(D * 3 * FD);
+    }
+    m.f0w3 = pl.take<__nv_bfloat16>(D * 3 * D);
+    m.f1w3 = pl.take<__nv_bfloat16>(D * 3 * D);
+    const int64_t a3 = std::max(R * 3 * FD, L * R * 3 * D);
+    m.a3a = pl.take<__nv_bfloat16>(a3);
+    m.a3b = pl.take<__nv_bfloat16>(a3);
+    m.dqk_b = pl.take<__nv_bfloat16>(R * 2 * D);
+    m.dv_b = pl.take<__nv_bfloat16>(R * D);
+    m.cq_b = pl.take<__nv_bfloat16>(R * D);
+  }
 }
 
 static int64_t find(const std::vector<WEntry>& t, const std::string& n) {
@@ -321,6 +346,19 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
   if (mode == SMK_MODE_BF16) {
     if ((st = cast_bf16(weights, m->wb, table_numel(t), s)) != SMK_OK) return fail(st);
     if ((st = cast_bf16(m->kvw32, m->kvwb, (int64_t)cfg->dec_layers * 2 * D * D, s)) != SMK_OK) return fail(st);
+    const int FD = cfg->dec_ffn;
+    for (int l = 0; l < cfg->dec_layers; ++l) {
+      const DecW& d = m->dec[l];
+      const Dec3& d3 = m->dec3[l];
+      if ((st = split3_weight(weights + d.saw, d3.saw, 3 * D, (int)D, s)) != SMK_OK) return fail(st);
+      if ((st = split3_weight(weights + d.saow, d3.saow, D, (int)D, s)) != SMK_OK) return fail(st);
+      if ((st = split3_weight(weights + d.caw, d3.caqw, D, (int)D, s)) != SMK_OK) return fail(st);   // q rows only
+      if ((st = split3_weight(weights + d.caow, d3.caow, D, (int)D, s)) != SMK_OK) return fail(st);
+      if ((st = split3_weight(weights + d.l1w, d3.l1w, FD, (int)D, s)) != SMK_OK) return fail(st);
+      if ((st = split3_weight(weights + d.l2w, d3.l2w, D, FD, s)) != SMK_OK) return fail(st);
+    }
+    if ((st = split3_weight(weights + m->o_f0w, m->f0w3, D, (int)D, s)) != SMK_OK) return fail(st);
+    if ((st = split3_weight(weights + m->o_f1w, m->f1w3, D, (int)D, s)) != SMK_OK) return fail(st);
   }
   *out = m;
   return SMK_OK;
@@ -390,10 +428,47 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
     SMK_PROPAGATE(gemm_f32(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
   }
 
-  // ---- decoder (transformer_decoder.py:260-297, post-norm; fp32 on CUDA cores in both modes) ------------
+  // ---- decoder (transformer_decoder.py:260-297, post-norm) ---------------------------------------------------
   const float* qpos = w + m->o_query;
   const int64_t ldkv = (int64_t)L * 2 * D;
+  const int FD = c.dec_ffn;
   SMK_CHECK_CUDA(cudaMemsetAsync(m->tgt, 0, (size_t)R * D * 4, s));
+  if (bf) {
+    // bf16 mode: every B·nq-row GEMM on tcgen05 with the 3-term bf16 split folded into K (K' = 3K, ~fp32 accuracy:
+    // the objectness ranking downstream has top-1 gaps of 1e-7…3e-3), attention on the tcgen05 kernel.
+    auto gemm3 = [&](const __nv_bfloat16* a3, const __nv_bfloat16* w3, const float* bias, void* C, int64_t ldc, int rows, int N_, int K_,
+                     int epi, int out_f32) {
+      return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
+    };
+    const __nv_bfloat16* KVb = (const __nv_bfloat16*)m->KV;
+    for (int l = 0; l < L; ++l) {
+      const DecW& d = m->dec[l];
+      const Dec3& d3 = m->dec3[l];
+      // self-attention: q = k = tgt + query_pos, v = tgt
+      SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, m->a3a, m->a3b, R, D, s));
+      SMK_PROPAGATE(gemm3(m->a3b, d3.saw, w + d.sab, m->dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
+      SMK_PROPAGATE(gemm3(m->a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, m->dv_b, D, R, D, D, SMK_EPI_NONE, 0));
+      SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->dao, D, 1, B, nq, nq, c.heads, scale, s));
+      SMK_PROPAGATE(split3_act(m->dao, D, nullptr, 0, m->a3a, nullptr, R, D, s));
+      SMK_PROPAGATE(gemm3(m->a3a, d3.saow, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n1w, w + d.n1b, m->tgt, nullptr, R, D, 1e-5f, s));
+      // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
+      SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, nullptr, m->a3b, R, D, s));
+      SMK_PROPAGATE(gemm3(m->a3b, d3.caqw, w + d.cab, m->cq_b, D, R, D, D, SMK_EPI_NONE, 0));
+      const __nv_bfloat16* kl = KVb + (int64_t)l * 2 * D;
+      SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->dao, D, 1, B, nq, hw, c.heads, scale, s));
+      SMK_PROPAGATE(split3_act(m->dao, D, nullptr, 0, m->a3a, nullptr, R, D, s));
+      SMK_PROPAGATE(gemm3(m->a3a, d3.caow, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
+      // FFN
+      SMK_PROPAGATE(split3_act(m->tgt, D, nullptr, 0, m->a3a, nullptr, R, D, s));
+      SMK_PROPAGATE(gemm3(m->a3a, d3.l1w, w + d.l1b, m->ffh, FD, R, FD, D, SMK_EPI_RELU, 1));
+      SMK_PROPAGATE(split3_act(m->ffh, FD, nullptr, 0, m->a3a, nullptr, R, FD, s));
+      SMK_PROPAGATE(gemm3(m->a3a, d3.l2w, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n3w, w + d.n3b, m->tgt, nullptr, R, D, 1e-5f, s));
+      SMK_PROPAGATE(layernorm_f32(m->tgt, nullptr, w + m->o_dnw, w + m->o_dnb, m->queries + (int64_t)l * R * D, nullptr, R, D, 1e-5f, s));
+    }
+  } else {
   for (int l = 0; l < L; ++l) {
     const DecW& d = m->dec[l];
     // self-attention: q = k = tgt + query_pos, v = tgt
@@ -407,23 +482,18 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
     // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
     SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
     SMK_PROPAGATE(gemm_f32(m->qin, D, w + d.caw, D, w + d.cab, m->dqk, D, R, D, D, SMK_EPI_NONE, s));
-    if (bf) {
-      const __nv_bfloat16* kv = (const __nv_bfloat16*)m->KV + ldkv /*skip cls row*/ + (int64_t)l * 2 * D;
-      SMK_PROPAGATE((attention<float, __nv_bfloat16>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv,
-                                                     ldkv, (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
-    } else {
-      const float* kv = (const float*)m->KV + ldkv + (int64_t)l * 2 * D;
-      SMK_PROPAGATE((attention<float, float>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv, ldkv,
-                                             (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
-    }
+    const float* kv = (const float*)m->KV + ldkv + (int64_t)l * 2 * D;
+    SMK_PROPAGATE((attention<float, float>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv, ldkv,
+                                           (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
     SMK_PROPAGATE(gemm_f32(m->dao, D, w + d.caow, D, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
     // FFN
-    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.l1w, D, w + d.l1b, m->ffh, c.dec_ffn, R, c.dec_ffn, D, SMK_EPI_RELU, s));
-    SMK_PROPAGATE(gemm_f32(m->ffh, c.dec_ffn, w + d.l2w, c.dec_ffn, w + d.l2b, m->t2, D, R, D, c.dec_ffn, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.l1w, D, w + d.l1b, m->ffh, FD, R, FD, D, SMK_EPI_RELU, s));
+    SMK_PROPAGATE(gemm_f32(m->ffh, FD, w + d.l2w, FD, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n3w, w + d.n3b, m->tgt, nullptr, R, D, 1e-5f, s));
     // shared final norm on every layer's output (transformer_decoder.py:138-145)
     SMK_PROPAGATE(layernorm_f32(m->tgt, nullptr, w + m->o_dnw, w + m->o_dnb, m->queries + (int64_t)l * R * D, nullptr, R, D, 1e-5f, s));
+  }
   }
 
   // ---- heads ----------------------------------------------------------------------------------------
@@ -433,8 +503,15 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
   if (objectness) {
     const float* qsrc = m->queries + (int64_t)layer0 * R * D;
     const int rows = Lout * R;
-    SMK_PROPAGATE(gemm_f32(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
-    SMK_PROPAGATE(gemm_f32(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
+    if (bf) {
+      SMK_PROPAGATE(split3_act(qsrc, D, nullptr, 0, m->a3a, nullptr, rows, D, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->a3a, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->oh1, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
+      SMK_PROPAGATE(split3_act(m->oh1, D, nullptr, 0, m->a3a, nullptr, rows, D, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->a3a, 3 * D, m->f1w3, 3 * D, w + m->o_f1b, m->oh2, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
+    } else {
+      SMK_PROPAGATE(gemm_f32(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
+      SMK_PROPAGATE(gemm_f32(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
+    }
     SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
     SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));
   }

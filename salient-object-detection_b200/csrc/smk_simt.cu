@@ -372,6 +372,65 @@ int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3-term bf16 split ("bf16x3") laid out along K so that ONE tensor-core GEMM with K' = 3K computes
+//   A·W^T ≈ A_hi·W_hi^T + A_hi·W_lo^T + A_lo·W_hi^T      (hi = bf16(x), lo = bf16(x − hi); error ~2^-16 relative)
+// activations: row → [hi | hi | lo];  weights: row → [hi | lo | hi].  Used for the decoder tail, whose objectness
+// ranking needs near-fp32 GEMMs but whose FLOPs are small.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_hi_lo(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// out_a[r] = split(x[r]);  out_b[r] = split(x[r] + pos[r % period])  (either output may be null; x may be null = 0)
+__global__ void __launch_bounds__(256)
+split3_act_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ pos, int period,
+                  __nv_bfloat16* __restrict__ out_a, __nv_bfloat16* __restrict__ out_b, int64_t rows, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  const float v = x ? x[r * ldx + k] : 0.f;
+  __nv_bfloat16 hi, lo;
+  if (out_a) {
+    split_hi_lo(v, hi, lo);
+    __nv_bfloat16* o = out_a + r * 3 * K;
+    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+  }
+  if (out_b) {
+    split_hi_lo(v + pos[(int64_t)(r % period) * K + k], hi, lo);
+    __nv_bfloat16* o = out_b + r * 3 * K;
+    o[k] = hi; o[K + k] = hi; o[2 * K + k] = lo;
+  }
+}
+int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_bfloat16* out_a, __nv_bfloat16* out_b, int64_t rows,
+               int K, cudaStream_t s) {
+  if (rows == 0) return SMK_OK;
+  {
+    ProfScope prof(PROF_OTHER, (double)rows * K * (4.0 + (out_a ? 6.0 : 0.0) + (out_b ? 6.0 : 0.0)), s);
+    split3_act_kernel<<<(unsigned)((rows * K + 255) / 256), 256, 0, s>>>(x, ldx, pos, period > 0 ? period : 1, out_a, out_b, rows, K);
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+__global__ void __launch_bounds__(256)
+split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t rows, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  __nv_bfloat16 hi, lo;
+  split_hi_lo(w[i], hi, lo);
+  __nv_bfloat16* o = out + r * 3 * K;
+  o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
+}
+int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s) {
+  if (rows == 0) return SMK_OK;
+  split3_weight_kernel<<<(unsigned)((rows * K + 255) / 256), 256, 0, s>>>(w, out, rows, K);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Mask head (maskformer.py:144-162, :223): logits at patch resolution = queries · memory^T, then the
 // pixel decoder's bilinear xsf applied to the nq-channel logits (bilinear is linear and per-channel, so
 // it commutes with the contraction — SURVEY.md K12), sigmoid, store mask_pred[b,l,q,:,:].
@@ -571,4 +630,10 @@ extern "C" int smk_attention(const void* q, const void* k, const void* v, void* 
 extern "C" int smk_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
   SMK_REQUIRE(in && out && n >= 0, "smk_cast_bf16: bad arguments");
   return cast_bf16(in, (__nv_bfloat16*)out, n, (cudaStream_t)stream);
+}
+
+extern "C" int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream) {
+  SMK_REQUIRE(x && out && rows >= 0 && K > 0, "smk_split3: bad arguments");
+  if (is_weight) return split3_weight(x, (__nv_bfloat16*)out, rows, K, (cudaStream_t)stream);
+  return split3_act(x, K, nullptr, 0, (__nv_bfloat16*)out, nullptr, rows, K, (cudaStream_t)stream);
 }

@@ -1,4 +1,5 @@
 """GPU parity tests of single kernels through the C-ABI: CUDA path vs the CPU oracle / golden fixtures."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -152,6 +153,7 @@ def test_gemm_f32_matches_torch(M_, N, K, epi):
 @pytest.mark.parametrize("M_,N,K,epi,f32", [(128, 128, 64, 0, True), (128, 128, 384, 0, True), (197, 384, 384, 0, False),
                                             (1000, 1152, 384, 0, False), (333, 1536, 384, 1, False), (130, 384, 1536, 4, True),
                                             (50432, 1536, 384, 1, False), (50432, 384, 1536, 4, True), (40000, 4608, 384, 0, False),
+                                            (50432, 1152, 384, 0, False), (50432, 384, 384, 4, True), (5120, 768, 1152, 0, False),
                                             (64, 256, 768, 2, True)])
 def test_gemm_bf16_tcgen05_matches_torch(M_, N, K, epi, f32):
     torch.manual_seed(2)
@@ -205,3 +207,43 @@ def test_attention_tcgen05_matches_torch(B, N):
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, D)
     err = (out.float() - ref).abs().max().item()
     assert err <= 0.03, err
+
+
+def test_bf16x3_split_gemm_is_near_fp32():
+    """Decoder tail: A·W^T through ONE tcgen05 GEMM over K' = 3K with the 3-term bf16 split folded into K."""
+    torch.manual_seed(5)
+    for M_, N, K, epi in [(5120, 384, 384, 0), (5120, 1536, 384, 2), (400, 384, 1536, 0), (20, 768, 384, 0)]:
+        A = torch.randn(M_, K, device=DEV) * 2
+        W = torch.randn(N, K, device=DEV) * 0.05
+        bias = torch.randn(N, device=DEV)
+        a3 = torch.empty(M_, 3 * K, dtype=torch.bfloat16, device=DEV)
+        w3 = torch.empty(N, 3 * K, dtype=torch.bfloat16, device=DEV)
+        check(lib().smk_split3(ptr(A), M_, K, ptr(a3), 0, stream_ptr()))
+        check(lib().smk_split3(ptr(W), N, K, ptr(w3), 1, stream_ptr()))
+        out = gemm_bf16(a3, w3, bias, epi, out_f32=True)
+        ref = A.double() @ W.double().t() + bias.double()
+        if epi & 2:
+            ref = torch.relu(ref)
+        err = (out.double() - ref).abs().max().item()
+        assert err <= 3e-4, (M_, N, K, err)     # plain bf16 operands would give ~3e-2 here
+
+
+@pytest.mark.parametrize("Lq,Lk,kv_rows,kv_row0", [(20, 196, 197, 1), (20, 20, 20, 0), (10, 196, 197, 1), (128, 250, 256, 3)])
+def test_attention_tcgen05_general_layout(Lq, Lk, kv_rows, kv_row0):
+    """Decoder cross / self attention layout: separate q, k, v matrices, per-image key offset (cls skipped), fp32 out."""
+    torch.manual_seed(6)
+    B, H, dh = 5, 6, 64
+    D = H * dh
+    q = torch.randn(B * Lq, D, device=DEV).to(torch.bfloat16)
+    kv = torch.randn(B * kv_rows, 2 * D, device=DEV).to(torch.bfloat16)       # k | v interleaved per row (ld = 2D)
+    out = torch.zeros(B * Lq, D, device=DEV, dtype=torch.float32)
+    k_view, v_view = kv[:, :D], kv[:, D:]
+    check(lib().smk_attention_tc_general(ptr(q), D, C.c_void_p(k_view.data_ptr()), 2 * D, C.c_void_p(v_view.data_ptr()), 2 * D,
+                                         B * kv_rows, kv_rows, kv_row0, ptr(out), D, 1, B, Lq, Lk, H, 0.125, stream_ptr()))
+    torch.cuda.synchronize()
+    qh = q.float().view(B, Lq, H, dh).transpose(1, 2)
+    kk = kv.float().view(B, kv_rows, 2 * D)[:, kv_row0:kv_row0 + Lk]
+    kh = kk[..., :D].reshape(B, Lk, H, dh).transpose(1, 2)
+    vh = kk[..., D:].reshape(B, Lk, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    assert (out - ref).abs().max().item() <= 0.03
