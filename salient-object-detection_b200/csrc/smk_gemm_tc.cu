@@ -1,11 +1,16 @@
 // bf16 tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T (+bias, GELU/ReLU, +residual)
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread) and
-// TMEM owner, warps 2-9 = epilogue (two warpgroups, each owning half of the tile's columns; TMEM → registers →
-// global).  With K = 384 the MMA time of a tile is only 12 cycles per accumulator column, so the epilogue must
-// stay under ~12 instructions per output element: hence 8 epilogue warps and the MUFU-light GELU below.  Operands are staged by TMA into a
-// kStages-deep ring of 128-byte-swizzled shared-memory tiles; fp32 accumulators live in TMEM and are
+// TMEM owner, warps 2-9 = epilogue (two warpgroups, each owning half of the tile's columns).  Operands are staged
+// by TMA into a kStages-deep ring of 128-byte-swizzled shared-memory tiles; fp32 accumulators live in TMEM and are
 // double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Epilogue: TMEM → registers (tcgen05.ld, one accumulator row per thread) → bias / activation → swizzled
+// shared-memory staging tile (conflict-free 16-byte stores) → TMA tile store.  A per-thread row store straight to
+// global memory costs 32 L1 wavefronts per instruction (every lane a different 128-byte line) and made the
+// epilogue 2-5x slower than the MMAs; the TMA store writes full lines.  The fp32 residual stream is updated by a
+// TMA *reduce-add* (cp.reduce.async.bulk.tensor .add, performed at L2): X += A·W^T + b without the SM ever reading X.
+// With K = 384 a tile's MMAs take only 12 cycles per accumulator column, so the activation must stay near
+// 10 instructions per element (gelu_fast below).
 // Serves: patch-embed (vision_transformer.py:184-188), qkv / proj / fc1 / fc2 (:113,131,88-94), the
 // decoder's memory K/V projection (transformer_decoder.py:283-291 via nn.MultiheadAttention in_proj).
 #include <mutex>
@@ -17,30 +22,37 @@ namespace smk {
 using namespace tc;
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_STAGING_PER_WARP = 4096;   // 32 rows x 128 B (fp32 chunk) or 2 x (32 rows x 64 B) (bf16 chunks, double-buffered)
 
-// exact-GELU (vision_transformer.py:78 nn.GELU, erf form) evaluated as  0.5x(1 + erf(|x|/√2)·sign x)  with
-// erf(z) = 1 − 2^(−p(z)), p a degree-5 fit on [0,4]: max abs error 1.9e-5 = 0.06 bf16 ulp of the result
-// (the bf16-mode output is rounded to bf16 right after).  10 FMA-pipe instructions + one MUFU.EX2; the fp32
-// validation mode keeps erff().
+// exact-GELU (vision_transformer.py:78 nn.GELU, erf form) as  relu(x) − 0.5·|x|·(1 − erf(|x|/√2))  with
+// 1 − erf(u/√2) = 2^(u·q(u)), q a degree-4 fit (monotone beyond the fit range, so no clamp is needed):
+// max abs error 1.9e-5 = 0.11 bf16 ulp of the result (the bf16-mode output is rounded to bf16 right after).
+// 9 FMA-pipe instructions + one MUFU.EX2; the fp32 validation mode keeps erff().
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.0f);
-  float p = fmaf(z, 0.00164591f, -0.02243328f);
-  p = fmaf(z, p, 0.13533017f);
-  p = fmaf(z, p, 0.92796782f);
-  p = fmaf(z, p, 1.62590536f);
-  const float t = exp2f(-(z * p));               // 1 − erf(z)
-  const float hx = 0.5f * x, ax = fabsf(hx);
-  return fmaf(-ax, t, hx + ax);                  // hx + |hx|·erf(z)
+  const float u = fabsf(x);
+  float q = fmaf(u, -0.00029095853f, 0.0056083198f);
+  q = fmaf(u, q, -0.04784644f);
+  q = fmaf(u, q, -0.46398392f);
+  q = fmaf(u, q, -1.1496887f);
+  const float t = ex2_approx(u * q);              // 1 − erf(|x|/√2)
+  return fmaf(-0.5f * u, t, fmaxf(x, 0.f));
 }
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 128) ? 6 : (BN == 192 ? 5 : 4);
+  static constexpr int kStages = (BN == 128) ? 6 : 4;
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = TC_EPI_WARPS * TC_STAGING_PER_WARP;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 struct TcGemmParams {
@@ -50,18 +62,21 @@ struct TcGemmParams {
   int64_t ldc;
   int epi;        // SMK_EPI_* flags
   int out_f32;    // 0 → bf16 output, 1 → fp32 output
-  // token assembly for patch-embed: output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
+  // token assembly for patch-embed (kDirect): output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
   int tok_hw;
   const float* tok_pos;
 };
 
-template <int BN>
+// kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
+template <int BN, bool kDirect>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    const TcGemmParams p) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -74,6 +89,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!kDirect) tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS); }
     fence_barrier_init();
@@ -132,83 +148,105 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== epilogue: warps 2..9; lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
     const int quarter = warp & 3;
     const int col_half = (warp - 2) >> 2;
+    constexpr int kChunks = BN / 64;             // 32-column chunks per warp per tile
+    uint8_t* stg = staging + (warp - 2) * TC_STAGING_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t it = 0;                             // staging-buffer parity (bf16 output)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const int m = m_blk * TC_BM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      int64_t out_row = m;
-      const float* pos_row = nullptr;
-      if (p.tok_hw > 0) {
-        out_row = (int64_t)m + m / p.tok_hw + 1;
-        pos_row = p.tok_pos + (int64_t)(1 + m % p.tok_hw) * p.N;
-      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int c = col_half * kChunks + ci;
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        if (row_ok) {
-          const int n0 = n_blk * BN + c * 32;
-          float v[32];
+        if (ci == kChunks - 1) {                 // accumulator fully read: hand the TMEM buffer back before the math
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int n0 = n_blk * BN + c * 32;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
-          if (p.epi & SMK_EPI_GELU) {
+        }
+        if (p.epi & SMK_EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          }
-          if (p.epi & SMK_EPI_RELU) {
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (p.epi & SMK_EPI_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (pos_row) {
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if constexpr (kDirect) {
+          if (m < p.M) {
+            const int64_t out_row = (int64_t)m + m / p.tok_hw + 1;
+            const float* pos_row = p.tok_pos + (int64_t)(1 + m % p.tok_hw) * p.N;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
-          }
-          if (p.out_f32) {
             float* crow = reinterpret_cast<float*>(p.C) + out_row * p.ldc + n0;
-            if (p.epi & SMK_EPI_RESIDUAL) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(crow + j);
-                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
-              }
-            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + n0;
+          }
+        } else {
+          const int row0 = m_blk * TC_BM + quarter * 32;
+          if (p.out_f32) {
+            // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            uint8_t* srow = stg + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.epi & SMK_EPI_RESIDUAL) tma_reduce_add_2d(&tmC, stg, n0, row0);
+              else tma_store_2d(&tmC, stg, n0, row0);
+              bulk_commit();
+            }
+          } else {
+            // staging tile: 32 rows x 64 B, 64-byte swizzle (16-byte chunk index ^= (row >> 1) & 3), two buffers
+            uint8_t* buf = stg + (it & 1) * 2048;
+            ++it;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            uint8_t* srow = buf + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
               uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), t3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
               pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
               pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(crow + j) = pk;
+              *reinterpret_cast<uint4*>(srow + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, n0, row0);
+              bulk_commit();
             }
           }
         }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (!kDirect && lane == 0) bulk_wait<0>();   // all tile stores complete before the CTA retires
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -222,8 +260,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static std::once_flag g_encode_once;
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -231,17 +269,33 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
       g_encode = (PFN_encodeTiled)fn;
   });
   if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SMK_ERR_CUDA; }
+  SMK_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "tensor map: element size %d unsupported", elem_bytes);
   SMK_REQUIRE(((uintptr_t)base % 16) == 0 && row_stride_bytes % 16 == 0, "tensor map: base/stride must be 16-byte aligned");
-  SMK_REQUIRE(box_inner * 2 == 128 && box_outer <= 256, "tensor map: box {%u,%u} unsupported", box_inner, box_outer);
+  SMK_REQUIRE(box_outer <= 256 && box_inner <= 256 && (swizzle_bytes == 0 || (int)box_inner * elem_bytes <= swizzle_bytes),
+              "tensor map: box {%u,%u} unsupported with swizzle %d", box_inner, box_outer, swizzle_bytes);
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  switch (swizzle_bytes) {
+    case 0: break;
+    case 32: sw = CU_TENSOR_MAP_SWIZZLE_32B; break;
+    case 64: sw = CU_TENSOR_MAP_SWIZZLE_64B; break;
+    case 128: sw = CU_TENSOR_MAP_SWIZZLE_128B; break;
+    default: set_error("tensor map: swizzle %d unsupported", swizzle_bytes); return SMK_ERR_INVALID;
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SMK_ERR_CUDA; }
   return SMK_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  SMK_REQUIRE(box_inner * 2 == 128, "tensor map: operand box must be 128 bytes wide");
+  return make_tmap_2d(out, 2, base, inner, outer, row_stride_bytes, box_inner, box_outer, 128);
 }
 
 static int g_num_sms = 0;
@@ -255,22 +309,36 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p, cudaStream_t s) {
+template <int BN, bool kDirect>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM - 1) / TC_BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
     ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
-    gemm_bf16_tc_kernel<BN><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, p);
+    gemm_bf16_tc_kernel<BN, kDirect><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, tcm, p);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
+}
+
+// Tile width: minimise (waves over the SMs) x BN, i.e. the tensor-pipe time of the busiest SM; ties go to the wider
+// tile (fewer A+B shared-memory bytes per MMA cycle: 128 B at BN=128, 107 at 192, 96 at 256).
+static int pick_bn(int M, int N) {
+  const int64_t mb = (M + TC_BM - 1) / TC_BM, sms = num_sms();
+  int best = 128;
+  int64_t best_cost = -1;
+  for (int bn : {128, 192, 256}) {
+    if (N % bn) continue;
+    const int64_t tiles = (N / bn) * mb, cost = (tiles + sms - 1) / sms * bn;
+    if (best_cost < 0 || cost <= best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 // A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements)
@@ -280,15 +348,21 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32, "gemm_bf16: residual epilogue needs fp32 output");
   SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
+  SMK_REQUIRE(tok_hw == 0 || (out_f32 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
-  // wider tiles relieve shared-memory bandwidth (A+B bytes per MMA cycle: 128 B at BN=128, 107 at 192, 96 at 256)
-  const int64_t mb = (M + 127) / 128;
-  const int BN = (N % 256 == 0 && (N / 256) * mb >= num_sms()) ? 256 : ((N % 192 == 0 && (N / 192) * mb >= num_sms()) ? 192 : 128);
-  CUtensorMap ta, tb;
+  const int BN = pick_bn(M, N);
+  CUtensorMap ta, tb, tcm;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)BN));
   TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos};
-  return BN == 256 ? launch_tc<256>(ta, tb, p, s) : (BN == 192 ? launch_tc<192>(ta, tb, p, s) : launch_tc<128>(ta, tb, p, s));
+  if (tok_hw > 0) {
+    tcm = ta;   // unused by the direct-store epilogue
+    return BN == 256 ? launch_tc<256, true>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, true>(ta, tb, tcm, p, s) : launch_tc<128, true>(ta, tb, tcm, p, s));
+  }
+  // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (bf16, 64-byte swizzle) per row
+  const int esz = out_f32 ? 4 : 2;
+  SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * esz, 32, 32, out_f32 ? 128 : 64));
+  return BN == 256 ? launch_tc<256, false>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, false>(ta, tb, tcm, p, s) : launch_tc<128, false>(ta, tb, tcm, p, s));
 }
 
 }  // namespace smk
