@@ -159,6 +159,9 @@ int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float 
 int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_total_rows,
                              int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk, int heads,
                              float scale, void* stream);
+/* tuning aid: phase trace of CTA 0 of the tcgen05 attention kernel ([16 items][10 warps][8 events] clock64 stamps in device
+ * memory); NULL switches it off. */
+int smk_debug_attn_trace(long long* buf);
 /* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
  * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */
 int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream);

@@ -1,205 +1,362 @@
-// Fused encoder self-attention on tcgen05 (vision_transformer.py:110-130): per (image, head, 128-query tile)
-//   S = Q·K^T  (UMMA 128 x Nk x 64, accumulators in TMEM)  →  single-pass softmax in registers (one thread per
-//   query row, tcgen05.ld)  →  P (bf16) written to shared memory in the 128B-swizzled K-major layout  →
-//   O = P·V   (V consumed as an MN-major operand straight from its TMA tile)  →  O / rowsum → bf16 → global.
-// Q, K, V are read in place from the fused-QKV GEMM output [B*N, 3*D] by TMA (no permute copy, :113-118).
-// One key tile: N <= 256 tokens (224x224 / patch 16 → 197).  Longer sequences use the CUDA-core kernel.
-// 160 threads: warp 0 = TMA + MMA issue + TMEM owner, warps 1-4 = softmax / epilogue (TMEM lane quarters).
+// Fused multi-head softmax attention on tcgen05 (encoder: vision_transformer.py:110-130; decoder self / cross
+// attention: transformer_decoder.py:271-291 via nn.MultiheadAttention), head dim 64, up to 256 queries and 256 keys
+// per (image, head).
+//
+// Persistent and warp-specialised: one CTA per SM loops over (image, head) items.
+//   warp 0      TMA producer: Q (one or two 128-row tiles), K and V boxes straight out of the projection outputs
+//               (strided tensor maps, no permute copy :113-118).  Q/K and V have separate full/empty barriers: Q and K are
+//               released as soon as both S = Q·K^T products retire, so the next item's loads overlap this item's softmax.
+//   warp 1      tcgen05.mma issuer: S_t = Q_t·K^T (UMMA 128 x nk x 64) into TMEM slot t, later O_t = P_t·V (V consumed
+//               as an MN-major operand from its TMA tile) into the same slot.
+//   warps 2-9   two softmax groups (one per query tile, 4 warps = the 4 TMEM lane quarters): one thread per query row,
+//               row max then exp2 in registers from tcgen05.ld, P (bf16) written to shared memory in the 128B-swizzled
+//               K-major layout; after O_t lands: O / rowsum → shared-memory staging → TMA tile store through a 3-D
+//               {column, row-in-image, image} tensor map, which clips the rows beyond the image's last query.
+// The MUFU exp2 (16/clk/SM) is the bound of this kernel, not the tensor pipe: 197x208 exponentials per (image, head)
+// against 1664 MMA cycles.
 #include "smk_tc.cuh"
 
 namespace smk {
 
 using namespace tc;
 
-constexpr int AT_BM = 128, AT_DH = 64, AT_THREADS = 160, AT_TMEM_COLS = 256;
-constexpr int AT_REGION_A = 65536;   // Q (16 KB) + K (<= 32 KB), later reused for P (4 K-blocks x 16 KB)
-constexpr int AT_REGION_V = 32768;
-constexpr int AT_SMEM = AT_REGION_A + AT_REGION_V + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int AT_BM = 128, AT_DH = 64, AT_THREADS = 320, AT_TMEM_COLS = 512, AT_MAXK = 256;
+constexpr int AT_Q_BYTES = 2 * AT_BM * 128;          // two query tiles
+constexpr int AT_KV_BYTES = AT_MAXK * 128;           // up to 256 keys x 64 dims bf16
+constexpr int AT_P_BYTES = (AT_MAXK / 64) * 16384;   // per query tile: 4 key blocks of 128 rows x 128 B
+constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_P = AT_OFF_V + AT_KV_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_P_BYTES;
+constexpr int AT_SMEM = AT_OFF_BAR + 256 /*barriers*/ + 1024 /*align*/;
+static_assert(AT_SMEM <= 227 * 1024, "attention shared memory budget");
 
 struct AttnTcParams {
   int Lq, Lk, nk_pad;           // valid query rows / keys per image, keys padded to a multiple of 16
+  int n_qtiles;                 // 1 (Lq <= 128) or 2
   int q_rows, kv_rows, kv_row0; // image b: queries start at row b*q_rows, keys/values at row b*kv_rows + kv_row0
-  void* out;                    // [B*q_rows, ldo]; bf16 or fp32
-  int64_t ldo;
+  int heads, n_items;           // items = images x heads
   int out_f32;
   float scale_log2e;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// optional phase trace of CTA 0 (debug builds of the tuning scripts only): [item < 16][warp 10][event 8] clock64 stamps
+__device__ long long* g_attn_trace = nullptr;
+#define AT_TRACE(ev)                                                                                         \
+  do {                                                                                                       \
+    if (g_attn_trace && blockIdx.x == 0 && lane == 0 && it < 16) g_attn_trace[(it * 10 + warp) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-               const AttnTcParams p) {
+               const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sP = smem;                       // aliases Q/K once S has been produced
-  uint8_t* sV = smem + AT_REGION_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_REGION_A + AT_REGION_V);
-  uint64_t *bar_qk = bars, *bar_v = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_o = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sK = smem + AT_OFF_K;
+  uint8_t* sV = smem + AT_OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t *qk_full = bars, *qk_empty = bars + 1, *v_full = bars + 2, *v_empty = bars + 3;
+  uint64_t *s_full = bars + 4, *p_full = bars + 6, *o_full = bars + 8, *o_drained = bars + 10;   // [2] each
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q_row0 = b * p.q_rows, kv_row0 = b * p.kv_rows + p.kv_row0;
+  const int nt = p.n_qtiles;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_ptr, AT_TMEM_COLS);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1); mbar_init(&o_drained[t], 4); }
+    fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(tmem_ptr, AT_TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
+    // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t kv_bytes = (uint32_t)p.nk_pad * 128u;
-      mbar_arrive_expect_tx(bar_qk, 16384u + kv_bytes);
-      tma_load_2d(sQ, &tmQ, bar_qk, h * AT_DH, q_row0 + qt * AT_BM);
-      tma_load_2d(sK, &tmK, bar_qk, h * AT_DH, kv_row0);
-      mbar_arrive_expect_tx(bar_v, kv_bytes);
-      tma_load_2d(sV, &tmV, bar_v, h * AT_DH, kv_row0);
-      // S = Q · K^T
-      mbar_wait(bar_qk, 0);
-      tc_fence_after_sync();
-      const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
-      const uint64_t qd = smem_desc_k_sw128(smem_u32(sQ)), kd = smem_desc_k_sw128(smem_u32(sK));
-#pragma unroll
-      for (int k = 0; k < AT_DH / 16; ++k) umma_bf16_ss(tmem_base, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
-      tc_commit(bar_s);
-      // O = P · V   (accumulates into TMEM columns [0,64): S has been fully read out by then)
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after_sync();
-      const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_DH, 0, 1);
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-      for (int j = 0; j < p.nk_pad / 16; ++j) {
-        const uint64_t pd = smem_desc_k_sw128(pa + (uint32_t)((j >> 2) * 16384 + (j & 3) * 32));
-        const uint64_t vd = smem_desc_mn_sw128(va + (uint32_t)(j * 2048), 1024);
-        umma_bf16_ss(tmem_base, pd, vd, idesc_o, j != 0);
+      const uint32_t q_bytes = (uint32_t)nt * AT_BM * 128u, kv_bytes = (uint32_t)p.nk_pad * 128u;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int b = item / p.heads, h = item % p.heads;
+        const int kv_row = b * p.kv_rows + p.kv_row0;
+        mbar_wait(qk_empty, (it & 1) ^ 1);
+        AT_TRACE(0);
+        mbar_arrive_expect_tx(qk_full, q_bytes + kv_bytes);
+        tma_load_2d(sQ, &tmQ, qk_full, h * AT_DH, b * p.q_rows);
+        tma_load_2d(sK, &tmK, qk_full, h * AT_DH, kv_row);
+        mbar_wait(v_empty, (it & 1) ^ 1);
+        AT_TRACE(1);
+        mbar_arrive_expect_tx(v_full, kv_bytes);
+        tma_load_2d(sV, &tmV, v_full, h * AT_DH, kv_row);
       }
-      tc_commit(bar_o);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
+      const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_DH, 0, 1);
+      const uint64_t kd = smem_desc_k_sw128(smem_u32(sK));
+      const uint32_t va = smem_u32(sV);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        mbar_wait(qk_full, par);
+        AT_TRACE(0);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&o_drained[t], par ^ 1);      // slot t: the previous item's O has been read out
+          AT_TRACE(1 + t);
+          tc_fence_after_sync();
+          const uint64_t qd = smem_desc_k_sw128(smem_u32(sQ + t * AT_BM * 128));
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+#pragma unroll
+          for (int k = 0; k < AT_DH / 16; ++k) umma_bf16_ss(d_tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+          tc_commit(&s_full[t]);
+        }
+        tc_commit(qk_empty);                      // Q and K may be overwritten once both S products retire
+        mbar_wait(v_full, par);
+        AT_TRACE(3);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&p_full[t], par);             // P_t is in shared memory and S_t has been fully read
+          AT_TRACE(4 + t);
+          tc_fence_after_sync();
+          const uint32_t pa = smem_u32(smem + AT_OFF_P + t * AT_P_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+          for (int j = 0; j < p.nk_pad / 16; ++j) {
+            const uint64_t pd = smem_desc_k_sw128(pa + (uint32_t)((j >> 2) * 16384 + (j & 3) * 32));
+            const uint64_t vd = smem_desc_mn_sw128(va + (uint32_t)(j * 2048), 1024);
+            umma_bf16_ss(d_tmem, pd, vd, idesc_o, j != 0);
+          }
+          tc_commit(&o_full[t]);
+        }
+        tc_commit(v_empty);
+        AT_TRACE(6);
+      }
     }
   } else {
+    // ===== softmax + epilogue: group t = (warp - 2) / 4 owns query tile t; TMEM lane quarter = warp % 4 =====
+    const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;             // row within the tile = TMEM lane
-    const int row = qt * AT_BM + r;                // token index within the image
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // warps whose 32 rows are all beyond Lq do no softmax work (their P rows keep stale-but-finite Q/K bits; MMA rows
-    // are independent and those output rows are never stored)
-    const int n_chunks = (qt * AT_BM + quarter * 32 < p.Lq) ? (p.nk_pad + 31) / 32 : 0;
-    mbar_wait(bar_s, 0);
-    tc_fence_after_sync();
-    // pass 1: row maximum over the valid keys
-    float mx = -INFINITY;
-    for (int c = 0; c < n_chunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
+    if (t < nt) {
+      const int r = quarter * 32 + lane;             // row within the tile = TMEM lane
+      const int row0 = t * AT_BM + quarter * 32;     // first query row (within the image) of this warp
+      const bool active = row0 < p.Lq;               // warps past the last query only keep the barrier protocol going
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 256);
+      const uint32_t sP = smem_u32(smem + AT_OFF_P + t * AT_P_BYTES);
+      const uint32_t prow = sP + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+      const uint32_t x7s = (uint32_t)(r & 7) << 4;   // 128-byte swizzle: 16-byte chunk index ^= row & 7
+      // epilogue staging (P_t is dead once O_t has landed): this warp's own 4 KB of P rows in key blocks 0 and 1, so that no
+      // other warp's next-item P writes can touch a tile the TMA store is still reading
+      const uint32_t stg = sP + (uint32_t)(quarter * 4096);
+      constexpr uint32_t kStg2 = 16384;
+      const int n_full = p.Lk >> 5;                  // 32-column chunks of valid keys
+      const int n_tail = (p.nk_pad - n_full * 32) >> 4;   // 0..2 trailing 16-column pieces holding the last valid keys + padding
+      const float sc = p.scale_log2e;
+      // P row store: 8 keys (16 bytes) starting at key0 (multiple of 8)
+      auto store8 = [&](int key0, float e0, float e1, float e2, float e3, float e4, float e5, float e6, float e7) {
+        const uint32_t a = prow + (uint32_t)((key0 >> 6) * 16384) + ((((uint32_t)(key0 & 63) >> 3) << 4) ^ x7s);
+        st_shared_v4(a, pack_bf16x2(e0, e1), pack_bf16x2(e2, e3), pack_bf16x2(e4, e5), pack_bf16x2(e6, e7));
+      };
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        const int b = item / p.heads, h = item % p.heads;
+        if (active && lane == 0) bulk_wait_read<0>();   // previous item's output tile has left the staging area
+        __syncwarp();
+        AT_TRACE(0);
+        mbar_wait(&s_full[t], par);
+        tc_fence_after_sync();
+        AT_TRACE(1);
+        float sum = 0.f;
+        if (active) {
+          uint32_t va[32], vb[32], vt[16];
+          // ---- pass 1: row maximum over the valid keys (TMEM loads one chunk ahead of the math) ----
+          float m0 = -INFINITY, m1 = -INFINITY;
+          auto max32 = [&](const uint32_t (&v)[32]) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < p.Lk) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    const float mxs = mx * p.scale_log2e;
-    // pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P → smem (bf16, K-major, 128B swizzle)
-    float sum = 0.f;
-    uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
-    for (int c = 0; c < n_chunks; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      float e[32];
+            for (int j = 0; j < 32; j += 4) {
+              m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          };
+          if (n_full > 0) tmem_ld_32x32(taddr, va);
+          for (int c = 0; c < n_full; c += 2) {
+            tmem_ld_wait32(va);
+            if (c + 1 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), vb);
+            max32(va);
+            if (c + 1 < n_full) {
+              tmem_ld_wait32(vb);
+              if (c + 2 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 2) * 32), va);
+              max32(vb);
+            }
+          }
+          for (int u = 0; u < n_tail; ++u) {
+            const int col0 = n_full * 32 + u * 16;
+            tmem_ld_32x16(taddr + (uint32_t)col0, vt);
+            tmem_ld_wait16(vt);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pv = exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs));
-        e[j] = (c * 32 + j < p.Lk) ? pv : 0.f;
-        sum += e[j];
-      }
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.Lk) m0 = fmaxf(m0, __uint_as_float(vt[j]));
+          }
+          const float mxs = fmaxf(m0, m1) * sc;
+          AT_TRACE(2);
+          // ---- pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P → smem (bf16, K-major, 128B swizzle) ----
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          auto exp32 = [&](uint32_t (&v)[32], int c) {
+            float e[32];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {                // 4 x (8 keys = 16 bytes)
-        const int key0 = c * 32 + g * 8;
-        if (key0 < p.nk_pad) {
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(e[g * 8 + 0], e[g * 8 + 1]), t1 = __floats2bfloat162_rn(e[g * 8 + 2], e[g * 8 + 3]);
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(e[g * 8 + 4], e[g * 8 + 5]), t3 = __floats2bfloat162_rn(e[g * 8 + 6], e[g * 8 + 7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-          pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-          const int kblk = key0 >> 6, chunk16 = (key0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(prow + kblk * 16384 + ((chunk16 ^ (r & 7)) << 4)) = pk;
+            for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mxs));
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) { s0 += e[j]; s1 += e[j + 1]; s2 += e[j + 2]; s3 += e[j + 3]; }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              store8(c * 32 + g * 8, e[g * 8], e[g * 8 + 1], e[g * 8 + 2], e[g * 8 + 3], e[g * 8 + 4], e[g * 8 + 5], e[g * 8 + 6], e[g * 8 + 7]);
+          };
+          if (n_full > 0) tmem_ld_32x32(taddr, va);
+          for (int c = 0; c < n_full; c += 2) {
+            tmem_ld_wait32(va);
+            if (c + 1 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), vb);
+            exp32(va, c);
+            if (c + 1 < n_full) {
+              tmem_ld_wait32(vb);
+              if (c + 2 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 2) * 32), va);
+              exp32(vb, c + 1);
+            }
+          }
+          for (int u = 0; u < n_tail; ++u) {
+            const int col0 = n_full * 32 + u * 16;
+            tmem_ld_32x16(taddr + (uint32_t)col0, vt);
+            tmem_ld_wait16(vt);
+            float e[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              e[j] = (col0 + j < p.Lk) ? ex2_approx(fmaf(__uint_as_float(vt[j]), sc, -mxs)) : 0.f;
+              s0 += e[j];
+            }
+            store8(col0, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
+            store8(col0 + 8, e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15]);
+          }
+          sum = (s0 + s1) + (s2 + s3);
         }
-      }
-    }
-    fence_proxy_async();            // generic-proxy smem writes → visible to the tensor core (async proxy)
-    tc_fence_before_sync();         // our TMEM reads of S are ordered before the PV MMAs that overwrite it
-    mbar_arrive(bar_p);
-    // epilogue: O / rowsum → bf16 → out[b*N + row, h*64 : h*64+64]
-    mbar_wait(bar_o, 0);
-    tc_fence_after_sync();
-    const float inv = 1.0f / sum;   // inf for skipped rows (never stored)
-    const int64_t orow = (int64_t)(q_row0 + row) * p.ldo + h * AT_DH;
+        fence_proxy_async();            // generic-proxy smem writes → visible to the tensor core (async proxy)
+        tc_fence_before_sync();         // our TMEM reads of S are ordered before the PV MMAs that overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        AT_TRACE(3);
+        // epilogue: O / rowsum → staging → TMA store to out[b, row0 .. row0+32, h*64 .. h*64+64]
+        mbar_wait(&o_full[t], par);
+        tc_fence_after_sync();
+        AT_TRACE(4);
+        uint32_t oa[32], ob[32];
+        if (active) {
+          tmem_ld_32x32(taddr, oa);
+          tmem_ld_32x32(taddr + 32u, ob);
+          tmem_ld_wait32(oa);
+          tmem_ld_wait32(ob);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_drained[t]);       // slot t may receive the next item's S
+        AT_TRACE(5);
+        if (active) {
+          const float inv = 1.0f / sum;
+          auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+          if (p.out_f32) {
+            // two 32-column fp32 boxes of 32 rows x 128 B each, 128-byte swizzle
+            const uint32_t srow = stg + lane * 128;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      if (row < p.Lq) {
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + orow + c * 32;
+            for (int j = 0; j < 8; ++j) {
+              st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(oa[4 * j])), __float_as_uint(f(oa[4 * j + 1])),
+                           __float_as_uint(f(oa[4 * j + 2])), __float_as_uint(f(oa[4 * j + 3])));
+              st_shared_v4(srow + kStg2 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
+                           __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
+            }
+          } else {
+            const uint32_t srow = stg + lane * 128;        // one 64-column bf16 box of 32 rows x 128 B
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv,
-                                                            __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + c * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(o + j) = pk;
+            for (int j = 0; j < 4; ++j) {
+              st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), pack_bf16x2(f(oa[8 * j]), f(oa[8 * j + 1])), pack_bf16x2(f(oa[8 * j + 2]), f(oa[8 * j + 3])),
+                           pack_bf16x2(f(oa[8 * j + 4]), f(oa[8 * j + 5])), pack_bf16x2(f(oa[8 * j + 6]), f(oa[8 * j + 7])));
+              st_shared_v4(srow + (((uint32_t)(j + 4) << 4) ^ x7s), pack_bf16x2(f(ob[8 * j]), f(ob[8 * j + 1])), pack_bf16x2(f(ob[8 * j + 2]), f(ob[8 * j + 3])),
+                           pack_bf16x2(f(ob[8 * j + 4]), f(ob[8 * j + 5])), pack_bf16x2(f(ob[8 * j + 6]), f(ob[8 * j + 7])));
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmO, smem + (stg - smem_u32(smem)), h * AT_DH, row0, b);
+            if (p.out_f32) tma_store_3d(&tmO, smem + (stg + kStg2 - smem_u32(smem)), h * AT_DH + 32, row0, b);
+            bulk_commit();
           }
         }
+        AT_TRACE(6);
       }
+      if (active && lane == 0) bulk_wait<0>();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
+}
+
+static int at_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
                          int64_t kv_total_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk,
                          int heads, float scale, cudaStream_t s) {
   const int D = heads * AT_DH;
-  SMK_REQUIRE(Lk >= 1 && Lk <= 256 && Lq >= 1, "attention_tc: Lk=%d keys not supported (1..256)", Lk);
-  SMK_REQUIRE(B >= 1 && B <= 65535 && heads >= 1 && heads <= 65535, "attention_tc: bad batch/heads");
-  SMK_REQUIRE(ldo % 8 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc: output must be 16-byte aligned");
+  SMK_REQUIRE(Lk >= 1 && Lk <= AT_MAXK && Lq >= 1 && Lq <= 2 * AT_BM, "attention_tc: Lq=%d / Lk=%d not supported (1..256)", Lq, Lk);
+  SMK_REQUIRE(B >= 1 && heads >= 1 && (int64_t)B * heads < (1 << 30), "attention_tc: bad batch/heads");
+  const int esz = out_f32 ? 4 : 2;
+  SMK_REQUIRE((ldo * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc: output must be 16-byte aligned");
   const int nk_pad = (Lk + 15) / 16 * 16;
-  CUtensorMap tq, tk, tv;
-  SMK_PROPAGATE(make_tmap_bf16_2d(&tq, q, (uint64_t)D, (uint64_t)B * Lq, (uint64_t)ldq * 2, AT_DH, AT_BM));
+  const int nt = Lq > AT_BM ? 2 : 1;
+  CUtensorMap tq, tk, tv, to;
+  SMK_PROPAGATE(make_tmap_bf16_2d(&tq, q, (uint64_t)D, (uint64_t)B * Lq, (uint64_t)ldq * 2, AT_DH, (uint32_t)(nt * AT_BM)));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tk, k, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldk * 2, AT_DH, (uint32_t)nk_pad));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tv, v, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldv * 2, AT_DH, (uint32_t)nk_pad));
+  {
+    // {column, query row within the image, image}: rows >= Lq of a 32-row output box are clipped by the TMA unit
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)Lq, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)ldo * esz, (uint64_t)Lq * ldo * esz};
+    const uint32_t box[3] = {out_f32 ? 32u : 64u, 32u, 1u};
+    SMK_PROPAGATE(make_tmap_nd(&to, esz, out, 3, dims, strides, box, 128));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_set = true;
   }
-  AttnTcParams p{Lq, Lk, nk_pad, Lq, kv_rows, kv_row0, out, ldo, out_f32, scale * 1.4426950408889634f};
-  dim3 grid((Lq + AT_BM - 1) / AT_BM, heads, B);
+  const int n_items = B * heads;
+  AttnTcParams p{Lq, Lk, nk_pad, nt, Lq, kv_rows, kv_row0, heads, n_items, out_f32, scale * 1.4426950408889634f};
+  const int grid = n_items < at_num_sms() ? n_items : at_num_sms();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AT_DH * heads * B, s);
-    attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, s>>>(tq, tk, tv, p);
+    attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, s>>>(tq, tk, tv, to, p);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -212,6 +369,11 @@ int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int
 }
 
 }  // namespace smk
+
+extern "C" int smk_debug_attn_trace(long long* buf) {   // tuning aid: nullptr switches the trace off
+  SMK_CHECK_CUDA(cudaMemcpyToSymbol(smk::g_attn_trace, &buf, sizeof(buf)));
+  return SMK_OK;
+}
 
 extern "C" int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
   SMK_REQUIRE(qkv && out, "smk_attention_tc: null pointer");

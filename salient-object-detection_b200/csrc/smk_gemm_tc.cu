@@ -150,6 +150,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int col_half = (warp - 2) >> 2;
     constexpr int kChunks = BN / 64;             // 32-column chunks per warp per tile
     uint8_t* stg = staging + (warp - 2) * TC_STAGING_PER_WARP;
+    const uint32_t stg_u32 = smem_u32(stg);
+    auto r4 = [](float f) { return __float_as_uint(f); };
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;                             // staging-buffer parity (bf16 output)
@@ -208,10 +210,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
-            uint8_t* srow = stg + lane * 128;
+            const uint32_t srow = stg_u32 + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              st_shared_v4(srow + ((j ^ (lane & 7)) << 4), r4(v[4 * j]), r4(v[4 * j + 1]), r4(v[4 * j + 2]), r4(v[4 * j + 3]));
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -225,16 +227,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ++it;
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
-            uint8_t* srow = buf + lane * 64;
+            const uint32_t srow = stg_u32 + (uint32_t)(buf - stg) + lane * 64;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), t3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(srow + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
-            }
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(srow + ((j ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -260,8 +257,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static std::once_flag g_encode_once;
 
-int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+int make_tmap_nd(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -269,10 +266,11 @@ int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* base, uint64_t in
       g_encode = (PFN_encodeTiled)fn;
   });
   if (!g_encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SMK_ERR_CUDA; }
+  SMK_REQUIRE(rank == 2 || rank == 3, "tensor map: rank %d unsupported", rank);
   SMK_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "tensor map: element size %d unsupported", elem_bytes);
-  SMK_REQUIRE(((uintptr_t)base % 16) == 0 && row_stride_bytes % 16 == 0, "tensor map: base/stride must be 16-byte aligned");
-  SMK_REQUIRE(box_outer <= 256 && box_inner <= 256 && (swizzle_bytes == 0 || (int)box_inner * elem_bytes <= swizzle_bytes),
-              "tensor map: box {%u,%u} unsupported with swizzle %d", box_inner, box_outer, swizzle_bytes);
+  SMK_REQUIRE(((uintptr_t)base % 16) == 0, "tensor map: base must be 16-byte aligned");
+  SMK_REQUIRE(swizzle_bytes == 0 || (int)box[0] * elem_bytes <= swizzle_bytes, "tensor map: box width %u exceeds the %d-byte swizzle span",
+              box[0], swizzle_bytes);
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
   switch (swizzle_bytes) {
     case 0: break;
@@ -281,15 +279,29 @@ int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* base, uint64_t in
     case 128: sw = CU_TENSOR_MAP_SWIZZLE_128B; break;
     default: set_error("tensor map: swizzle %d unsupported", swizzle_bytes); return SMK_ERR_INVALID;
   }
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  cuuint64_t d[3], st[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    SMK_REQUIRE(box[i] >= 1 && box[i] <= 256 && dims[i] >= 1, "tensor map: bad box/dim %d", i);
+    d[i] = dims[i];
+    bx[i] = box[i];
+    if (i + 1 < rank) {
+      SMK_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map: stride %d must be a multiple of 16 bytes", i);
+      st[i] = strides_bytes[i];
+    }
+  }
+  CUresult r = g_encode(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                        const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SMK_ERR_CUDA; }
   return SMK_OK;
+}
+
+int make_tmap_2d(CUtensorMap* out, int elem_bytes, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  const uint64_t dims[2] = {inner, outer}, strides[1] = {row_stride_bytes};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_nd(out, elem_bytes, base, 2, dims, strides, box, swizzle_bytes);
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
