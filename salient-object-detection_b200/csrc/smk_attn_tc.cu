@@ -6,14 +6,17 @@
 //   warp 0      TMA producer: Q (one or two 128-row tiles), K and V boxes straight out of the projection outputs
 //               (strided tensor maps, no permute copy :113-118).  Q/K and V have separate full/empty barriers: Q and K are
 //               released as soon as both S = Q·K^T products retire, so the next item's loads overlap this item's softmax.
-//   warp 1      tcgen05.mma issuer: S_t = Q_t·K^T (UMMA 128 x nk x 64) into TMEM slot t, later O_t = P_t·V (V consumed
-//               as an MN-major operand from its TMA tile) into the same slot.
+//   warp 1      tcgen05.mma issuer.  S_t = Q_t·K^T (UMMA 128 x nk x 64, SS) into TMEM slot t; O_t = P_t·V with P_t read
+//               from TMEM (TS form: no shared-memory round trip for P) and V consumed as an MN-major operand from its
+//               TMA tile.  Issue order ping-pongs the two slots (PV0, next S0, PV1, next S1) so that one tile's MMAs and
+//               epilogue run under the other tile's softmax.
 //   warps 2-9   two softmax groups (one per query tile, 4 warps = the 4 TMEM lane quarters): one thread per query row,
-//               row max then exp2 in registers from tcgen05.ld, P (bf16) written to shared memory in the 128B-swizzled
-//               K-major layout; after O_t lands: O / rowsum → shared-memory staging → TMA tile store through a 3-D
-//               {column, row-in-image, image} tensor map, which clips the rows beyond the image's last query.
-// The MUFU exp2 (16/clk/SM) is the bound of this kernel, not the tensor pipe: 197x208 exponentials per (image, head)
-// against 1664 MMA cycles.
+//               row max then exp2 in registers from tcgen05.ld, P (bf16 pairs) written back over S with tcgen05.st;
+//               after O_t lands: O / rowsum → shared-memory staging → TMA tile store through a 3-D {column,
+//               row-in-image, image} tensor map, which clips the rows beyond the image's last query.
+// TMEM slot t (256 columns): S in [0, nk), P packed in [0, nk/2) (P chunk c overwrites S columns that are already in
+// registers), O in [128, 192) (S columns consumed before the first P·V MMA is issued).
+// The MUFU exp2 (16/clk/SM) and the TMEM read port bound this kernel, not the tensor pipe.
 #include "smk_tc.cuh"
 
 namespace smk {
@@ -23,10 +26,11 @@ using namespace tc;
 constexpr int AT_BM = 128, AT_DH = 64, AT_THREADS = 320, AT_TMEM_COLS = 512, AT_MAXK = 256;
 constexpr int AT_Q_BYTES = 2 * AT_BM * 128;          // two query tiles
 constexpr int AT_KV_BYTES = AT_MAXK * 128;           // up to 256 keys x 64 dims bf16
-constexpr int AT_P_BYTES = (AT_MAXK / 64) * 16384;   // per query tile: 4 key blocks of 128 rows x 128 B
-constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_P = AT_OFF_V + AT_KV_BYTES;
-constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_P_BYTES;
+constexpr int AT_STG_BYTES = 8192;                   // per softmax warp: 32 rows x 256 B (64 fp32) output staging
+constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_STG = AT_OFF_V + AT_KV_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_STG + 8 * AT_STG_BYTES;
 constexpr int AT_SMEM = AT_OFF_BAR + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int AT_O_COL = 128;                        // O accumulator columns within a slot
 static_assert(AT_SMEM <= 227 * 1024, "attention shared memory budget");
 
 struct AttnTcParams {
@@ -49,10 +53,10 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// optional phase trace of CTA 0 (debug builds of the tuning scripts only): [item < 16][warp 10][event 8] clock64 stamps
+// optional phase trace of CTA 0 (tuning scripts only): [item < 16][warp 10][event 8] clock64 stamps
 __device__ long long* g_attn_trace = nullptr;
-#define AT_TRACE(ev)                                                                                         \
-  do {                                                                                                       \
+#define AT_TRACE(ev)                                                                                                     \
+  do {                                                                                                                   \
     if (g_attn_trace && blockIdx.x == 0 && lane == 0 && it < 16) g_attn_trace[(it * 10 + warp) * 8 + (ev)] = clock64(); \
   } while (0)
 
@@ -71,6 +75,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = p.n_qtiles;
+  const int n_my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -88,64 +93,70 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const uint32_t q_bytes = (uint32_t)nt * AT_BM * 128u, kv_bytes = (uint32_t)p.nk_pad * 128u;
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int b = item / p.heads, h = item % p.heads;
-        const int kv_row = b * p.kv_rows + p.kv_row0;
-        mbar_wait(qk_empty, (it & 1) ^ 1);
-        AT_TRACE(0);
-        mbar_arrive_expect_tx(qk_full, q_bytes + kv_bytes);
-        tma_load_2d(sQ, &tmQ, qk_full, h * AT_DH, b * p.q_rows);
-        tma_load_2d(sK, &tmK, qk_full, h * AT_DH, kv_row);
-        mbar_wait(v_empty, (it & 1) ^ 1);
-        AT_TRACE(1);
-        mbar_arrive_expect_tx(v_full, kv_bytes);
-        tma_load_2d(sV, &tmV, v_full, h * AT_DH, kv_row);
-      }
+    // ===== TMA producer (whole warp, one elected lane issues) =====
+    const uint32_t q_bytes = (uint32_t)nt * AT_BM * 128u, kv_bytes = (uint32_t)p.nk_pad * 128u;
+    for (int it = 0; it < n_my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / p.heads, h = item % p.heads;
+      const int kv_row = b * p.kv_rows + p.kv_row0;
+      mbar_wait(qk_empty, (it & 1) ^ 1);
+      AT_TRACE(0);
+      mbar_arrive_expect_tx_w(qk_full, q_bytes + kv_bytes);
+      tma_load_2d_w(sQ, &tmQ, qk_full, h * AT_DH, b * p.q_rows);
+      tma_load_2d_w(sK, &tmK, qk_full, h * AT_DH, kv_row);
+      mbar_wait(v_empty, (it & 1) ^ 1);
+      AT_TRACE(1);
+      mbar_arrive_expect_tx_w(v_full, kv_bytes);
+      tma_load_2d_w(sV, &tmV, v_full, h * AT_DH, kv_row);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
-      const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_DH, 0, 1);
-      const uint64_t kd = smem_desc_k_sw128(smem_u32(sK));
-      const uint32_t va = smem_u32(sV);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const uint32_t par = it & 1;
-        mbar_wait(qk_full, par);
-        AT_TRACE(0);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(&o_drained[t], par ^ 1);      // slot t: the previous item's O has been read out
-          AT_TRACE(1 + t);
-          tc_fence_after_sync();
-          const uint64_t qd = smem_desc_k_sw128(smem_u32(sQ + t * AT_BM * 128));
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+    // ===== MMA issuer (whole warp stays convergent; one elected lane issues each tcgen05 instruction) =====
+    const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
+    const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_DH, 0, 1);
+    const uint64_t kd = smem_desc_k_sw128(smem_u32(sK));
+    const uint64_t vd0 = smem_desc_mn_sw128(smem_u32(sV), 1024);
+    const int n_ksteps = p.nk_pad / 16;
+    auto issue_s = [&](int t) {               // S_t = Q_t · K^T
+      const uint64_t qd = smem_desc_k_sw128(smem_u32(sQ + t * AT_BM * 128));
+      const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
 #pragma unroll
-          for (int k = 0; k < AT_DH / 16; ++k) umma_bf16_ss(d_tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
-          tc_commit(&s_full[t]);
-        }
-        tc_commit(qk_empty);                      // Q and K may be overwritten once both S products retire
-        mbar_wait(v_full, par);
-        AT_TRACE(3);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(&p_full[t], par);             // P_t is in shared memory and S_t has been fully read
-          AT_TRACE(4 + t);
+      for (int k = 0; k < AT_DH / 16; ++k) umma_bf16_ss_w(d_tmem, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_s, k != 0);
+      tc_commit_w(&s_full[t]);
+    };
+    auto issue_pv = [&](int t) {              // O_t = P_t · V, P_t from TMEM (8 packed columns per 16 keys)
+      const uint32_t slot = tmem_base + (uint32_t)(t * 256);
+#pragma unroll 4
+      for (int j = 0; j < n_ksteps; ++j)      // V: +2048 B per 16 keys → +128 in the descriptor's (addr >> 4) field
+        umma_bf16_ts_w(slot + AT_O_COL, slot + (uint32_t)(j * 8), vd0 + (uint64_t)(j * 128), idesc_o, j != 0);
+      tc_commit_w(&o_full[t]);
+    };
+    if (n_my_items > 0) {
+      const int it = 0;
+      mbar_wait(qk_full, 0);
+      tc_fence_after_sync();
+      AT_TRACE(0);
+      for (int t = 0; t < nt; ++t) issue_s(t);
+      tc_commit_w(qk_empty);                  // Q and K may be overwritten once both S products retire
+    }
+    for (int it = 0; it < n_my_items; ++it) {
+      const uint32_t par = it & 1;
+      const bool has_next = it + 1 < n_my_items;
+      mbar_wait(v_full, par);
+      AT_TRACE(1);
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait(&p_full[t], par);           // P_t is in TMEM and S_t has been fully read
+        tc_fence_after_sync();
+        AT_TRACE(2 + 2 * t);
+        issue_pv(t);
+        if (t == nt - 1) tc_commit_w(v_empty);
+        if (has_next) {
+          if (t == 0) mbar_wait(qk_full, par ^ 1);
+          mbar_wait(&o_drained[t], par);      // slot t: this item's O has been read out
           tc_fence_after_sync();
-          const uint32_t pa = smem_u32(smem + AT_OFF_P + t * AT_P_BYTES);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
-          for (int j = 0; j < p.nk_pad / 16; ++j) {
-            const uint64_t pd = smem_desc_k_sw128(pa + (uint32_t)((j >> 2) * 16384 + (j & 3) * 32));
-            const uint64_t vd = smem_desc_mn_sw128(va + (uint32_t)(j * 2048), 1024);
-            umma_bf16_ss(d_tmem, pd, vd, idesc_o, j != 0);
-          }
-          tc_commit(&o_full[t]);
+          AT_TRACE(3 + 2 * t);
+          issue_s(t);
+          if (t == nt - 1) tc_commit_w(qk_empty);
         }
-        tc_commit(v_empty);
-        AT_TRACE(6);
       }
     }
   } else {
@@ -153,31 +164,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
     if (t < nt) {
-      const int r = quarter * 32 + lane;             // row within the tile = TMEM lane
       const int row0 = t * AT_BM + quarter * 32;     // first query row (within the image) of this warp
       const bool active = row0 < p.Lq;               // warps past the last query only keep the barrier protocol going
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 256);
-      const uint32_t sP = smem_u32(smem + AT_OFF_P + t * AT_P_BYTES);
-      const uint32_t prow = sP + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-      const uint32_t x7s = (uint32_t)(r & 7) << 4;   // 128-byte swizzle: 16-byte chunk index ^= row & 7
-      // epilogue staging (P_t is dead once O_t has landed): this warp's own 4 KB of P rows in key blocks 0 and 1, so that no
-      // other warp's next-item P writes can touch a tile the TMA store is still reading
-      const uint32_t stg = sP + (uint32_t)(quarter * 4096);
-      constexpr uint32_t kStg2 = 16384;
+      const uint32_t x7s = (uint32_t)(lane & 7) << 4;   // 128-byte swizzle of the staging tile: 16-byte chunk index ^= row & 7
+      uint8_t* stg_ptr = smem + AT_OFF_STG + (warp - 2) * AT_STG_BYTES;
+      const uint32_t stg = smem_u32(stg_ptr);
       const int n_full = p.Lk >> 5;                  // 32-column chunks of valid keys
       const int n_tail = (p.nk_pad - n_full * 32) >> 4;   // 0..2 trailing 16-column pieces holding the last valid keys + padding
       const float sc = p.scale_log2e;
-      // P row store: 8 keys (16 bytes) starting at key0 (multiple of 8)
-      auto store8 = [&](int key0, float e0, float e1, float e2, float e3, float e4, float e5, float e6, float e7) {
-        const uint32_t a = prow + (uint32_t)((key0 >> 6) * 16384) + ((((uint32_t)(key0 & 63) >> 3) << 4) ^ x7s);
-        st_shared_v4(a, pack_bf16x2(e0, e1), pack_bf16x2(e2, e3), pack_bf16x2(e4, e5), pack_bf16x2(e6, e7));
-      };
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      for (int it = 0; it < n_my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
         const uint32_t par = it & 1;
         const int b = item / p.heads, h = item % p.heads;
-        if (active && lane == 0) bulk_wait_read<0>();   // previous item's output tile has left the staging area
-        __syncwarp();
         AT_TRACE(0);
         mbar_wait(&s_full[t], par);
         tc_fence_after_sync();
@@ -215,7 +214,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           const float mxs = fmaxf(m0, m1) * sc;
           AT_TRACE(2);
-          // ---- pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P → smem (bf16, K-major, 128B swizzle) ----
+          // ---- pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P (bf16 pairs) → TMEM columns [16c, 16c+16) ----
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           auto exp32 = [&](uint32_t (&v)[32], int c) {
             float e[32];
@@ -223,9 +222,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mxs));
 #pragma unroll
             for (int j = 0; j < 32; j += 4) { s0 += e[j]; s1 += e[j + 1]; s2 += e[j + 2]; s3 += e[j + 3]; }
+            uint32_t pk[16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              store8(c * 32 + g * 8, e[g * 8], e[g * 8 + 1], e[g * 8 + 2], e[g * 8 + 3], e[g * 8 + 4], e[g * 8 + 5], e[g * 8 + 6], e[g * 8 + 7]);
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+            tmem_st_32x16(taddr + (uint32_t)(c * 16), pk);
           };
           if (n_full > 0) tmem_ld_32x32(taddr, va);
           for (int c = 0; c < n_full; c += 2) {
@@ -248,13 +248,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               e[j] = (col0 + j < p.Lk) ? ex2_approx(fmaf(__uint_as_float(vt[j]), sc, -mxs)) : 0.f;
               s0 += e[j];
             }
-            store8(col0, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
-            store8(col0 + 8, e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15]);
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+            tmem_st_32x8(taddr + (uint32_t)(col0 >> 1), pk);
           }
           sum = (s0 + s1) + (s2 + s3);
+          tmem_st_wait();
         }
-        fence_proxy_async();            // generic-proxy smem writes → visible to the tensor core (async proxy)
-        tc_fence_before_sync();         // our TMEM reads of S are ordered before the PV MMAs that overwrite it
+        tc_fence_before_sync();         // our TMEM reads of S / writes of P are ordered before the PV MMAs
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
         AT_TRACE(3);
@@ -264,8 +266,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         AT_TRACE(4);
         uint32_t oa[32], ob[32];
         if (active) {
-          tmem_ld_32x32(taddr, oa);
-          tmem_ld_32x32(taddr + 32u, ob);
+          tmem_ld_32x32(taddr + AT_O_COL, oa);
+          tmem_ld_32x32(taddr + AT_O_COL + 32u, ob);
           tmem_ld_wait32(oa);
           tmem_ld_wait32(ob);
         }
@@ -274,20 +276,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&o_drained[t]);       // slot t may receive the next item's S
         AT_TRACE(5);
         if (active) {
+          if (lane == 0) bulk_wait_read<0>();            // the previous item's output tile has left the staging buffer
+          __syncwarp();
           const float inv = 1.0f / sum;
           auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
+          const uint32_t srow = stg + lane * 128;
           if (p.out_f32) {
             // two 32-column fp32 boxes of 32 rows x 128 B each, 128-byte swizzle
-            const uint32_t srow = stg + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(oa[4 * j])), __float_as_uint(f(oa[4 * j + 1])),
                            __float_as_uint(f(oa[4 * j + 2])), __float_as_uint(f(oa[4 * j + 3])));
-              st_shared_v4(srow + kStg2 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
+              st_shared_v4(srow + 4096 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
                            __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
             }
           } else {
-            const uint32_t srow = stg + lane * 128;        // one 64-column bf16 box of 32 rows x 128 B
+            // one 64-column bf16 box of 32 rows x 128 B
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), pack_bf16x2(f(oa[8 * j]), f(oa[8 * j + 1])), pack_bf16x2(f(oa[8 * j + 2]), f(oa[8 * j + 3])),
@@ -299,8 +303,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmO, smem + (stg - smem_u32(smem)), h * AT_DH, row0, b);
-            if (p.out_f32) tma_store_3d(&tmO, smem + (stg + kStg2 - smem_u32(smem)), h * AT_DH + 32, row0, b);
+            tma_store_3d(&tmO, stg_ptr, h * AT_DH, row0, b);
+            if (p.out_f32) tma_store_3d(&tmO, stg_ptr + 4096, h * AT_DH + 32, row0, b);
             bulk_commit();
           }
         }
