@@ -93,6 +93,44 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, floa
   return __fmaf_rn(top, ly0, __fmul_rn(bot, ly1));
 }
 
+// x4 specialisation (the evaluator's scale_factor=4 and the shipped pixel decoder): the 4 outputs x = 4i .. 4i+3 of one row
+// only read source columns {max(i-1,0), i, min(i+1,w-1)} — outputs 0,1 blend (left, centre), outputs 2,3 blend (centre,
+// right).  Where make_tap() clamps (first / last source column) the clamped pair holds the same value twice, so the
+// result is bit-identical to the generic tap (a*l0 + a*l1 paths only differ when the weights are exactly 1 and 0).
+struct QuadX {
+  int cm, cc, cp;
+  float l0[4], l1[4];
+};
+__device__ __forceinline__ QuadX make_quadx(int i, int w) {
+  QuadX q;
+  q.cm = max(i - 1, 0);
+  q.cc = min(i, w - 1);
+  q.cp = min(i + 1, w - 1);
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const Tap t = make_tap(4 * i + f, 0.25f, w);
+    q.l0[f] = t.l0;
+    q.l1[f] = t.l1;
+  }
+  return q;
+}
+__device__ __forceinline__ void quad4(const float* __restrict__ r0, const float* __restrict__ r1, const QuadX& q, float ly0, float ly1,
+                                      float (&out)[4]) {
+  const float am = r0[q.cm], ac = r0[q.cc], ap = r0[q.cp];
+  const float bm = r1[q.cm], bc = r1[q.cc], bp = r1[q.cp];
+  out[0] = bilerp(am, ac, bm, bc, q.l0[0], q.l1[0], ly0, ly1);
+  out[1] = bilerp(am, ac, bm, bc, q.l0[1], q.l1[1], ly0, ly1);
+  out[2] = bilerp(ac, ap, bc, bp, q.l0[2], q.l1[2], ly0, ly1);
+  out[3] = bilerp(ac, ap, bc, bp, q.l0[3], q.l1[3], ly0, ly1);
+}
+// sigmoid with MUFU.EX2 + MUFU.RCP (≈3 ulp): 1 / (1 + 2^(-x·log2 e))
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace smk

@@ -283,6 +283,241 @@ mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// x4 fast paths (up == 4, W % 4 == 0, W <= 1024): a thread owns one source column i — the 4 full-resolution pixels
+// 4i .. 4i+3 of a row come from 6 shared-memory reads (quad4) and one 4-byte ground-truth load — and walks rows
+// y = ys, ys + YS, ...  Same arithmetic as the generic kernels (make_tap + bilerp), so every count is identical.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEvalThreads)
+query_iou_x4_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
+                    int nq, int hp, int wp, int H, int W, int32_t* __restrict__ q_counts) {
+  extern __shared__ float plane[];
+  __shared__ int red[kEvalWarps];
+  const int q = blockIdx.x, b = blockIdx.y;
+  const float* src = mask_pred + (int64_t)b * batch_stride + (int64_t)q * hp * wp;
+  for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) plane[i] = src[i];
+  __syncthreads();
+  const int Q4 = W >> 2, YS = kEvalThreads / Q4;
+  const int i = threadIdx.x % Q4, ys = threadIdx.x / Q4;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+  int inter = 0, npred = 0, ngt = 0;
+  if (ys < YS) {
+    const QuadX qx = make_quadx(i, wp);
+    for (int y = ys; y < H; y += YS) {
+      const Tap ty = make_tap(y, 0.25f, hp);
+      float v[4];
+      quad4(plane + ty.i0 * wp, plane + ty.i1 * wp, qx, ty.l0, ty.l1, v);
+      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + 4 * i);
+      const unsigned pm = (v[0] > 0.5f ? 1u : 0u) | (v[1] > 0.5f ? 2u : 0u) | (v[2] > 0.5f ? 4u : 0u) | (v[3] > 0.5f ? 8u : 0u);
+      const unsigned tm = (gq.x ? 1u : 0u) | (gq.y ? 2u : 0u) | (gq.z ? 4u : 0u) | (gq.w ? 8u : 0u);
+      inter += __popc(pm & tm);
+      npred += __popc(pm);
+      ngt += __popc(tm);
+    }
+  }
+  inter = block_sum_int(inter, red);
+  npred = block_sum_int(npred, red);
+  ngt = block_sum_int(ngt, red);
+  if (threadIdx.x == 0) {
+    int32_t* o = q_counts + ((int64_t)b * nq + q) * SMK_QCOUNT_STRIDE;
+    o[0] = inter;
+    o[1] = npred + ngt - inter;   // |p ∪ g|
+  }
+}
+
+// all reductions for the objectness-selected (blockIdx.x == 0) and best-IoU (1) mask of image blockIdx.y
+__global__ void __launch_bounds__(kEvalThreads)
+mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
+                       int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
+                       int nq, int hp, int wp, int H, int W, const float* __restrict__ thresholds,
+                       int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
+  extern __shared__ float dyn[];
+  __shared__ int hist[kEvalWarps][512];
+  __shared__ float thr[256];
+  __shared__ int red_i[kEvalWarps];
+  __shared__ double red_d[kEvalWarps];
+  __shared__ int s_sel;
+  const int which = blockIdx.x, b = blockIdx.y;
+  const int n_masks = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    int sel = 0;
+    if (which == 0) {           // objectness top-1 (evaluator.pyc@L219-221); lowest index on ties
+      const float* ob = objectness + (int64_t)b * obj_stride;
+      float best = ob[0];
+      for (int i = 1; i < nq; ++i)
+        if (ob[i] > best) { best = ob[i]; sel = i; }
+    } else {                    // upper bound: argmax_q I/(U+1e-7) in float32, first maximum
+      const int32_t* qc = q_counts + (int64_t)b * nq * SMK_QCOUNT_STRIDE;
+      float best = -1.0f;
+      for (int i = 0; i < nq; ++i) {
+        float iou = __fdiv_rn((float)qc[2 * i], __fadd_rn((float)qc[2 * i + 1], 1e-7f));
+        if (iou > best) { best = iou; sel = i; }
+      }
+    }
+    idx_out[(int64_t)b * 2 + which] = sel;
+    s_sel = sel;
+  }
+  for (int i = threadIdx.x; i < kEvalWarps * 512; i += kEvalThreads) (&hist[0][0])[i] = 0;
+  if (threadIdx.x < 255) thr[threadIdx.x] = thresholds[threadIdx.x];
+  if (threadIdx.x == 255) thr[255] = 3.0e38f;
+  __syncthreads();
+  const int sel = s_sel;
+  const float* src = planes + (int64_t)b * batch_stride + (int64_t)sel * hp * wp;
+  for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) dyn[i] = src[i];
+  __syncthreads();
+  const float* pl = dyn;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+  const int Q4 = W >> 2, YS = kEvalThreads / Q4;
+  const int qi = threadIdx.x % Q4, ys = threadIdx.x / Q4;
+  const bool active = ys < YS;
+  const int n_iter = (H + YS - 1) / YS;        // uniform trip count: the histogram uses warp collectives
+  const int x0 = 4 * qi;
+
+  // ---- pass A over the ground truth: area and centroid (s_measure.py:11-31) -----------------
+  int ng = 0, sxg = 0, syg = 0;
+  if (active) {
+    for (int y = ys; y < H; y += YS) {
+      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
+      const int t0 = gq.x != 0, t1 = gq.y != 0, t2 = gq.z != 0, t3 = gq.w != 0;
+      const int rowc = t0 + t1 + t2 + t3;
+      ng += rowc;
+      sxg += rowc * x0 + t1 + 2 * t2 + 3 * t3;
+      syg += rowc * y;
+    }
+  }
+  ng = block_sum_int(ng, red_i);
+  sxg = block_sum_int(sxg, red_i);
+  syg = block_sum_int(syg, red_i);
+  int X, Y;
+  if (ng == 0) {   // python round(cols / 2): half-to-even
+    X = (int)rint((double)W / 2.0);
+    Y = (int)rint((double)H / 2.0);
+  } else {         // torch.round(float32 ratio): half-to-even
+    X = (int)rintf(__fdiv_rn((float)sxg, (float)ng));
+    Y = (int)rintf(__fdiv_rn((float)syg, (float)ng));
+  }
+  const int n_left = min(max(X - x0, 0), 4);   // how many of this thread's 4 pixels lie left of the centroid column
+
+  // ---- pass B: histograms, counts at 0.5, moments ---------------------------------------------
+  const QuadX qx = make_quadx(active ? qi : 0, wp);
+  double sabs = 0, fg_p = 0, fg_p2 = 0, bg_q = 0, bg_q2 = 0;
+  double p_all = 0, p_l = 0, p_t = 0, p_tl = 0, p2_all = 0, p2_l = 0, p2_t = 0, p2_tl = 0, pg_all = 0, pg_l = 0, pg_t = 0, pg_tl = 0;
+  int g_l = 0, g_t = 0, g_tl = 0, tp05 = 0, tpfp05 = 0;
+  int* myhist = hist[warp];
+  for (int k = 0; k < n_iter; ++k) {
+    const int y = ys + k * YS;
+    const bool valid = active && y < H;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned tm = 0;
+    if (valid) {
+      const Tap ty = make_tap(y, 0.25f, hp);
+      quad4(pl + ty.i0 * wp, pl + ty.i1 * wp, qx, ty.l0, ty.l1, v);
+      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
+      tm = (gq.x ? 1u : 0u) | (gq.y ? 2u : 0u) | (gq.z ? 4u : 0u) | (gq.w ? 8u : 0u);
+    }
+    double qp = 0, qp2 = 0, qpg = 0, lp = 0, lp2 = 0, lpg = 0;
+    int lg_ = 0;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const float vv = v[f];
+      const int t = (tm >> f) & 1;
+      // bin = #{k : t_k < v}, exact float32 thresholds, strict compare (f_measure.py:65, :45)
+      int kb = min(max((int)(vv * 255.0f), 0), 255);
+      while (kb < 255 && thr[kb] < vv) ++kb;
+      while (kb > 0 && !(thr[kb - 1] < vv)) --kb;
+      const int key = valid ? (t ? kb : 256 + kb) : 1024;
+      const int first = __shfl_sync(0xffffffffu, key, 0);
+      if (__all_sync(0xffffffffu, key == first)) {       // saturated regions: one add for the whole warp
+        if (lane == 0 && first < 512) atomicAdd(&myhist[first], 32);
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&myhist[key], __popc(peers));
+      }
+      if (valid) {
+        const int p = vv > 0.5f;
+        tp05 += p & t;
+        tpfp05 += p;
+        const double dv = (double)vv, dv2 = dv * dv, dg = t ? dv : 0.0;
+        if (t) { fg_p += dv; fg_p2 += dv2; sabs += 1.0 - dv; }
+        else   { const double w = 1.0 - dv; bg_q += w; bg_q2 += w * w; sabs += dv; }
+        qp += dv; qp2 += dv2; qpg += dg;
+        if (f < n_left) { lp += dv; lp2 += dv2; lpg += dg; lg_ += t; }
+      }
+    }
+    if (valid) {
+      const int qg = __popc(tm);
+      p_all += qp; p2_all += qp2; pg_all += qpg;
+      p_l += lp; p2_l += lp2; pg_l += lpg; g_l += lg_;
+      if (y < Y) { p_t += qp; p2_t += qp2; pg_t += qpg; g_t += qg; p_tl += lp; p2_tl += lp2; pg_tl += lpg; g_tl += lg_; }
+    }
+  }
+  const int64_t mrow = (int64_t)b * n_masks + which;
+  int32_t* oc = m_counts + mrow * SMK_MCOUNT_STRIDE;
+  double* os = m_sums + mrow * SMK_MSUM_STRIDE;
+
+  const double sp = block_sum_double(p_all, red_d);
+  sabs = block_sum_double(sabs, red_d);
+  fg_p = block_sum_double(fg_p, red_d); fg_p2 = block_sum_double(fg_p2, red_d);
+  bg_q = block_sum_double(bg_q, red_d); bg_q2 = block_sum_double(bg_q2, red_d);
+  p_l = block_sum_double(p_l, red_d); p_t = block_sum_double(p_t, red_d); p_tl = block_sum_double(p_tl, red_d);
+  p2_all = block_sum_double(p2_all, red_d); p2_l = block_sum_double(p2_l, red_d);
+  p2_t = block_sum_double(p2_t, red_d); p2_tl = block_sum_double(p2_tl, red_d);
+  pg_all = block_sum_double(pg_all, red_d); pg_l = block_sum_double(pg_l, red_d);
+  pg_t = block_sum_double(pg_t, red_d); pg_tl = block_sum_double(pg_tl, red_d);
+  g_l = block_sum_int(g_l, red_i); g_t = block_sum_int(g_t, red_i); g_tl = block_sum_int(g_tl, red_i);
+  tp05 = block_sum_int(tp05, red_i); tpfp05 = block_sum_int(tpfp05, red_i);
+  p_all = sp;
+
+  // F-mean threshold (f_measure.py:76): 2 * mean(p) in float32
+  const int npix = H * W;
+  const float tau = 2.0f * (float)(sp / (double)npix);
+
+  // ---- pass C: counts at the adaptive threshold -----------------------------------------------
+  int tpm = 0, tpfpm = 0;
+  if (active) {
+    for (int y = ys; y < H; y += YS) {
+      const Tap ty = make_tap(y, 0.25f, hp);
+      float v[4];
+      quad4(pl + ty.i0 * wp, pl + ty.i1 * wp, qx, ty.l0, ty.l1, v);
+      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
+      const unsigned pm = (v[0] > tau ? 1u : 0u) | (v[1] > tau ? 2u : 0u) | (v[2] > tau ? 4u : 0u) | (v[3] > tau ? 8u : 0u);
+      const unsigned tm = (gq.x ? 1u : 0u) | (gq.y ? 2u : 0u) | (gq.z ? 4u : 0u) | (gq.w ? 8u : 0u);
+      tpm += __popc(pm & tm);
+      tpfpm += __popc(pm);
+    }
+  }
+  tpm = block_sum_int(tpm, red_i);
+  tpfpm = block_sum_int(tpfpm, red_i);
+
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += kEvalThreads) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalWarps; ++w) s += hist[w][i];
+    oc[i] = s;
+  }
+  if (threadIdx.x == 0) {
+    oc[512] = tp05; oc[513] = tpfp05; oc[514] = ng; oc[515] = tpm; oc[516] = tpfpm;
+    oc[517] = X; oc[518] = Y; oc[519] = npix; oc[520] = sel;
+    for (int i = 521; i < SMK_MCOUNT_STRIDE; ++i) oc[i] = 0;
+    os[0] = sp; os[1] = sabs; os[2] = (double)tau; os[3] = fg_p; os[4] = fg_p2; os[5] = bg_q; os[6] = bg_q2; os[7] = 0;
+    // quadrants LT, RT, LB, RB (s_measure.py:71-94): [:Y,:X] [:Y,X:] [Y:,:X] [Y:,X:]
+    const int Xc = min(max(X, 0), W), Yc = min(max(Y, 0), H);
+    const double n_q[4] = {(double)Xc * Yc, (double)(W - Xc) * Yc, (double)Xc * (H - Yc), (double)(W - Xc) * (H - Yc)};
+    const double sp_q[4] = {p_tl, p_t - p_tl, p_l - p_tl, p_all - p_t - p_l + p_tl};
+    const double sp2_q[4] = {p2_tl, p2_t - p2_tl, p2_l - p2_tl, p2_all - p2_t - p2_l + p2_tl};
+    const double spg_q[4] = {pg_tl, pg_t - pg_tl, pg_l - pg_tl, pg_all - pg_t - pg_l + pg_tl};
+    const double sg_q[4] = {(double)g_tl, (double)(g_t - g_tl), (double)(g_l - g_tl), (double)(ng - g_t - g_l + g_tl)};
+    for (int qd = 0; qd < 4; ++qd) {
+      os[8 + 5 * qd + 0] = n_q[qd]; os[8 + 5 * qd + 1] = sp_q[qd]; os[8 + 5 * qd + 2] = sp2_q[qd];
+      os[8 + 5 * qd + 3] = sg_q[qd]; os[8 + 5 * qd + 4] = spg_q[qd];
+    }
+    for (int i = 28; i < SMK_MSUM_STRIDE; ++i) os[i] = 0;
+  }
+}
+
 __global__ void upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w, int up,
                                          int H, int W) {
   // grid (ceil(H/8), n); 256 threads = 8 rows of one plane per CTA, lanes along x
@@ -327,16 +562,28 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
+  const bool x4 = up == 4 && (W % 4) == 0 && W <= 4 * kEvalThreads && ((uintptr_t)gt % 4) == 0;
+  if (x4 && plane_bytes > 24 * 1024) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
+  }
   {
     // algorithmic bytes "as if materialised" (SURVEY.md §8d): every full-resolution mask pixel (fp32) + the GT plane
     ProfScope prof(PROF_EVAL, (double)B * ((double)nq * H * W * 4.0 + (double)H * W), s);
-    query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
+    if (x4)
+      query_iou_x4_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, H, W, q_counts);
+    else
+      query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
   }
   SMK_CHECK_LAUNCH();
   {
     ProfScope prof(PROF_EVAL, (double)B * 2.0 * ((double)H * W * 4.0 + (double)H * W), s);
-    mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
-        mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
+    if (x4)
+      mask_metrics_x4_kernel<<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq,
+                                                                          hp, wp, H, W, g_thresholds, idx, m_counts, m_sums);
+    else
+      mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
+          mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;

@@ -434,51 +434,138 @@ int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaS
 // Mask head (maskformer.py:144-162, :223): logits at patch resolution = queries · memory^T, then the
 // pixel decoder's bilinear xsf applied to the nq-channel logits (bilinear is linear and per-channel, so
 // it commutes with the contraction — SURVEY.md K12), sigmoid, store mask_pred[b,l,q,:,:].
-// grid (L, B), 256 threads.  dynamic smem: nq*D (queries) + nq*hw (logits) floats.
+// grid (layer groups, B), 256 threads.  One CTA owns R = (layers per group) x nq query rows of one image:
+//   stage 1  logits[R][hw] = Q[R][D] · T[hw][D]^T in fp32, register-tiled (8 rows x 4 tokens per thread and tile),
+//            K streamed through shared memory in chunks of 32 (float4 reads, conflict-free row stride 36);
+//   stage 2  each warp produces full output rows: x sf bilinear of the logits plane held in shared memory, sigmoid,
+//            coalesced 128-byte stores (the only HBM traffic that matters: nq x (hp sf) x (wp sf) x 4 B per layer).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int MH_KC = 32, MH_LD = MH_KC + 4, MH_MAXT_CAP = 3, MH_THREADS = 256;
+
+template <int MH_MAXT>   // (8 rows x 4 tokens) register tiles per thread: 1 at 224x224 (245 tiles), up to 3 at 384x384
+__global__ void __launch_bounds__(MH_THREADS, MH_MAXT == 1 ? 3 : 1)
 mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const float* __restrict__ tokens /*[B,N,D] final LN*/,
-                 float* __restrict__ mask_pred /*[B,L,nq,hp*sf,wp*sf]*/, float* __restrict__ logits_out, int B, int nq, int D,
-                 int hp, int wp, int sf, int layer0) {
+                 float* __restrict__ mask_pred /*[B,L,nq,hp*sf,wp*sf]*/, float* __restrict__ logits_out, int B, int L, int Lg, int nq,
+                 int D, int hp, int wp, int sf, int layer0) {
   extern __shared__ float sm[];
-  float* qs = sm;                 // [nq][D]
-  float* lg = sm + nq * D;        // [nq][hw]
-  const int l = blockIdx.x, b = blockIdx.y, L = gridDim.x;
   const int hw = hp * wp, N = hw + 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* qsrc = queries + (((int64_t)(layer0 + l) * B + b) * nq) * D;
-  for (int i = threadIdx.x; i < nq * D; i += 256) qs[i] = qsrc[i];
-  __syncthreads();
-  const float* mem = tokens + ((int64_t)b * N + 1) * D;   // skip the cls token (maskformer.py:104)
-  const int per_lane = D / 32;                            // D = 384 → 12
-  for (int n = warp; n < hw; n += 8) {
-    float mv[16];
+  const int b = blockIdx.y, l0 = blockIdx.x * Lg;          // first output layer of this CTA
+  const int nl = min(Lg, L - l0), R = nl * nq;             // query rows owned
+  const int RO = (R + 7) / 8, R8 = RO * 8;                 // row octets
+  const int NQ4 = (hw + 3) / 4;                            // token quads (token n = tq + NQ4 * i, i < 4)
+  float* lg = sm;                                          // [R][hw]
+  float* As = lg + (size_t)Lg * nq * hw;                   // [R8][MH_LD]
+  float* Ts = As + (size_t)((Lg * nq + 7) / 8 * 8) * MH_LD;   // [NQ4 * 4][MH_LD]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* mem = tokens + ((int64_t)b * N + 1) * D;    // skip the cls token (maskformer.py:104)
+  const int n_tiles = RO * NQ4;
+
+  float acc[MH_MAXT][8][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) mv[j] = (j < per_lane) ? mem[(int64_t)n * D + lane + 32 * j] : 0.f;
-    for (int qi = 0; qi < nq; ++qi) {
-      float s = 0.f;
+  for (int t = 0; t < MH_MAXT; ++t)
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < per_lane) s = fmaf(mv[j], qs[qi * D + lane + 32 * j], s);
-      s = warp_sum(s);
-      if (lane == 0) lg[qi * hw + n] = s;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[t][j][i] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += MH_KC) {
+    __syncthreads();
+    for (int i = tid; i < R8 * (MH_KC / 4); i += MH_THREADS) {
+      const int r = i / (MH_KC / 4), c = i % (MH_KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R) {
+        const int l = layer0 + l0 + r / nq, q = r % nq;
+        v = *reinterpret_cast<const float4*>(queries + (((int64_t)l * B + b) * nq + q) * D + k0 + 4 * c);
+      }
+      *reinterpret_cast<float4*>(As + r * MH_LD + 4 * c) = v;
+    }
+    for (int i = tid; i < NQ4 * 4 * (MH_KC / 4); i += MH_THREADS) {
+      const int n = i / (MH_KC / 4), c = i % (MH_KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < hw) v = *reinterpret_cast<const float4*>(mem + (int64_t)n * D + k0 + 4 * c);
+      *reinterpret_cast<float4*>(Ts + n * MH_LD + 4 * c) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < MH_MAXT; ++t) {
+      const int tile = tid + t * MH_THREADS;
+      if (tile < n_tiles) {
+        const int ro = tile / NQ4, tq = tile % NQ4;
+        const float* ap = As + ro * 8 * MH_LD;
+        const float* tp = Ts + tq * MH_LD;
+#pragma unroll 2
+        for (int k = 0; k < MH_KC; k += 4) {
+          float4 tv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tv[i] = *reinterpret_cast<const float4*>(tp + (size_t)i * NQ4 * MH_LD + k);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 av = *reinterpret_cast<const float4*>(ap + j * MH_LD + k);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float a = acc[t][j][i];
+              a = fmaf(av.x, tv[i].x, a);
+              a = fmaf(av.y, tv[i].y, a);
+              a = fmaf(av.z, tv[i].z, a);
+              a = fmaf(av.w, tv[i].w, a);
+              acc[t][j][i] = a;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MH_MAXT; ++t) {
+    const int tile = tid + t * MH_THREADS;
+    if (tile < n_tiles) {
+      const int ro = tile / NQ4, tq = tile % NQ4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = ro * 8 + j;
+        if (r < R) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = tq + NQ4 * i;
+            if (n < hw) lg[r * hw + n] = acc[t][j][i];
+          }
+        }
+      }
     }
   }
   __syncthreads();
   const int Ho = hp * sf, Wo = wp * sf;
   const float rscale = 1.0f / (float)sf;
-  float* out = mask_pred + (((int64_t)b * L + l) * nq) * Ho * Wo;
-  float* lout = logits_out ? logits_out + (((int64_t)b * L + l) * nq) * Ho * Wo : nullptr;
-  for (int row = warp; row < nq * Ho; row += 8) {
-    const int qi = row / Ho, y = row % Ho;
-    const float* pl = lg + qi * hw;
+  float* out = mask_pred + (((int64_t)b * L + l0) * nq) * Ho * Wo;
+  float* lout = logits_out ? logits_out + (((int64_t)b * L + l0) * nq) * Ho * Wo : nullptr;
+  if (sf == 4 && wp <= MH_THREADS) {
+    // x4 fast path: a thread owns one source column i (4 output pixels per row, one 16-byte store) and walks output rows
+    const int i = tid % wp, rs = tid / wp, RS = MH_THREADS / wp;
+    if (rs < RS) {
+      const QuadX qx = make_quadx(i, wp);
+      for (int row = rs; row < R * Ho; row += RS) {
+        const int r = row / Ho, y = row % Ho;
+        const float* pl = lg + r * hw;
+        const Tap ty = make_tap(y, rscale, hp);
+        float z[4];
+        quad4(pl + ty.i0 * wp, pl + ty.i1 * wp, qx, ty.l0, ty.l1, z);
+        __stcs(reinterpret_cast<float4*>(out + (int64_t)row * Wo + 4 * i),
+               make_float4(sigmoid_fast(z[0]), sigmoid_fast(z[1]), sigmoid_fast(z[2]), sigmoid_fast(z[3])));
+        if (lout) *reinterpret_cast<float4*>(lout + (int64_t)row * Wo + 4 * i) = make_float4(z[0], z[1], z[2], z[3]);
+      }
+    }
+    return;
+  }
+  for (int row = warp; row < R * Ho; row += MH_THREADS / 32) {
+    const int r = row / Ho, y = row % Ho;
+    const float* pl = lg + r * hw;
     Tap ty = make_tap(y, rscale, hp);
     const float* r0 = pl + ty.i0 * wp;
     const float* r1 = pl + ty.i1 * wp;
     for (int x = lane; x < Wo; x += 32) {
       Tap tx = make_tap(x, rscale, wp);
       const float z = bilerp(r0[tx.i0], r0[tx.i1], r1[tx.i0], r1[tx.i1], tx.l0, tx.l1, ty.l0, ty.l1);
-      out[(int64_t)row * Wo + x] = sigmoidf_(z);
+      __stcs(out + (int64_t)row * Wo + x, sigmoid_fast(z));
       if (lout) lout[(int64_t)row * Wo + x] = z;
     }
   }
@@ -486,14 +573,24 @@ mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const floa
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq,
               int D, int hp, int wp, int sf, cudaStream_t s) {
   if (B == 0) return SMK_OK;
-  SMK_REQUIRE(D % 32 == 0 && D <= 512 && B <= 65535, "mask_head: D=%d unsupported", D);
-  const size_t smem = ((size_t)nq * D + (size_t)nq * hp * wp) * sizeof(float);
-  SMK_REQUIRE(smem <= 200 * 1024, "mask_head: %zu bytes of shared memory needed", smem);
-  if (smem > 48 * 1024) SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SMK_REQUIRE(D % MH_KC == 0 && B <= 65535, "mask_head: D=%d unsupported", D);
+  const int hw = hp * wp, NQ4 = (hw + 3) / 4;
+  // layers per CTA: as many as keep the row count <= 40 and the tile count within MH_MAXT per thread
+  int Lg = 40 / nq;
+  if (Lg < 1) Lg = 1;
+  if (Lg > L) Lg = L;
+  while (Lg > 1 && ((Lg * nq + 7) / 8) * NQ4 > MH_MAXT_CAP * MH_THREADS) --Lg;
+  const int n_tiles = ((Lg * nq + 7) / 8) * NQ4;
+  SMK_REQUIRE(n_tiles <= MH_MAXT_CAP * MH_THREADS, "mask_head: %d queries x %d patches exceed the register tiling", nq, hw);
+  const size_t smem = ((size_t)Lg * nq * hw + (size_t)((Lg * nq + 7) / 8 * 8) * MH_LD + (size_t)NQ4 * 4 * MH_LD) * sizeof(float);
+  SMK_REQUIRE(smem <= 220 * 1024, "mask_head: %zu bytes of shared memory needed", smem);
+  auto kern = n_tiles <= MH_THREADS ? mask_head_kernel<1> : mask_head_kernel<MH_MAXT_CAP>;
+  if (smem > 48 * 1024) SMK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     // algorithmic bytes: read tokens + queries, write the [nq, hp*sf, wp*sf] probability planes
     ProfScope prof(PROF_MASK_HEAD, (double)B * L * ((double)(hp * wp + nq) * D + (double)nq * hp * sf * wp * sf) * 4.0, s);
-    mask_head_kernel<<<dim3(L, B), 256, smem, s>>>(queries, tokens, mask_pred, logits_out, B, nq, D, hp, wp, sf, layer0);
+    kern<<<dim3((L + Lg - 1) / Lg, B), MH_THREADS, smem, s>>>(queries, tokens, mask_pred, logits_out, B, L, Lg, nq, D, hp, wp,
+                                                                           sf, layer0);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
