@@ -139,7 +139,8 @@ enum { SMK_EPI_NONE = 0, SMK_EPI_GELU = 1, SMK_EPI_RELU = 2, SMK_EPI_RESIDUAL = 
 /* C[M,N] = A[M,K] · W[N,K]^T + bias[N], fp32 on CUDA cores.  lda/ldc in elements. */
 int smk_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
                  int M, int N, int K, int epilogue, void* stream);
-/* bf16 tcgen05 GEMM: A [M,K] bf16 (lda), W [N,K] bf16; output bf16 (out_f32 = 0) or fp32 (1); fp32 accumulate.
+/* bf16 tcgen05 GEMM: A [M,K] bf16 (lda), W [N,K] bf16; fp32 accumulate.  out_f32: 0 = bf16 output, 1 = fp32 output,
+ * 2 = bf16x3 split output (row = [hi | hi | lo], 3N columns, ldc >= 3N: the A operand of a following split GEMM).
  * K % 64 == 0, N % 128 == 0. */
 int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* C, int64_t ldc,
                   int M, int N, int K, int epilogue, int out_f32, void* stream);
@@ -155,7 +156,8 @@ int smk_attention(const void* q, const void* k, const void* v, void* o, int batc
  * N <= 256 tokens per image (one key tile). */
 int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
 /* general form: q [B*Lq, ldq], k / v [kv_total_rows, ld] bf16 (head h at columns [h*64, h*64+64) of each pointer); image b's
- * queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0; out [B*Lq, ldo] fp32 (out_f32) or bf16. */
+ * queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0; out [B*Lq, ldo]: out_f32 0 = bf16, 1 = fp32,
+ * 2 = bf16x3 split ([hi | hi | lo], 3*heads*64 columns). */
 int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_total_rows,
                              int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk, int heads,
                              float scale, void* stream);

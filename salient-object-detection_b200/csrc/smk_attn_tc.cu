@@ -281,7 +281,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float inv = 1.0f / sum;
           auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
           const uint32_t srow = stg + lane * 128;
-          if (p.out_f32) {
+          if (p.out_f32 == 1) {
             // two 32-column fp32 boxes of 32 rows x 128 B each, 128-byte swizzle
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -289,6 +289,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                            __float_as_uint(f(oa[4 * j + 2])), __float_as_uint(f(oa[4 * j + 3])));
               st_shared_v4(srow + 4096 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
                            __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
+            }
+          } else if (p.out_f32 == 2) {
+            // bf16x3 split: hi and lo 64-column boxes (32 rows x 128 B each); hi is stored twice ([hi | hi | lo])
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c0 = 8 * j + 2 * e;
+                const float a = c0 < 32 ? f(oa[c0]) : f(ob[c0 - 32]), bb = c0 + 1 < 32 ? f(oa[c0 + 1]) : f(ob[c0 + 1 - 32]);
+                split_bf16x2(a, bb, hh[e], ll[e]);
+              }
+              const uint32_t off = ((uint32_t)j << 4) ^ x7s;
+              st_shared_v4(srow + off, hh[0], hh[1], hh[2], hh[3]);
+              st_shared_v4(srow + 4096 + off, ll[0], ll[1], ll[2], ll[3]);
             }
           } else {
             // one 64-column bf16 box of 32 rows x 128 B
@@ -304,7 +319,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             tma_store_3d(&tmO, stg_ptr, h * AT_DH, row0, b);
-            if (p.out_f32) tma_store_3d(&tmO, stg_ptr + 4096, h * AT_DH + 32, row0, b);
+            if (p.out_f32 == 1) tma_store_3d(&tmO, stg_ptr + 4096, h * AT_DH + 32, row0, b);
+            if (p.out_f32 == 2) {
+              const int Dm = p.heads * AT_DH;
+              tma_store_3d(&tmO, stg_ptr, Dm + h * AT_DH, row0, b);
+              tma_store_3d(&tmO, stg_ptr + 4096, 2 * Dm + h * AT_DH, row0, b);
+            }
             bulk_commit();
           }
         }
@@ -335,7 +355,8 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   const int D = heads * AT_DH;
   SMK_REQUIRE(Lk >= 1 && Lk <= AT_MAXK && Lq >= 1 && Lq <= 2 * AT_BM, "attention_tc: Lq=%d / Lk=%d not supported (1..256)", Lq, Lk);
   SMK_REQUIRE(B >= 1 && heads >= 1 && (int64_t)B * heads < (1 << 30), "attention_tc: bad batch/heads");
-  const int esz = out_f32 ? 4 : 2;
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2 && (out_f32 != 2 || ldo >= 3 * (int64_t)D), "attention_tc: bad output mode / ldo");
+  const int esz = out_f32 == 1 ? 4 : 2;
   SMK_REQUIRE((ldo * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc: output must be 16-byte aligned");
   const int nk_pad = (Lk + 15) / 16 * 16;
   const int nt = Lq > AT_BM ? 2 : 1;
@@ -345,9 +366,9 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   SMK_PROPAGATE(make_tmap_bf16_2d(&tv, v, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldv * 2, AT_DH, (uint32_t)nk_pad));
   {
     // {column, query row within the image, image}: rows >= Lq of a 32-row output box are clipped by the TMA unit
-    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)Lq, (uint64_t)B};
+    const uint64_t dims[3] = {(uint64_t)(out_f32 == 2 ? 3 * D : D), (uint64_t)Lq, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)ldo * esz, (uint64_t)Lq * ldo * esz};
-    const uint32_t box[3] = {out_f32 ? 32u : 64u, 32u, 1u};
+    const uint32_t box[3] = {out_f32 == 1 ? 32u : 64u, 32u, 1u};
     SMK_PROPAGATE(make_tmap_nd(&to, esz, out, 3, dims, strides, box, 128));
   }
   static bool attr_set = false;

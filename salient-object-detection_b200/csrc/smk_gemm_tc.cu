@@ -61,7 +61,7 @@ struct TcGemmParams {
   void* C;
   int64_t ldc;
   int epi;        // SMK_EPI_* flags
-  int out_f32;    // 0 → bf16 output, 1 → fp32 output
+  int out_f32;    // 0 → bf16 output, 1 → fp32 output, 2 → bf16x3 split output [hi | hi | lo] (3N columns)
   // token assembly for patch-embed (kDirect): output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
   int tok_hw;
   const float* tok_pos;
@@ -206,7 +206,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
           const int row0 = m_blk * TC_BM + quarter * 32;
-          if (p.out_f32) {
+          if (p.out_f32 == 1) {
             // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -219,6 +219,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) {
               if (p.epi & SMK_EPI_RESIDUAL) tma_reduce_add_2d(&tmC, stg, n0, row0);
               else tma_store_2d(&tmC, stg, n0, row0);
+              bulk_commit();
+            }
+          } else if (p.out_f32 == 2) {
+            // bf16x3 split output: hi tile → columns n0 and N + n0, lo tile → 2N + n0 (two 32 x 64 B staging tiles)
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            const uint32_t srow = stg_u32 + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], h[e], l[e]);
+              const uint32_t off = (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+              st_shared_v4(srow + off, h[0], h[1], h[2], h[3]);
+              st_shared_v4(srow + 2048 + off, l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stg, n0, row0);
+              tma_store_2d(&tmC, stg, p.N + n0, row0);
+              tma_store_2d(&tmC, stg + 2048, 2 * p.N + n0, row0);
               bulk_commit();
             }
           } else {
@@ -357,10 +379,12 @@ static int pick_bn(int M, int N) {
 int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                  int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s) {
   SMK_REQUIRE(K % TC_BK == 0 && N % 128 == 0, "gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, N);
-  SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32, "gemm_bf16: residual epilogue needs fp32 output");
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2, "gemm_bf16: out_f32 must be 0 (bf16), 1 (fp32) or 2 (bf16x3 split)");
+  SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32 == 1, "gemm_bf16: residual epilogue needs fp32 output");
+  SMK_REQUIRE(out_f32 != 2 || ldc >= 3 * (int64_t)N, "gemm_bf16: split output needs ldc >= 3N");
   SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
-  SMK_REQUIRE(tok_hw == 0 || (out_f32 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
+  SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
   const int BN = pick_bn(M, N);
   CUtensorMap ta, tb, tcm;
@@ -372,8 +396,9 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
     return BN == 256 ? launch_tc<256, true>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, true>(ta, tb, tcm, p, s) : launch_tc<128, true>(ta, tb, tcm, p, s));
   }
   // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (bf16, 64-byte swizzle) per row
-  const int esz = out_f32 ? 4 : 2;
-  SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * esz, 32, 32, out_f32 ? 128 : 64));
+  const int esz = out_f32 == 1 ? 4 : 2;
+  SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(out_f32 == 2 ? 3 * N : N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32,
+                             out_f32 == 1 ? 128 : 64));
   return BN == 256 ? launch_tc<256, false>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, false>(ta, tb, tcm, p, s) : launch_tc<128, false>(ta, tb, tcm, p, s));
 }
 

@@ -137,7 +137,7 @@ struct smk_model {
   __nv_bfloat16* tokb;            // bf16 copy (bf16 mode)
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
   std::vector<Dec3> dec3;         // bf16 mode only
-  __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *dqk_b, *dv_b, *cq_b;
+  __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *a3c, *a3f, *a3q, *dqk_b, *dv_b, *cq_b;
   float* debug_logits;
   int last_B;
 };
@@ -200,9 +200,11 @@ static void plan(smk_model& m, Plan& pl) {
     }
     m.f0w3 = pl.take<__nv_bfloat16>(D * 3 * D);
     m.f1w3 = pl.take<__nv_bfloat16>(D * 3 * D);
-    const int64_t a3 = std::max(R * 3 * FD, L * R * 3 * D);
-    m.a3a = pl.take<__nv_bfloat16>(a3);
-    m.a3b = pl.take<__nv_bfloat16>(a3);
+    m.a3a = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(tgt)
+    m.a3b = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(tgt + query_pos)
+    m.a3c = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(attention output)
+    m.a3f = pl.take<__nv_bfloat16>(std::max(R * 3 * FD, L * R * 3 * D));   // split(FFN hidden) / split(objectness hidden)
+    m.a3q = pl.take<__nv_bfloat16>(L * R * 3 * D);                     // split(final-norm queries), all layers
     m.dqk_b = pl.take<__nv_bfloat16>(R * 2 * D);
     m.dv_b = pl.take<__nv_bfloat16>(R * D);
     m.cq_b = pl.take<__nv_bfloat16>(R * D);
@@ -441,32 +443,29 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
       return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
     };
     const __nv_bfloat16* KVb = (const __nv_bfloat16*)m->KV;
+    // Every producer writes the bf16x3 split its consumer GEMM needs (LayerNorm, attention and ReLU-GEMM epilogues), so a
+    // decoder layer is 12 launches: 7 split GEMMs, 2 attentions, 3 fused add+LayerNorm(+final norm) kernels.
+    SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, m->a3a, m->a3b, R, D, s));   // layer 0 input: tgt = 0
     for (int l = 0; l < L; ++l) {
       const DecW& d = m->dec[l];
       const Dec3& d3 = m->dec3[l];
       // self-attention: q = k = tgt + query_pos, v = tgt
-      SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, m->a3a, m->a3b, R, D, s));
       SMK_PROPAGATE(gemm3(m->a3b, d3.saw, w + d.sab, m->dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
       SMK_PROPAGATE(gemm3(m->a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, m->dv_b, D, R, D, D, SMK_EPI_NONE, 0));
-      SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->dao, D, 1, B, nq, nq, c.heads, scale, s));
-      SMK_PROPAGATE(split3_act(m->dao, D, nullptr, 0, m->a3a, nullptr, R, D, s));
-      SMK_PROPAGATE(gemm3(m->a3a, d3.saow, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n1w, w + d.n1b, m->tgt, nullptr, R, D, 1e-5f, s));
+      SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
+      SMK_PROPAGATE(gemm3(m->a3c, d3.saow, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, m->a3b, nullptr, nullptr, nullptr, nullptr, R, D, s));
       // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
-      SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, nullptr, m->a3b, R, D, s));
       SMK_PROPAGATE(gemm3(m->a3b, d3.caqw, w + d.cab, m->cq_b, D, R, D, D, SMK_EPI_NONE, 0));
       const __nv_bfloat16* kl = KVb + (int64_t)l * 2 * D;
-      SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->dao, D, 1, B, nq, hw, c.heads, scale, s));
-      SMK_PROPAGATE(split3_act(m->dao, D, nullptr, 0, m->a3a, nullptr, R, D, s));
-      SMK_PROPAGATE(gemm3(m->a3a, d3.caow, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
-      // FFN
-      SMK_PROPAGATE(split3_act(m->tgt, D, nullptr, 0, m->a3a, nullptr, R, D, s));
-      SMK_PROPAGATE(gemm3(m->a3a, d3.l1w, w + d.l1b, m->ffh, FD, R, FD, D, SMK_EPI_RELU, 1));
-      SMK_PROPAGATE(split3_act(m->ffh, FD, nullptr, 0, m->a3a, nullptr, R, FD, s));
-      SMK_PROPAGATE(gemm3(m->a3a, d3.l2w, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n3w, w + d.n3b, m->tgt, nullptr, R, D, 1e-5f, s));
-      SMK_PROPAGATE(layernorm_f32(m->tgt, nullptr, w + m->o_dnw, w + m->o_dnb, m->queries + (int64_t)l * R * D, nullptr, R, D, 1e-5f, s));
+      SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
+      SMK_PROPAGATE(gemm3(m->a3c, d3.caow, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, m->a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s));
+      // FFN (ReLU); the shared final norm on every layer's output (transformer_decoder.py:138-145) rides on the last LayerNorm
+      SMK_PROPAGATE(gemm3(m->a3a, d3.l1w, w + d.l1b, m->a3f, 3 * FD, R, FD, D, SMK_EPI_RELU, 2));
+      SMK_PROPAGATE(gemm3(m->a3f, d3.l2w, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, 1));
+      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n3w, w + d.n3b, 1e-5f, qpos, nq, m->a3a, m->a3b, w + m->o_dnw, w + m->o_dnb,
+                                  m->queries + (int64_t)l * R * D, m->a3q + (int64_t)l * R * 3 * D, R, D, s));
     }
   } else {
   for (int l = 0; l < L; ++l) {
@@ -504,10 +503,9 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
     const float* qsrc = m->queries + (int64_t)layer0 * R * D;
     const int rows = Lout * R;
     if (bf) {
-      SMK_PROPAGATE(split3_act(qsrc, D, nullptr, 0, m->a3a, nullptr, rows, D, s));
-      SMK_PROPAGATE(gemm_bf16_tc(m->a3a, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->oh1, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
-      SMK_PROPAGATE(split3_act(m->oh1, D, nullptr, 0, m->a3a, nullptr, rows, D, s));
-      SMK_PROPAGATE(gemm_bf16_tc(m->a3a, 3 * D, m->f1w3, 3 * D, w + m->o_f1b, m->oh2, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
+      const __nv_bfloat16* q3 = m->a3q + (int64_t)layer0 * R * 3 * D;
+      SMK_PROPAGATE(gemm_bf16_tc(q3, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->a3f, 3 * D, rows, D, 3 * D, SMK_EPI_RELU, 2, 0, nullptr, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->a3f, 3 * D, m->f1w3, 3 * D, w + m->o_f1b, m->oh2, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
     } else {
       SMK_PROPAGATE(gemm_f32(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
       SMK_PROPAGATE(gemm_f32(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));

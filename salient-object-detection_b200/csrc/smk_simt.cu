@@ -97,6 +97,110 @@ int layernorm_bf16(const float* x, const float* res, const float* gamma, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decoder post-norm step (transformer_decoder.py:260-297), fused:  y = LN(x + res)  (written back over x) and, as asked,
+//   a3a = bf16x3 split of y, a3b = bf16x3 split of (y + query_pos)  — the A operands of the next split GEMMs —
+//   y2 = LN2(y) (the shared final decoder.norm, :138-145) in fp32 and as a bf16x3 split (objectness head input).
+// One warp per row, the row stays in registers.  Split rows are [hi | hi | lo], 3·D columns.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split4(__nv_bfloat16* row3, int D, int e, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  uint2 hi, lo;
+  hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<uint32_t*>(&l0); lo.y = *reinterpret_cast<uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(row3 + e) = hi;
+  *reinterpret_cast<uint2*>(row3 + D + e) = hi;
+  *reinterpret_cast<uint2*>(row3 + 2 * D + e) = lo;
+}
+
+template <int kChunks>
+__global__ void __launch_bounds__(256)
+dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     const float* __restrict__ pos, int period, __nv_bfloat16* __restrict__ a3a, __nv_bfloat16* __restrict__ a3b,
+                     const float* __restrict__ gamma2, const float* __restrict__ beta2, float* __restrict__ y2,
+                     __nv_bfloat16* __restrict__ y2s, int64_t rows, int D) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4* xr = reinterpret_cast<float4*>(x + row * D);
+  const float4* rr = res ? reinterpret_cast<const float4*>(res + row * D) : nullptr;
+  float4 v[kChunks];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    v[c] = xr[lane + 32 * c];
+    if (rr) {
+      const float4 r = rr[lane + 32 * c];
+      v[c].x += r.x; v[c].y += r.y; v[c].z += r.z; v[c].w += r.w;
+    }
+    s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+  }
+  auto normalise = [&](const float* g, const float* b_, float sum) {
+    const float mean = warp_sum(sum) / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+      ss += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)D + eps);
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int i = lane + 32 * c;
+      const float4 gg = reinterpret_cast<const float4*>(g)[i], bb = reinterpret_cast<const float4*>(b_)[i];
+      v[c].x = (v[c].x - mean) * rstd * gg.x + bb.x;
+      v[c].y = (v[c].y - mean) * rstd * gg.y + bb.y;
+      v[c].z = (v[c].z - mean) * rstd * gg.z + bb.z;
+      v[c].w = (v[c].w - mean) * rstd * gg.w + bb.w;
+      s2 += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    }
+    return s2;
+  };
+  const float s_y = normalise(gamma, beta, s);
+  const float* prow = pos ? pos + (int64_t)(row % period) * D : nullptr;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int i = lane + 32 * c;
+    xr[i] = v[c];
+    if (a3a) store_split4(a3a + row * 3 * D, D, 4 * i, v[c]);
+    if (a3b) {
+      const float4 pp = reinterpret_cast<const float4*>(prow)[i];
+      store_split4(a3b + row * 3 * D, D, 4 * i, make_float4(v[c].x + pp.x, v[c].y + pp.y, v[c].z + pp.z, v[c].w + pp.w));
+    }
+  }
+  if (gamma2) {
+    normalise(gamma2, beta2, s_y);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int i = lane + 32 * c;
+      if (y2) reinterpret_cast<float4*>(y2 + row * D)[i] = v[c];
+      if (y2s) store_split4(y2s + row * 3 * D, D, 4 * i, v[c]);
+    }
+  }
+}
+
+int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
+                  __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
+                  int64_t rows, int D, cudaStream_t s) {
+  SMK_REQUIRE(D % 128 == 0 && D <= 512, "dec_layernorm: D=%d must be a multiple of 128 and <= 512", D);
+  SMK_REQUIRE(!a3b || (pos && period > 0), "dec_layernorm: a3b needs the query positions");
+  if (rows == 0) return SMK_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  ProfScope prof(PROF_LAYERNORM, (double)rows * D * (8.0 + (res ? 4.0 : 0.0) + (a3a ? 6.0 : 0.0) + (a3b ? 6.0 : 0.0) + (y2 ? 4.0 : 0.0) +
+                                                     (y2s ? 6.0 : 0.0)), s);
+  switch (D / 128) {
+#define SMK_DLN_CASE(c) \
+  case c: dec_layernorm_kernel<c><<<grid, 256, 0, s>>>(x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D); break;
+    SMK_DLN_CASE(1) SMK_DLN_CASE(2) SMK_DLN_CASE(3) SMK_DLN_CASE(4)
+#undef SMK_DLN_CASE
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 GEMM  C[M,N] = A[M,K] · W[N,K]^T + bias  (both operands K-contiguous = nn.Linear layout)
 // 64x64x16 tiles, 256 threads, 4x4 micro-tile.
 // ------------------------------------------------------------------------------------------------

@@ -247,3 +247,40 @@ def test_attention_tcgen05_general_layout(Lq, Lk, kv_rows, kv_row0):
     vh = kk[..., D:].reshape(B, Lk, H, dh).transpose(1, 2)
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
     assert (out - ref).abs().max().item() <= 0.03
+
+
+def test_gemm_bf16_tcgen05_split3_output():
+    """out_f32 = 2: the epilogue writes the bf16x3 split [hi | hi | lo] of the fp32 result (decoder FFN hidden, objectness hidden)."""
+    torch.manual_seed(7)
+    M_, N, K = 700, 384, 384
+    A = torch.randn(M_, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    out = torch.zeros(M_, 3 * N, dtype=torch.bfloat16, device=DEV)
+    check(lib().smk_gemm_bf16(ptr(A), K, ptr(W), ptr(bias), ptr(out), 3 * N, M_, N, K, 2, 2, stream_ptr()), "gemm split3")
+    torch.cuda.synchronize()
+    ref = torch.relu(A.float() @ W.float().t() + bias)
+    hi, hi2, lo = out[:, :N].float(), out[:, N:2 * N].float(), out[:, 2 * N:].float()
+    assert torch.equal(hi, hi2)
+    assert (hi - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
+    assert (hi + lo - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())      # hi + lo carries ~16 mantissa bits
+
+
+def test_attention_tcgen05_split3_output():
+    torch.manual_seed(8)
+    B, H, dh, Lq, Lk = 5, 6, 64, 20, 196
+    D = H * dh
+    q = torch.randn(B * Lq, D, device=DEV).to(torch.bfloat16)
+    k = torch.randn(B * Lk, D, device=DEV).to(torch.bfloat16)
+    v = torch.randn(B * Lk, D, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(B * Lq, 3 * D, device=DEV, dtype=torch.bfloat16)
+    check(lib().smk_attention_tc_general(ptr(q), D, ptr(k), D, ptr(v), D, B * Lk, Lk, 0, ptr(out), 3 * D, 2, B, Lq, Lk, H, 0.125, stream_ptr()))
+    torch.cuda.synchronize()
+    qh = q.float().view(B, Lq, H, dh).transpose(1, 2)
+    kh = k.float().view(B, Lk, H, dh).transpose(1, 2)
+    vh = v.float().view(B, Lk, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    hi, hi2, lo = out[:, :D].float(), out[:, D:2 * D].float(), out[:, 2 * D:].float()
+    assert torch.equal(hi, hi2)
+    assert (hi + lo - ref).abs().max().item() <= 0.03
+    assert (lo.abs() <= hi.abs() * 2.0 ** -7 + 1e-30).all()          # lo is the rounding residue of hi
