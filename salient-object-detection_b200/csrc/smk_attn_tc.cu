@@ -90,7 +90,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
+  // through a warp reduction (REDUX → uniform register) so that ptxas can keep the MMA operands in uniform registers
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_ptr);
 
   if (warp == 0) {
     // ===== TMA producer (whole warp, one elected lane issues) =====

@@ -13,6 +13,8 @@
 // 10 instructions per element (gelu_fast below).
 // Serves: patch-embed (vision_transformer.py:184-188), qkv / proj / fc1 / fc2 (:113,131,88-94), the
 // decoder's memory K/V projection (transformer_decoder.py:283-291 via nn.MultiheadAttention in_proj).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "smk_tc.cuh"
@@ -43,16 +45,17 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-0.5f * u, t, fmaxf(x, 0.f));
 }
 
-template <int BN>
+template <int BN, int kCtas>
 struct TcCfg {
-  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr int kBNL = BN / kCtas;                          // B-tile rows loaded by one CTA
   static constexpr int kABytes = TC_BM * TC_BK * 2;
-  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kBBytes = kBNL * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
   static constexpr int kStagingBytes = TC_EPI_WARPS * TC_STAGING_PER_WARP;
+  static constexpr int kStages = (227 * 1024 - kStagingBytes - 1024 - 256) / kStageBytes > 8 ? 8 : (227 * 1024 - kStagingBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kSmemBytes <= 227 * 1024 && kStages >= 3, "shared memory budget");
 };
 
 struct TcGemmParams {
@@ -68,11 +71,14 @@ struct TcGemmParams {
 };
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
-template <int BN, bool kDirect>
+// kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
+// M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
+// the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
+template <int BN, bool kDirect, int kCtas>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const TcGemmParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, kCtas>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -83,49 +89,67 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blocks = p.N / BN, m_blocks = (p.M + TC_BM - 1) / TC_BM;
+  const int n_blocks = p.N / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);
   const int num_tiles = n_blocks * m_blocks, k_blocks = p.K / TC_BK;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;   // tiles are owned by clusters
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (!kDirect) tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS * kCtas); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+  if (warp == 1) {
+    if constexpr (kCtas == 2) tmem_alloc2(tmem_ptr, Cfg::kTmemCols);
+    else tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr;
+  // The TMEM base address is read from shared memory, i.e. into a per-thread register; routed through a warp reduction
+  // (REDUX writes a uniform register) it becomes provably warp-uniform.  Otherwise ptxas wraps every single-thread
+  // tcgen05.mma in an ELECT / R2UR.BROADCAST / branch "waterfall" that costs ~100 cycles per MMA — more than a
+  // 128 x 128 x 16 MMA (64 cycles) takes to execute, which made the issuing thread the bottleneck of every GEMM.
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_ptr);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
-          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+          if constexpr (kCtas == 2) {
+            // both CTAs' bytes complete on the even CTA's barrier (its MMA thread is the only consumer)
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sa, &tmA, bar, kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
+            tma_load_2d_cg2(sa + Cfg::kABytes, &tmB, bar, kb * TC_BK, n_blk * BN + (int)rank * Cfg::kBNL);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(TC_BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(TC_BM * kCtas, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -135,12 +159,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sa + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)   // +32 B per 16-element K step → +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
+            if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
+          else tc_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);              // accumulator complete → epilogue
+        // accumulator complete → epilogue (of both CTAs)
+        if constexpr (kCtas == 2) tc_commit_cg2(&tmem_full[acc], 3);
+        else tc_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -155,8 +185,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;                             // staging-buffer parity (bf16 output)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+    const uint32_t tmem_empty_remote = kCtas == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = (tile / n_blocks) * kCtas + (int)rank, n_blk = tile % n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const int m = m_blk * TC_BM + quarter * 32 + lane;
@@ -170,7 +201,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ci == kChunks - 1) {                 // accumulator fully read: hand the TMEM buffer back before the math
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (kCtas == 2 && rank != 0) mbar_arrive_cluster(tmem_empty_remote + (uint32_t)(acc * 8));
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         const int n0 = n_blk * BN + c * 32;
         float v[32];
@@ -268,8 +302,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (!kDirect && lane == 0) bulk_wait<0>();   // all tile stores complete before the CTA retires
   }
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();        // the peer may still read this CTA's operand tiles / signal its barriers until here
+    if (warp == 1) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -343,36 +382,65 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool kDirect>
+template <int BN, bool kDirect, int kCtas>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, kCtas>;
   static bool attr_set = false;
   if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = (p.N / BN) * ((p.M + TC_BM - 1) / TC_BM);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tiles = (p.N / BN) * ((p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas));
+  const int slots = num_sms() / kCtas;                     // CTAs (kCtas = 1) or CTA pairs (2) that can be resident
+  const int grid = (tiles < slots ? tiles : slots) * kCtas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kCtas > 1 ? 1 : 0;
   {
     ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
-    gemm_bf16_tc_kernel<BN, kDirect><<<grid, TC_THREADS, Cfg::kSmemBytes, s>>>(ta, tb, tcm, p);
+    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
 
 // Tile width: minimise (waves over the SMs) x BN, i.e. the tensor-pipe time of the busiest SM; ties go to the wider
-// tile (fewer A+B shared-memory bytes per MMA cycle: 128 B at BN=128, 107 at 192, 96 at 256).
-static int pick_bn(int M, int N) {
-  const int64_t mb = (M + TC_BM - 1) / TC_BM, sms = num_sms();
+// tile (fewer operand bytes per MMA cycle).  `slots` = resident CTAs (or CTA pairs), `bm` = rows per tile.
+static int pick_bn(int M, int N, int bm, int slots) {
+  static int forced = -1;                      // SMK_GEMM_BN=128|192|256 forces the tile width (tuning aid)
+  if (forced < 0) {
+    const char* e = getenv("SMK_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0 && N % forced == 0) return forced;
+  const int64_t mb = (M + bm - 1) / bm;
   int best = 128;
   int64_t best_cost = -1;
   for (int bn : {128, 192, 256}) {
     if (N % bn) continue;
-    const int64_t tiles = (N / bn) * mb, cost = (tiles + sms - 1) / sms * bn;
+    const int64_t tiles = (N / bn) * mb, cost = (tiles + slots - 1) / slots * bn;
     if (best_cost < 0 || cost <= best_cost) { best = bn; best_cost = cost; }
   }
   return best;
+}
+
+// 0 = single-CTA tiles only, 1 = CTA pairs where the problem is large enough (default); SMK_GEMM_CTA_PAIR overrides (tuning)
+static int cta_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SMK_GEMM_CTA_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
 }
 
 // A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements)
@@ -386,20 +454,27 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
-  const int BN = pick_bn(M, N);
+  const bool pair = tok_hw == 0 && cta_pair_mode() != 0 && M > TC_BM;
+  const int kc = pair ? 2 : 1;
+  const int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
   CUtensorMap ta, tb, tcm;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
-  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)BN));
+  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));
   TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos};
   if (tok_hw > 0) {
     tcm = ta;   // unused by the direct-store epilogue
-    return BN == 256 ? launch_tc<256, true>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, true>(ta, tb, tcm, p, s) : launch_tc<128, true>(ta, tb, tcm, p, s));
+    return BN == 256 ? launch_tc<256, true, 1>(ta, tb, tcm, p, s)
+                     : (BN == 192 ? launch_tc<192, true, 1>(ta, tb, tcm, p, s) : launch_tc<128, true, 1>(ta, tb, tcm, p, s));
   }
   // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (bf16, 64-byte swizzle) per row
   const int esz = out_f32 == 1 ? 4 : 2;
   SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(out_f32 == 2 ? 3 * N : N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32,
                              out_f32 == 1 ? 128 : 64));
-  return BN == 256 ? launch_tc<256, false>(ta, tb, tcm, p, s) : (BN == 192 ? launch_tc<192, false>(ta, tb, tcm, p, s) : launch_tc<128, false>(ta, tb, tcm, p, s));
+  if (pair)
+    return BN == 256 ? launch_tc<256, false, 2>(ta, tb, tcm, p, s)
+                     : (BN == 192 ? launch_tc<192, false, 2>(ta, tb, tcm, p, s) : launch_tc<128, false, 2>(ta, tb, tcm, p, s));
+  return BN == 256 ? launch_tc<256, false, 1>(ta, tb, tcm, p, s)
+                   : (BN == 192 ? launch_tc<192, false, 1>(ta, tb, tcm, p, s) : launch_tc<128, false, 1>(ta, tb, tcm, p, s));
 }
 
 }  // namespace smk

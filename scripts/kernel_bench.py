@@ -13,6 +13,8 @@ from selfmask_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--only", default="")
+ap.add_argument("--shapes", default="", help="extra GEMM cases name:M:N:K:epi:f32,...")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 M = args.batch * 197
@@ -32,7 +34,8 @@ def timeit(fn, nbuf, iters=args.iters):
     return e0.elapsed_time(e1) / iters * 1e3   # us
 
 
-def gemm_case(name, N, K, epi, f32):
+def gemm_case(name, N, K, epi, f32, M=None):
+    M = M or globals()["M"]
     nbuf = 4
     A = [(torch.randn(M, K, device=dev)).to(torch.bfloat16) for _ in range(nbuf)]
     W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
@@ -48,11 +51,16 @@ def gemm_case(name, N, K, epi, f32):
           f"min-HBM {byts / 1e6:6.0f} MB = {byts / us / 1e3:6.0f} GB/s")
 
 
-gemm_case("qkv", 1152, 384, 0, False)
-gemm_case("proj", 384, 384, 4, True)
-gemm_case("fc1", 1536, 384, 1, False)
-gemm_case("fc2", 384, 1536, 4, True)
-gemm_case("kv", 4608, 384, 0, False)
+CASES = {"qkv": (1152, 384, 0, False), "proj": (384, 384, 4, True), "fc1": (1536, 384, 1, False), "fc2": (384, 1536, 4, True),
+         "kv": (4608, 384, 0, False)}
+for name, c in CASES.items():
+    if not args.only or name in args.only.split(","):
+        gemm_case(name, *c)
+for sh in filter(None, args.shapes.split(",")):
+    nm, m_, n_, k_, e_, f_ = sh.split(":")
+    gemm_case(nm, int(n_), int(k_), int(e_), bool(int(f_)), M=int(m_))
+if args.only or args.shapes:
+    sys.exit(0)
 
 # attention (encoder shape)
 B, N, H = args.batch, 197, 6
