@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=48, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: warm up, then run exactly ONE step between cudaProfilerStart/Stop and exit "
+                         "(ncu --profile-from-start off sees the step's launches 0..n-1 in order; prints no bench line)")
     return ap.parse_args()
 
 
@@ -134,7 +137,9 @@ def workload_config(args, **extra):
     c = {"workload": f"SelfMask nq{args.nq} ViT-S/16 inference+metrics, batch {args.batch}/GPU at {args.size}x{args.size} "
                      f"(BASELINE.json configs[2]), batch-sharded, count all-reduce",
          "per_gpu_batch": args.batch, "image": [args.size, args.size], "n_queries": args.nq, "numeric_mode": args.mode,
-         "mask_layers": 6, "l2": "inputs larger than L2 (x is 154 MB/step at batch 256; activations ~1 GB)"}
+         "mask_layers": 6, "input": "uint8 pixels (normalisation fused on device)",
+         "l2": "working set larger than L2: every step streams ~1.3 GB of activations through the 126 MB L2, so the 51 MB of "
+               "inputs (x uint8 + GT) are evicted between steps"}
     c.update(extra)
     return c
 
@@ -164,7 +169,9 @@ def main():
     model = S.SelfMaskB200(n_queries=args.nq, mode=args.mode, max_batch=B, return_intermediate=True).to(dev)
     model.load_state_dict(Y.synth_state_dict(model.table(), seed=0))
     uniq = min(B, 32)
-    x_host = Y.normalize_images(Y.synth_images_u8(uniq, args.size, args.size, seed=1234 + rank)).repeat((B + uniq - 1) // uniq, 1, 1, 1)[:B]
+    # raw uint8 pixels: the loader's ImageNet normalisation (datasets/base_dataset.py:250) is fused into the patch im2col on
+    # the device, bit-identically (tests/test_gpu_model.py), so a step moves 1 byte per pixel-channel over PCIe instead of 4
+    x_host = torch.from_numpy(Y.synth_images_u8(uniq, args.size, args.size, seed=1234 + rank)).repeat((B + uniq - 1) // uniq, 1, 1, 1)[:B]
     g_host = torch.from_numpy(Y.synth_gt(uniq, args.size, args.size, seed=4321 + rank)).repeat((B + uniq - 1) // uniq, 1, 1, 1)[:B]
     x_host, g_host = x_host.contiguous().pin_memory(), g_host.contiguous().pin_memory()
     x, g = x_host.to(dev), g_host.to(dev)
@@ -187,6 +194,12 @@ def main():
     for _ in range(Wm):
         step()
     barrier()
+    if args.ncu_step:
+        torch.cuda.cudart().cudaProfilerStart()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = lib().smk_launch_count()
@@ -208,9 +221,10 @@ def main():
     res = S.summarize(counts.cpu().numpy(), sums.cpu().numpy())        # metric of the last step (sanity; outside the timed region)
 
     # ---- end to end through the public API: pinned host batches → Evaluator.__call__ → 14 averages ----------
+    ev = S.Evaluator(network=model)
+
     def e2e_pass():
-        batches = ({"x": x_host, "m": g_host} for _ in range(K))
-        ev = S.Evaluator(network=model, dataset=batches)
+        ev.dataset = ({"x": x_host, "m": g_host} for _ in range(K))
         r = ev(dataset_name="synthetic", dir_ckpt=None, batch_size=B, device=dev)
         if world > 1:      # same collective as the step: every rank's per-image rows → identical averages everywhere
             c = torch.from_numpy(ev.records["m_counts"]).to(dev)
@@ -227,7 +241,7 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = n_total * K / float(dt.item())
-    h2d = x_host.numel() * 4 + g_host.numel()
+    h2d = x_host.numel() * x_host.element_size() + g_host.numel() * g_host.element_size()
     d2h = B * 2 * (528 * 4 + 32 * 8) + B * 2 * 4 + B * args.nq * 2 * 4
 
     # ---- per-stage device time with CUDA events on the launching stream (roofline block) -------------------------
@@ -251,12 +265,18 @@ def main():
         stages[nme] = {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] // prof_steps, "share": ms_c[i] / total_ms if total_ms else 0,
                        "achieved": ach, "unit": "TFLOP/s" if i in tensor_cats else "GB/s",
                        "frac_of_peak": ach / (pk["tensor"] if i in tensor_cats else pk["hbm"])}
+    traffic = None          # real DRAM bytes per launch of the dominant stage's kernels, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
     dom = max(range(8), key=lambda i: ms_c[i])
+    if os.path.exists(tpath) and args.mode == "bf16" and (args.batch, args.size, args.nq) == (256, 224, 20):
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(names[dom])
     dom_tensor = dom in tensor_cats
     ach = stages[names[dom]]["achieved"]
     roofline = {"kernel": names[dom], "bound": "tensor" if dom_tensor else "hbm", "achieved": ach,
                 "peak": pk["tensor"] if dom_tensor else pk["hbm"], "unit": "TFLOP/s" if dom_tensor else "GB/s",
-                "frac": ach / (pk["tensor"] if dom_tensor else pk["hbm"]), "traffic": None,
+                "frac": ach / (pk["tensor"] if dom_tensor else pk["hbm"]), "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, launch-weighted mean)"
+                                  if traffic is not None else None,
                 "peak_source": f"MEASURED_PEAKS.json ({pk['src']}; sustained bf16 for a kernel timed inside a long step)",
                 "avg_launch_ms": ms_c[dom] / max(n_c[dom], 1), "stages": stages}
 

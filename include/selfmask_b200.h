@@ -96,6 +96,13 @@ int smk_model_destroy(smk_model* m);
 int smk_model_forward(smk_model* m, const float* x, int B, int H, int W, int all_layers,
                       float* mask_pred, float* objectness, float* features, void* stream);
 
+/* Same, from raw pixels: x [B,3,H,W] uint8 NCHW; the reference's host-side normalisation
+ * (datasets/base_dataset.py:250, torchvision to_tensor + normalize: ((float)u / 255 - mean[c]) / std[c]) is fused into
+ * the patch im2col with IEEE fp32 division, bit-identical to smk_model_forward on the host-normalised image.
+ * mean_std: HOST pointer to 6 floats {mean[3], std[3]}. */
+int smk_model_forward_u8(smk_model* m, const uint8_t* x, const float* mean_std, int B, int H, int W, int all_layers,
+                         float* mask_pred, float* objectness, float* features, void* stream);
+
 /* debug taps for stage-level parity tests: copies an internal activation (fp32) into `out`.
  * what: 1 final-LN encoder tokens [B,N,D]; 2 decoder queries after the shared final norm [L,B,nq,D];
  *       3 residual stream after the last encoder block [B,N,D] */
@@ -164,6 +171,7 @@ int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t 
 /* tuning aid: phase trace of CTA 0 of the tcgen05 attention kernel ([16 items][10 warps][8 events] clock64 stamps in device
  * memory); NULL switches it off. */
 int smk_debug_attn_trace(long long* buf);
+int smk_debug_gemm_trace(long long* buf);   /* tuning aid: per-CTA wait-cycle counters of the tcgen05 GEMM (16 per CTA); NULL = off */
 /* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
  * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */
 int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream);

@@ -41,6 +41,7 @@ SIGNATURES = {
     "smk_model_create": (_I, [C.POINTER(SmkConfig), _I, _P, _P, _L, _I, _I, _I, _P, C.POINTER(_P)]),
     "smk_model_destroy": (_I, [_P]),
     "smk_model_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "smk_model_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "smk_model_tap": (_I, [_P, _I, _P, _L, _P]),
     "smk_eval_batch": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "smk_mask_metrics": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "smk_attention_tc": (_I, [_P, _P, _I, _I, _I, _F, _P]),
     "smk_attention_tc_general": (_I, [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_debug_attn_trace": (_I, [_P]),
+    "smk_debug_gemm_trace": (_I, [_P]),
     "smk_split3": (_I, [_P, _L, _I, _P, _I, _P]),
     "smk_cast_bf16": (_I, [_P, _P, _L, _P]),
 }

@@ -29,7 +29,7 @@ constexpr int TC_STAGING_PER_WARP = 4096;   // 32 rows x 128 B (fp32 chunk) or 2
 // exact-GELU (vision_transformer.py:78 nn.GELU, erf form) as  relu(x) − 0.5·|x|·(1 − erf(|x|/√2))  with
 // 1 − erf(u/√2) = 2^(u·q(u)), q a degree-4 fit (monotone beyond the fit range, so no clamp is needed):
 // max abs error 1.9e-5 = 0.11 bf16 ulp of the result (the bf16-mode output is rounded to bf16 right after).
-// 9 FMA-pipe instructions + one MUFU.EX2; the fp32 validation mode keeps erff().
+// 7 FMA/ALU-pipe instructions + one MUFU.EX2; the fp32 validation mode keeps erff().
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -41,22 +41,55 @@ __device__ __forceinline__ float gelu_fast(float x) {
   q = fmaf(u, q, -0.04784644f);
   q = fmaf(u, q, -0.46398392f);
   q = fmaf(u, q, -1.1496887f);
-  const float t = ex2_approx(u * q);              // 1 − erf(|x|/√2)
-  return fmaf(-0.5f * u, t, fmaxf(x, 0.f));
+  const float t = ex2_approx(fmaf(u, q, -1.0f));  // 0.5·(1 − erf(|x|/√2)): the factor 0.5 rides in the exponent
+  return fmaf(-u, t, fmaxf(x, 0.f));
 }
 
-template <int BN, int kCtas>
+constexpr int TC_ARES_KB = 6;                 // A-resident mode: up to 6 k-blocks (K <= 384) of the 128-row A block stay in shared memory
+constexpr int TC_BAR_BYTES = 512;
+
+// kARes: "A-resident" schedule for K <= 384 (qkv, proj, fc1, memory K/V), optional (SMK_GEMM_ARES=1).  A CTA (or CTA pair)
+// walks a contiguous, balanced range of the m-major tile sequence, keeps the 128 x K block of A in shared memory for all
+// n-blocks of that m-block and streams only the weight tiles through the ring: operand bytes pulled from L2 drop from
+// (128 + BN)·K·2 per tile to BN·K·2 (qkv: 695 MB → 387 MB per launch).  Measured on B200 it is 5-10 % slower than the
+// strided order on this model's shapes: those GEMMs are bound by the epilogue (GELU / TMA stores) and by the ~150-cycle
+// floor of an SS-mode M = 128 MMA, not by the L2→SM operand feed (profiles/r01_gemm_experiments.md).
+template <int BN, int kCtas, bool kARes>
 struct TcCfg {
   static constexpr int kBNL = BN / kCtas;                          // B-tile rows loaded by one CTA
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = kBNL * TC_BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAResBytes = kARes ? TC_ARES_KB * kABytes : 0;
+  static constexpr int kStageBytes = kARes ? kBBytes : kABytes + kBBytes;
   static constexpr int kStagingBytes = TC_EPI_WARPS * TC_STAGING_PER_WARP;
-  static constexpr int kStages = (227 * 1024 - kStagingBytes - 1024 - 256) / kStageBytes > 8 ? 8 : (227 * 1024 - kStagingBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kRingBudget = 227 * 1024 - kStagingBytes - 1024 - TC_BAR_BYTES - kAResBytes;
+  static constexpr int kStages = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kAResBytes + kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + TC_BAR_BYTES;
   static_assert(kSmemBytes <= 227 * 1024 && kStages >= 3, "shared memory budget");
+  static_assert((2 * kStages + 4 + 2 * TC_ARES_KB) * 8 + 8 <= TC_BAR_BYTES, "barrier area");
 };
+
+// optional wait-cycle accounting (tuning scripts only): per CTA 16 counters
+//   [0] producer: cycles waiting for a free ring slot   [1] producer: total loop cycles
+//   [2] MMA: waiting for operands (full barriers)       [3] MMA: waiting for a free accumulator   [4] MMA: total
+//   [5] epilogue warp 2: waiting for the accumulator    [6] epilogue warp 2: waiting for staging (bulk_wait_read)   [7] total
+//   [8] tiles of this CTA   [9] epilogue warp 2: tcgen05.wait::ld   [10] epilogue warp 2: staging + store section
+__device__ long long* g_gemm_trace = nullptr;
+struct WaitClock {
+  long long acc = 0, t0 = 0;
+  bool on;
+  __device__ explicit WaitClock(bool on_) : on(on_) {}
+  __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+  __device__ __forceinline__ void end() { if (on) acc += clock64() - t0; }
+};
+
+// tuning-only switches in TcGemmParams::dbg (SMK_GEMM_DEBUG): results are garbage, timing isolates one pipeline stage
+constexpr int TC_DBG_NOEPI = 1;    // epilogue warps hand the accumulator straight back (no TMEM read, math or store)
+constexpr int TC_DBG_NOLOAD = 2;
+constexpr int TC_DBG_NOSTORE = 8;  // epilogue reads TMEM and does the math but skips staging + TMA store
+constexpr int TC_DBG_NOTMA = 16;   // epilogue stages to shared memory but does not issue the TMA store
+constexpr int TC_DBG_NOCOMMIT = 4; // (with NOLOAD) no per-k-block tcgen05.commit on the ring's empty barriers   // operands are loaded for the first ring pass only; the MMAs re-read the same shared memory
 
 struct TcGemmParams {
   int M, N, K;
@@ -68,31 +101,41 @@ struct TcGemmParams {
   // token assembly for patch-embed (kDirect): output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
   int tok_hw;
   const float* tok_pos;
+  int dbg;
 };
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
 // M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
 // the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
-template <int BN, bool kDirect, int kCtas>
+template <int BN, bool kDirect, int kCtas, bool kARes>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const TcGemmParams p) {
-  using Cfg = TcCfg<BN, kCtas>;
+  using Cfg = TcCfg<BN, kCtas, kARes>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_base + Cfg::kAResBytes;   // operand ring (the resident A block, if any, sits in front of it)
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;
+  uint64_t* a_empty = a_full + TC_ARES_KB;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + TC_ARES_KB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = p.N / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);
   const int num_tiles = n_blocks * m_blocks, k_blocks = p.K / TC_BK;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
-  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;   // tiles are owned by clusters
+  // tiles are owned by clusters.  Strided order (neighbouring CTAs work on neighbouring tiles) or, A-resident, a contiguous
+  // balanced range of the m-major sequence (tile = m_blk * n_blocks + n_blk)
+  const int n_cl = gridDim.x / kCtas, cl = blockIdx.x / kCtas;
+  const int tile0 = kARes ? (int)((int64_t)cl * num_tiles / n_cl) : cl;
+  const int tile_end = kARes ? (int)((int64_t)(cl + 1) * num_tiles / n_cl) : num_tiles;
+  const int tile_step = kARes ? 1 : n_cl;
+  long long* trace = g_gemm_trace ? g_gemm_trace + 16 * blockIdx.x : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -100,6 +143,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (!kDirect) tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS * kCtas); }
+    for (int i = 0; i < TC_ARES_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -121,25 +165,50 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      int cur_m = -1;
+      uint32_t a_fills = 0;                      // A-resident: m-blocks loaded so far (slot parity)
+      WaitClock w_slot(trace != nullptr), w_all(trace != nullptr);
+      w_all.begin();
+      int n_loads = 0;
+      for (int tile = tile0; tile < tile_end; tile += tile_step) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        const bool new_m = kARes && m_blk != cur_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          if (new_m && !((p.dbg & TC_DBG_NOLOAD) && a_fills > 0)) {
+            // slot kb is released when the last n-block of the previous m-block has consumed it
+            mbar_wait(&a_empty[kb], (a_fills & 1) ^ 1);
+            uint8_t* sa = smem_base + kb * Cfg::kABytes;
+            if constexpr (kCtas == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * Cfg::kABytes);
+              tma_load_2d_cg2(sa, &tmA, mapa_shared(smem_u32(&a_full[kb]), 0), kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
+            } else {
+              mbar_arrive_expect_tx(&a_full[kb], Cfg::kABytes);
+              tma_load_2d(sa, &tmA, &a_full[kb], kb * TC_BK, m_blk * TC_BM);
+            }
+          }
+          if ((p.dbg & TC_DBG_NOLOAD) && n_loads++ >= Cfg::kStages) continue;
+          w_slot.begin();
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          w_slot.end();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = kARes ? sa : sa + Cfg::kABytes;
           if constexpr (kCtas == 2) {
             // both CTAs' bytes complete on the even CTA's barrier (its MMA thread is the only consumer)
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2(sa, &tmA, bar, kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
-            tma_load_2d_cg2(sa + Cfg::kABytes, &tmB, bar, kb * TC_BK, n_blk * BN + (int)rank * Cfg::kBNL);
+            if constexpr (!kARes) tma_load_2d_cg2(sa, &tmA, bar, kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
+            tma_load_2d_cg2(sb, &tmB, bar, kb * TC_BK, n_blk * BN + (int)rank * Cfg::kBNL);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
-            tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+            if constexpr (!kARes) tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        if (new_m) { cur_m = m_blk; ++a_fills; }
       }
+      w_all.end();
+      if (trace) { trace[0] = w_slot.acc; trace[1] = w_all.acc; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -149,30 +218,54 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      int cur_m = -1;
+      uint32_t a_uses = 0;                       // A-resident: m-blocks consumed so far (slot parity)
+      WaitClock w_ops(trace != nullptr), w_acc(trace != nullptr), w_all(trace != nullptr);
+      w_all.begin();
+      int n_used = 0;
+      for (int tile = tile0; tile < tile_end; tile += tile_step) {
+        const int m_blk = tile / n_blocks;
+        const bool new_m = kARes && m_blk != cur_m;
+        const bool last_of_m = kARes && (tile + 1 == tile_end || (tile + 1) / n_blocks != m_blk);
+        w_acc.begin();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_acc.end();
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          w_ops.begin();
+          const bool skip_wait = (p.dbg & TC_DBG_NOLOAD) && n_used++ >= Cfg::kStages;
+          if (new_m && !((p.dbg & TC_DBG_NOLOAD) && a_uses > 0)) mbar_wait(&a_full[kb], a_uses & 1);
+          if (!skip_wait) mbar_wait(&full_bar[stage], phase);
+          w_ops.end();
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sa + Cfg::kABytes);
+          const uint32_t sa = kARes ? smem_u32(smem_base + kb * Cfg::kABytes) : smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = smem_u32(smem + stage * Cfg::kStageBytes) + (kARes ? 0u : (uint32_t)Cfg::kABytes);
+          const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
             if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
             else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
-          else tc_commit(&empty_bar[stage]);
+          if (!(p.dbg & TC_DBG_NOCOMMIT)) {
+            if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
+            else tc_commit(&empty_bar[stage]);
+          }
+          if (last_of_m) {                       // ... and the resident A k-block after its last n-block
+            if constexpr (kCtas == 2) tc_commit_cg2(&a_empty[kb], 3);
+            else tc_commit(&a_empty[kb]);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete → epilogue (of both CTAs)
         if constexpr (kCtas == 2) tc_commit_cg2(&tmem_full[acc], 3);
         else tc_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (new_m) { cur_m = m_blk; ++a_uses; }
       }
+      w_all.end();
+      if (trace) { trace[2] = w_ops.acc; trace[3] = w_acc.acc; trace[4] = w_all.acc; }
     }
   } else {
     // ===== epilogue: warps 2..9; lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
@@ -186,18 +279,43 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t it = 0;                             // staging-buffer parity (bf16 output)
     const uint32_t tmem_empty_remote = kCtas == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    const bool tr_w = trace != nullptr && warp == 2 && lane == 0;
+    WaitClock w_tm(tr_w), w_stg(tr_w), w_all(tr_w), w_ld(tr_w), w_st(tr_w);
+    long long n_tiles_done = 0;
+    w_all.begin();
+    for (int tile = tile0; tile < tile_end; tile += tile_step) {
       const int m_blk = (tile / n_blocks) * kCtas + (int)rank, n_blk = tile % n_blocks;
+      ++n_tiles_done;
+      w_tm.begin();
       mbar_wait(&tmem_full[acc], acc_phase);
+      w_tm.end();
       tc_fence_after_sync();
+      if (p.dbg & TC_DBG_NOEPI) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2 && rank != 0) mbar_arrive_cluster(tmem_empty_remote + (uint32_t)(acc * 8));
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int m = m_blk * TC_BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int ci = 0; ci < kChunks; ++ci) {
         const int c = col_half * kChunks + ci;
+        const int n0 = n_blk * BN + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+        float4 bv[8];
+        if (p.bias) {                            // L1 hits after the first tile; in flight under the TMEM load
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+        }
+        w_ld.begin();
         tmem_ld_wait();
+        w_ld.end();
         if (ci == kChunks - 1) {                 // accumulator fully read: hand the TMEM buffer back before the math
           tc_fence_before_sync();
           __syncwarp();
@@ -206,14 +324,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             else mbar_arrive(&tmem_empty[acc]);
           }
         }
-        const int n0 = n_blk * BN + c * 32;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            const float4 b = bv[j >> 2];
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
@@ -240,6 +357,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
           const int row0 = m_blk * TC_BM + quarter * 32;
+          if (p.dbg & TC_DBG_NOSTORE) {
+            float acc_sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_sum += v[j];
+            if (acc_sum == 1.2345e-30f) reinterpret_cast<float*>(p.C)[0] = acc_sum;   // keeps the math alive
+            continue;
+          }
+          w_st.begin();
           if (p.out_f32 == 1) {
             // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
             if (lane == 0) bulk_wait_read<0>();
@@ -290,16 +415,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & TC_DBG_NOTMA)) {
               tma_store_2d(&tmC, buf, n0, row0);
               bulk_commit();
             }
           }
+          w_st.end();
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    w_all.end();
     if (!kDirect && lane == 0) bulk_wait<0>();   // all tile stores complete before the CTA retires
+    if (tr_w) { trace[5] = w_tm.acc; trace[6] = w_stg.acc; trace[7] = w_all.acc; trace[8] = n_tiles_done; trace[9] = w_ld.acc; trace[10] = w_st.acc; }
   }
   tc_fence_before_sync();
   if constexpr (kCtas == 2) {
@@ -382,12 +510,13 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool kDirect, int kCtas>
+template <int BN, bool kDirect, int kCtas, bool kARes>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, kCtas>;
+  using Cfg = TcCfg<BN, kCtas, kARes>;
   static bool attr_set = false;
   if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas));
@@ -407,7 +536,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.numAttrs = kCtas > 1 ? 1 : 0;
   {
     ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
-    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas>, ta, tb, tcm, p));
+    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -433,14 +562,32 @@ static int pick_bn(int M, int N, int bm, int slots) {
   return best;
 }
 
-// 0 = single-CTA tiles only, 1 = CTA pairs where the problem is large enough (default); SMK_GEMM_CTA_PAIR overrides (tuning)
+// 0 = single-CTA tiles only (default: measured faster on every shape of this model), 1 = CTA pairs where the problem is
+// large enough (wins from K >= 1024 with N >= 512); SMK_GEMM_CTA_PAIR overrides (tuning)
 static int cta_pair_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("SMK_GEMM_CTA_PAIR");
-    mode = e ? atoi(e) : 1;
+    mode = e ? atoi(e) : 0;
   }
   return mode;
+}
+
+// SMK_GEMM_ARES=1 enables the A-resident schedule for K <= 384.  Default off: measured 5-10 % slower on this model's shapes
+// (the epilogue, not the operand feed, bounds those GEMMs; see profiles/r01_gemm_experiments.md)
+static int ares_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SMK_GEMM_ARES");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
+template <bool kDirect, int kCtas, bool kARes>
+static int launch_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
+  return BN == 256 ? launch_tc<256, kDirect, kCtas, kARes>(ta, tb, tcm, p, s)
+                   : (BN == 192 ? launch_tc<192, kDirect, kCtas, kARes>(ta, tb, tcm, p, s) : launch_tc<128, kDirect, kCtas, kARes>(ta, tb, tcm, p, s));
 }
 
 // A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements)
@@ -455,29 +602,38 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
   const bool pair = tok_hw == 0 && cta_pair_mode() != 0 && M > TC_BM;
+  const bool ares = tok_hw == 0 && ares_mode() != 0 && K <= TC_ARES_KB * TC_BK;
   const int kc = pair ? 2 : 1;
-  const int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
+  // A-resident: work is split by tile ranges, perfectly balanced for any width → the widest tile (fewest epilogue hand-overs)
+  int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
+  if (ares && !getenv("SMK_GEMM_BN")) BN = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
   CUtensorMap ta, tb, tcm;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));
-  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos};
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("SMK_GEMM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg};
   if (tok_hw > 0) {
     tcm = ta;   // unused by the direct-store epilogue
-    return BN == 256 ? launch_tc<256, true, 1>(ta, tb, tcm, p, s)
-                     : (BN == 192 ? launch_tc<192, true, 1>(ta, tb, tcm, p, s) : launch_tc<128, true, 1>(ta, tb, tcm, p, s));
+    return launch_bn<true, 1, false>(BN, ta, tb, tcm, p, s);
   }
   // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (bf16, 64-byte swizzle) per row
   const int esz = out_f32 == 1 ? 4 : 2;
   SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(out_f32 == 2 ? 3 * N : N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32,
                              out_f32 == 1 ? 128 : 64));
-  if (pair)
-    return BN == 256 ? launch_tc<256, false, 2>(ta, tb, tcm, p, s)
-                     : (BN == 192 ? launch_tc<192, false, 2>(ta, tb, tcm, p, s) : launch_tc<128, false, 2>(ta, tb, tcm, p, s));
-  return BN == 256 ? launch_tc<256, false, 1>(ta, tb, tcm, p, s)
-                   : (BN == 192 ? launch_tc<192, false, 1>(ta, tb, tcm, p, s) : launch_tc<128, false, 1>(ta, tb, tcm, p, s));
+  if (pair) return ares ? launch_bn<false, 2, true>(BN, ta, tb, tcm, p, s) : launch_bn<false, 2, false>(BN, ta, tb, tcm, p, s);
+  return ares ? launch_bn<false, 1, true>(BN, ta, tb, tcm, p, s) : launch_bn<false, 1, false>(BN, ta, tb, tcm, p, s);
 }
 
 }  // namespace smk
+
+extern "C" int smk_debug_gemm_trace(long long* buf) {   // tuning aid: >= 16 * grid counters; nullptr switches the trace off
+  SMK_CHECK_CUDA(cudaMemcpyToSymbol(smk::g_gemm_trace, &buf, sizeof(buf)));
+  return SMK_OK;
+}
 
 extern "C" int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* C, int64_t ldc, int M, int N, int K,
                              int epilogue, int out_f32, void* stream) {

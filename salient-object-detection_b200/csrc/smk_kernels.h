@@ -28,8 +28,9 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
 int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_bfloat16* out_a, __nv_bfloat16* out_b, int64_t rows,
                int K, cudaStream_t s);
 int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s);
-template <typename T>
-int im2col(const float* x, T* cols, int B, int H, int W, int P, int hp, int wp, cudaStream_t s);
+template <typename TIn, typename T>
+int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std /* host, 6 floats or null */,
+           cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
                     cudaStream_t s);
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);

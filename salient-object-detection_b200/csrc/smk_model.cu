@@ -371,9 +371,24 @@ extern "C" int smk_model_destroy(smk_model* m) {
   return SMK_OK;
 }
 
+static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8, const float* mean_std, int B, int H, int W, int all_layers,
+                              float* mask_pred, float* objectness, float* features, void* stream);
+
 extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int W, int all_layers, float* mask_pred,
                                  float* objectness, float* features, void* stream) {
   SMK_REQUIRE(m && x, "smk_model_forward: null pointer");
+  return model_forward_impl(m, x, nullptr, nullptr, B, H, W, all_layers, mask_pred, objectness, features, stream);
+}
+
+extern "C" int smk_model_forward_u8(smk_model* m, const uint8_t* x, const float* mean_std, int B, int H, int W, int all_layers,
+                                    float* mask_pred, float* objectness, float* features, void* stream) {
+  SMK_REQUIRE(m && x && mean_std, "smk_model_forward_u8: null pointer");
+  for (int c = 0; c < 3; ++c) SMK_REQUIRE(mean_std[3 + c] > 0.f, "smk_model_forward_u8: std[%d] must be positive", c);
+  return model_forward_impl(m, nullptr, x, mean_std, B, H, W, all_layers, mask_pred, objectness, features, stream);
+}
+
+static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8, const float* mean_std, int B, int H, int W, int all_layers,
+                              float* mask_pred, float* objectness, float* features, void* stream) {
   SMK_REQUIRE(B >= 0 && B <= m->max_batch, "batch %d exceeds max_batch %d", B, m->max_batch);
   SMK_REQUIRE(H == m->H && W == m->W, "image %dx%d does not match the model geometry %dx%d", H, W, m->H, m->W);
   if (B == 0) return SMK_OK;
@@ -390,7 +405,8 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
   // ---- encoder ------------------------------------------------------------------------------------
   if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
-    SMK_PROPAGATE(im2col<__nv_bfloat16>(x, Hm, B, H, W, c.patch, m->hp, m->wp, s));
+    if (x_u8) SMK_PROPAGATE((im2col<uint8_t, __nv_bfloat16>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s)));
+    else SMK_PROPAGATE((im2col<float, __nv_bfloat16>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s)));
     SMK_PROPAGATE(gemm_bf16_tc(Hm, Kpe, wb + m->o_pew, Kpe, w + m->o_peb, m->X, D, B * hw, D, Kpe, SMK_EPI_NONE, 1, hw, m->pos, s));
     SMK_PROPAGATE(assemble_tokens(nullptr, w + m->o_cls, m->pos, m->X, B, hw, D, true, s));
     for (int i = 0; i < c.depth; ++i) {
@@ -412,7 +428,8 @@ extern "C" int smk_model_forward(smk_model* m, const float* x, int B, int H, int
     SMK_PROPAGATE(gemm_bf16_tc(m->tokb, D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
   } else {
     float *Xn = (float*)m->Xn, *QKV = (float*)m->QKV, *AO = (float*)m->AO, *Hm = (float*)m->Hm;
-    SMK_PROPAGATE(im2col<float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, s));
+    if (x_u8) SMK_PROPAGATE((im2col<uint8_t, float>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s)));
+    else SMK_PROPAGATE((im2col<float, float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s)));
     SMK_PROPAGATE(gemm_f32(Hm, Kpe, w + m->o_pew, Kpe, w + m->o_peb, QKV, D, B * hw, D, Kpe, SMK_EPI_NONE, s));
     SMK_PROPAGATE(assemble_tokens(QKV, w + m->o_cls, m->pos, m->X, B, hw, D, false, s));
     for (int i = 0; i < c.depth; ++i) {

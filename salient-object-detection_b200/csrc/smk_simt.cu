@@ -381,36 +381,72 @@ SMK_ATT_INST(float, __nv_bfloat16)
 // ------------------------------------------------------------------------------------------------
 // Patch im2col (vision_transformer.py:184-188 conv k=s=P as a GEMM; :260-267 zero pad right/bottom):
 // cols[b*hw + py*wp + px][c*P*P + ky*P + kx] = x[b,c,py*P+ky,px*P+kx]
+// One CTA per (patch row, image): the 3 x P x W pixel strip goes through shared memory so that both the image reads
+// (whole rows) and the column writes (16-byte vectors of one patch row) are coalesced.
+// TIn = uint8_t: raw pixels, normalised here exactly like the reference's host-side loader
+// (datasets/base_dataset.py:250, torchvision to_tensor + normalize): ((float)u / 255 - mean[c]) / std[c] with IEEE
+// fp32 division and no FMA contraction → bit-identical to the float path fed with host-normalised images, at a quarter
+// of the host→device bytes.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+struct NormConst { float mean[3], std[3]; };
+
+template <typename TIn> __device__ __forceinline__ float load_pixel(const TIn* p, int c, const NormConst& nc);
+template <> __device__ __forceinline__ float load_pixel<float>(const float* p, int, const NormConst&) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* p, int c, const NormConst& nc) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg(p), 255.0f), nc.mean[c]), nc.std[c]);
+}
+
+template <typename TIn, typename T>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp) {
-  // grid (hp*wp, B); one CTA per patch; thread → (c, ky, kx) with kx fastest (coalesced 64-byte runs)
-  const int patch = blockIdx.x, b = blockIdx.y;
-  const int py = patch / wp, px = patch % wp;
-  const int K = 3 * P * P;
-  T* dst = cols + ((int64_t)b * hp * wp + patch) * K;
-  const float* src = x + (int64_t)b * 3 * H * W;
-  for (int i = threadIdx.x; i < K; i += 256) {
-    const int c = i / (P * P), r = i % (P * P), ky = r / P, kx = r % P;
-    const int yy = py * P + ky, xx = px * P + kx;
-    const float v = (yy < H && xx < W) ? src[((int64_t)c * H + yy) * W + xx] : 0.f;
-    dst[i] = from_float<T>(v);
+im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc) {
+  extern __shared__ __align__(16) uint8_t im2col_smem[];
+  T* strip = reinterpret_cast<T*>(im2col_smem);         // [3*P][ws], ws = wp*P + pad
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int Wp = wp * P, ws = Wp + 16 / (int)sizeof(T);
+  const TIn* src = x + (int64_t)b * 3 * H * W;
+  // phase 1: image rows → strip (zero beyond the image: make_input_divisible pads right/bottom)
+  for (int i = threadIdx.x; i < 3 * P * Wp; i += 256) {
+    const int r = i / Wp, xx = i - r * Wp, c = r / P, ky = r - c * P, yy = py * P + ky;
+    const float v = (yy < H && xx < W) ? load_pixel<TIn>(src + ((int64_t)c * H + yy) * W + xx, c, nc) : 0.f;
+    strip[r * ws + xx] = from_float<T>(v);
+  }
+  __syncthreads();
+  // phase 2: strip → cols, 16-byte vectors (kV elements of one patch row); K = 3*P*P, P % kV == 0
+  constexpr int kV = 16 / (int)sizeof(T);
+  const int K = 3 * P * P, vec_per_row = P / kV, vec_per_patch = K / kV;
+  T* dst = cols + ((int64_t)b * hp + py) * wp * K;
+  for (int i = threadIdx.x; i < wp * vec_per_patch; i += 256) {
+    const int px = i / vec_per_patch, j = i - px * vec_per_patch;     // j = (c*P + ky) * vec_per_row + kxv
+    const int r = j / vec_per_row, kxv = j - r * vec_per_row;
+    const uint4 v = *reinterpret_cast<const uint4*>(strip + r * ws + px * P + kxv * kV);
+    *reinterpret_cast<uint4*>(dst + (int64_t)px * K + j * kV) = v;
   }
 }
-template <typename T>
-int im2col(const float* x, T* cols, int B, int H, int W, int P, int hp, int wp, cudaStream_t s) {
+template <typename TIn, typename T>
+int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s) {
   if (B == 0) return SMK_OK;
   SMK_REQUIRE(B <= 65535, "im2col: batch too large");
+  SMK_REQUIRE(P % (16 / (int)sizeof(T)) == 0, "im2col: patch size %d must be a multiple of %d", P, 16 / (int)sizeof(T));
+  NormConst nc{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (mean_std) for (int c = 0; c < 3; ++c) { nc.mean[c] = mean_std[c]; nc.std[c] = mean_std[3 + c]; }
+  const int smem = 3 * P * (wp * P + 16 / (int)sizeof(T)) * (int)sizeof(T);
+  SMK_REQUIRE(smem <= 227 * 1024, "im2col: image too wide for the shared-memory strip (%d bytes)", smem);
+  static int attr_max = 0;
+  if (smem > 48 * 1024 && smem > attr_max) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel<TIn, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_max = smem;
+  }
   {
-    ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * (4.0 + sizeof(T)), s);
-    im2col_kernel<T><<<dim3(hp * wp, B), 256, 0, s>>>(x, cols, H, W, P, hp, wp);
+    ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + sizeof(T)), s);
+    im2col_kernel<TIn, T><<<dim3(hp, B), 256, smem, s>>>(x, cols, H, W, P, hp, wp, nc);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
-template int im2col<float>(const float*, float*, int, int, int, int, int, int, cudaStream_t);
-template int im2col<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, int, int, cudaStream_t);
+template int im2col<float, float>(const float*, float*, int, int, int, int, int, int, const float*, cudaStream_t);
+template int im2col<float, __nv_bfloat16>(const float*, __nv_bfloat16*, int, int, int, int, int, int, const float*, cudaStream_t);
+template int im2col<uint8_t, float>(const uint8_t*, float*, int, int, int, int, int, int, const float*, cudaStream_t);
+template int im2col<uint8_t, __nv_bfloat16>(const uint8_t*, __nv_bfloat16*, int, int, int, int, int, int, const float*, cudaStream_t);
 
 // tokens[b,0,:] = cls + pos[0];  tokens[b,1+p,:] = patch_out[b*hw+p,:] + pos[1+p]   (vision_transformer.py:276-280)
 __global__ void __launch_bounds__(128)

@@ -10,6 +10,7 @@ all metric reductions on the GPU; the host only turns integer counts into ratios
 means in dataset order (bit-compatible with `AverageMeter`).
 """
 import os
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Iterable, Optional
 
 import numpy as np
@@ -85,6 +86,8 @@ class Evaluator:
         self.model, self.arch, self.dir_dataset, self.visualizer, self.debug = network, arch, dir_dataset, visualizer, debug
         self.dataset = dataset
         self.records = None
+        self._copy_stream = None
+        self._pinned = {}
 
     def _batches(self, dataset_name: str, batch_size: int) -> Iterable[dict]:
         if self.dataset is None:
@@ -98,23 +101,69 @@ class Evaluator:
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.SmkError("the B200 evaluator runs on CUDA devices only")
-        recs = []
-        for dict_data in self._batches(dataset_name, batch_size):
-            x = dict_data["x"].to(device, non_blocking=True)
-            gt = dict_data["m"].to(device, non_blocking=True)
-            out = self.model(x, encoder_only=False, skip_decoder=False)     # BaseStructure._forward contract
-            rec = eval_batch(out["mask_pred"], out["objectness"], gt, up=4)
-            recs.append(rec)
-            if self.debug:
-                break
-        if not recs:
-            raise _lib.SmkError("empty dataset")
-        m_counts = torch.cat([r.m_counts for r in recs]).cpu().numpy()       # one sync for the whole sweep
-        m_sums = torch.cat([r.m_sums for r in recs]).cpu().numpy()
-        self.records = {"m_counts": m_counts, "m_sums": m_sums,
-                        "idx": torch.cat([r.idx for r in recs]).cpu().numpy(),
-                        "q_counts": torch.cat([r.q_counts for r in recs]).cpu().numpy()}
-        res = summarize(m_counts, m_sums)
+        # Three overlapped stages per batch (the reference does them serially, with >= 16 syncs per image):
+        #   copy stream   : host → device of batch i+1 (pinned host memory makes it asynchronous)
+        #   compute stream: model forward + fused evaluation of batch i, then device → host of its records
+        #   worker thread : integer counts → float32 metric values of batch i-1 (numpy, releases the GIL)
+        compute = torch.cuda.current_stream(device)
+        copy = self._copy_stream if getattr(self, "_copy_stream", None) is not None and self._copy_stream.device == device \
+            else torch.cuda.Stream(device)
+        self._copy_stream = copy
+
+        def stage(dict_data):
+            x, gt = dict_data["x"], dict_data["m"]
+            if gt.device.type == "cpu" and gt.dtype != torch.uint8:
+                gt = (gt != 0).to(torch.uint8)                 # 1 byte per pixel over PCIe instead of the loader's int64
+            copy.wait_stream(compute)                          # do not run ahead of the batch that still owns the buffers
+            with torch.cuda.stream(copy):
+                xd, gd = x.to(device, non_blocking=True), gt.to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return xd, gd, ev
+
+        ring = 4                                               # pinned record buffers, reused round-robin
+
+        def fetch(rec, i):
+            slot = self._pinned.setdefault((i % ring, rec.m_counts.shape[0], rec.q_counts.shape[1]), {})
+            if not slot:       # page-locked allocations are slow and synchronise the device: made once, then recycled
+                for k in ("m_counts", "m_sums", "idx", "q_counts"):
+                    t = getattr(rec, k)
+                    slot[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            for k, t in slot.items():
+                t.copy_(getattr(rec, k), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            return slot, ev
+
+        def reduce(host, ev):
+            ev.synchronize()
+            arrs = {k: t.numpy().copy() for k, t in host.items()}      # frees the pinned slot for batch i + ring
+            return arrs, finalize(arrs["m_counts"], arrs["m_sums"])
+
+        pending = []
+        with torch.cuda.device(device), ThreadPoolExecutor(max_workers=1) as pool:
+            it = iter(self._batches(dataset_name, batch_size))
+            first = next(it, None)
+            nxt = stage(first) if first is not None else None
+            while nxt is not None:
+                x, gt, ev = nxt
+                following = None if self.debug else next(it, None)
+                nxt = stage(following) if following is not None else None
+                compute.wait_event(ev)
+                x.record_stream(compute)
+                gt.record_stream(compute)
+                out = self.model(x, encoder_only=False, skip_decoder=False)     # BaseStructure._forward contract
+                rec = eval_batch(out["mask_pred"], out["objectness"], gt, up=4)
+                if len(pending) >= ring:
+                    pending[len(pending) - ring].result()      # the slot about to be overwritten has been copied out
+                pending.append(pool.submit(reduce, *fetch(rec, len(pending))))
+            if not pending:
+                raise _lib.SmkError("empty dataset")
+            done = [f.result() for f in pending]
+        self.records = {k: np.concatenate([d[0][k] for d in done]) for k in ("m_counts", "m_sums", "idx", "q_counts")}
+        vals = {k: np.concatenate([d[1][k] for d in done]) for k in METRIC_KEYS}
+        res = {k: running_mean(vals[k][:, 0]) for k in METRIC_KEYS}
+        res.update({k + "_ub": running_mean(vals[k][:, 1]) for k in METRIC_KEYS})
         if dir_ckpt is not None:
             os.makedirs(dir_ckpt, exist_ok=True)
             with open(f"{dir_ckpt}/metrics_{dataset_name}.txt", "w") as f:

@@ -35,13 +35,62 @@ def f_from_counts(tp, tp_fp, tp_fn, beta_square: float = 0.3):
 
 
 def counts_above_thresholds(hist: np.ndarray) -> np.ndarray:
-    """hist[..., 256] over bin(p) = #{k : t_k < p}  →  count(p > t_k) for k = 0..254 = Σ_{b>k} hist[b]."""
-    total = hist.sum(axis=-1, keepdims=True, dtype=np.int64)
-    return (total - np.cumsum(hist, axis=-1, dtype=np.int64))[..., :255]
+    """hist[..., 256] over bin(p) = #{k : t_k < p}  →  count(p > t_k) for k = 0..254 = Σ_{b>k} hist[b].
+    Stays in the input's integer width (per-image pixel counts fit int32)."""
+    cs = np.cumsum(hist, axis=-1, dtype=hist.dtype if hist.dtype in (np.int32, np.int64) else np.int64)
+    return cs[..., 255:256] - cs[..., :255]
 
 
 def s_measure_from_sums(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
-    """s_measure.py:108-124 from moment sums (float64).  counts [...,528] int, sums [...,32] float64."""
+    """s_measure.py:108-124 from moment sums (float64).  counts [...,528] int, sums [...,32] float64.
+    Vectorised over records; every expression keeps the operation order of `_s_measure_from_sums_loop` (same IEEE
+    double results, NaN cases included)."""
+    counts = np.asarray(counts)
+    sums = np.asarray(sums, np.float64)
+    shape = counts.shape[:-1]
+    c = counts.reshape(-1, counts.shape[-1])
+    s = sums.reshape(-1, sums.shape[-1])
+    n, G = c[:, 519].astype(np.float64), c[:, 514].astype(np.float64)
+    with np.errstate(all="ignore"):
+        mean_p = s[:, 0] / n
+
+        def obj(sum1, sum2, cnt):                          # s_measure.py:54-60, unbiased std
+            mu = sum1 / cnt
+            var = np.where(cnt > 1, (sum2 - cnt * mu * mu) / (cnt - 1), np.nan)
+            sd = np.sqrt(np.maximum(var, 0.0))
+            return 2.0 * mu / (mu * mu + 1.0 + sd + 1e-20)
+        u = G / n
+        s_obj = u * obj(s[:, 3], s[:, 4], G) + (1 - u) * obj(s[:, 5], s[:, 6], n - G)
+        X, Y = c[:, 517].astype(F32), c[:, 518].astype(F32)
+        hw = n.astype(F32)
+        q = s[:, 8:28].reshape(-1, 4, 5)
+        w1 = (X * Y) / hw
+        w2 = q[:, 1, 0].astype(F32) / hw
+        w3 = q[:, 2, 0].astype(F32) / hw
+        w4 = F32(1) - w1 - w2 - w3
+        Q = []
+        for k in range(4):
+            N, sp, sp2, sg, spg = (q[:, k, j] for j in range(5))
+            x, y = sp / N, sg / N
+            den = N - 1 + 1e-20
+            sx2 = (sp2 - N * x * x) / den
+            sy2 = (sg - N * y * y) / den
+            sxy = (spg - N * x * y) / den
+            a = 4 * x * y * sxy
+            b = (x * x + y * y) * (sx2 + sy2)
+            a = np.where(((y == 0.0) | (y == 1.0)) & ~np.isnan(a), 0.0, a)   # (g - ȳ) ≡ 0 → the reference's σxy is an exact zero
+            Qk = np.where(a != 0, a / (b + 1e-20), np.where(b == 0, 1.0, 0.0))
+            Q.append(np.where(N == 0, np.nan, Qk))
+        s_reg = w1.astype(np.float64) * Q[0] + w2.astype(np.float64) * Q[1] + w3.astype(np.float64) * Q[2] + w4.astype(np.float64) * Q[3]
+        val = alpha * s_obj + (1 - alpha) * s_reg
+        val = np.where(val < 0, 0.0, val)
+        out = np.where(G == 0, 1.0 - mean_p, np.where(G == n, mean_p, val))
+    return out.reshape(shape)
+
+
+def _s_measure_from_sums_loop(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
+    """Per-record scalar restatement (python floats) of `s_measure_from_sums`; kept as the readable definition and as
+    the test oracle of the vectorised version."""
     counts = np.asarray(counts)
     sums = np.asarray(sums, np.float64)
     out = np.empty(counts.shape[:-1], np.float64)
@@ -103,9 +152,11 @@ def s_measure_from_sums(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5
 def finalize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, np.ndarray]:
     """Per-mask metric values from the GPU records.  m_counts [...,528] int32, m_sums [...,32] float64.
     Returns float32 arrays of shape [...] (s_measure float64, like the reference's python float)."""
-    c = np.asarray(m_counts).astype(np.int64)
+    c = np.asarray(m_counts)
+    if c.dtype not in (np.int32, np.int64):
+        c = c.astype(np.int64)
     s = np.asarray(m_sums, np.float64)
-    tp05, tpfp05, G, tpm, tpfpm, n = c[..., 512], c[..., 513], c[..., 514], c[..., 515], c[..., 516], c[..., 519]
+    tp05, tpfp05, G, tpm, tpfpm, n = (c[..., i].astype(np.int64) for i in (512, 513, 514, 515, 516, 519))
     union = tpfp05 + G - tp05
     fg_above = counts_above_thresholds(c[..., 0:256])
     all_above = fg_above + counts_above_thresholds(c[..., 256:512])

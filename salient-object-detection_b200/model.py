@@ -65,6 +65,8 @@ class SelfMaskB200(torch.nn.Module):
         # attributes the reference callers read (maskformer.py:32-34,107,184-185)
         self.encoder = SimpleNamespace(patch_size=patch_size, depth=12, n_embs=384, n_heads=6, mlp_ratio=4)
         self.max_batch = max_batch
+        # uint8 inputs: the loader's normalisation constants (datasets/duts.py ImageNet mean / std, applied at base_dataset.py:250)
+        self.pixel_mean, self.pixel_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self._table = None
         self._blob = None          # fp32 weights, one device tensor in the library's canonical order
         self._handles = {}         # (H, W) -> (handle, workspace tensor)
@@ -158,12 +160,15 @@ class SelfMaskB200(torch.nn.Module):
     # ---- forward ------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x: torch.Tensor, encoder_only: bool = False, skip_decoder: bool = False) -> Dict[str, torch.Tensor]:
-        """x: b x 3 x H x W float32 on the GPU (maskformer.py:164).  `skip_decoder` is accepted and ignored,
-        as in the reference (:118-135)."""
+        """x: b x 3 x H x W float32 on the GPU (maskformer.py:164), ImageNet-normalised as the reference's loader
+        leaves it (datasets/base_dataset.py:250) — or uint8 raw pixels, in which case that normalisation
+        (`self.pixel_mean` / `self.pixel_std`) is fused into the patch-embedding im2col, bit-identically.
+        `skip_decoder` is accepted and ignored, as in the reference (:118-135)."""
         if x.ndim != 4 or x.shape[1] != 3:
             raise SmkError(f"expected b x 3 x H x W, got {tuple(x.shape)}")
         _lib.require_cuda(x, "x")
-        x = x.contiguous().float()
+        is_u8 = x.dtype == torch.uint8
+        x = x.contiguous() if is_u8 else x.contiguous().float()
         B, _, H, W = x.shape
         cfg = self.cfg
         hp, wp = -(-H // cfg.patch), -(-W // cfg.patch)
@@ -171,8 +176,15 @@ class SelfMaskB200(torch.nn.Module):
             handle = self._handle(B, H, W)
             L = cfg.dec_layers if (self.return_intermediate and not encoder_only) else 1
             ho, wo = hp * cfg.scale_factor, wp * cfg.scale_factor
+            def run(all_layers, mp, ob, ft):
+                if is_u8:
+                    ms = (C.c_float * 6)(*self.pixel_mean, *self.pixel_std)
+                    check(lib().smk_model_forward_u8(handle, ptr(x), ms, B, H, W, all_layers, mp, ob, ft, stream_ptr()),
+                          "smk_model_forward_u8")
+                else:
+                    check(lib().smk_model_forward(handle, ptr(x), B, H, W, all_layers, mp, ob, ft, stream_ptr()), "smk_model_forward")
             if encoder_only:
-                check(lib().smk_model_forward(handle, ptr(x), B, H, W, 0, None, None, None, stream_ptr()), "smk_model_forward")
+                run(0, None, None, None)
                 tok = torch.empty(B, hp * wp + 1, cfg.dim, dtype=torch.float32, device=x.device)
                 check(lib().smk_model_tap(handle, 1, ptr(tok), tok.numel(), stream_ptr()), "smk_model_tap")
                 # maskformer.py:183-189 (the reference `.view`s a b x D x hw tensor; here: b x h x w x D tokens)
@@ -180,8 +192,7 @@ class SelfMaskB200(torch.nn.Module):
             mask_pred = torch.empty(B, L, cfg.n_queries, ho, wo, dtype=torch.float32, device=x.device)
             objectness = torch.empty(B, L, cfg.n_queries, dtype=torch.float32, device=x.device)
             features = torch.empty(B, cfg.dim, dtype=torch.float32, device=x.device)
-            check(lib().smk_model_forward(handle, ptr(x), B, H, W, 1 if L > 1 else 0, ptr(mask_pred), ptr(objectness),
-                                          ptr(features), stream_ptr()), "smk_model_forward")
+            run(1 if L > 1 else 0, ptr(mask_pred), ptr(objectness), ptr(features))
         if self.return_intermediate:
             return {"objectness": objectness.unsqueeze(-1), "mask_pred": mask_pred, "features": features}
         return {"objectness": objectness[:, 0].unsqueeze(-1), "mask_pred": mask_pred[:, 0], "features": features}

@@ -1,15 +1,24 @@
 #!/bin/bash
-# ncu evidence for profiles/: launch list of one bench run + full-set captures of the top kernels.
+# ncu evidence for profiles/: launch list of exactly one bench step + full-set captures of one launch of every
+# distinct kernel / shape of the step.  `bench.py --ncu-step` brackets ONE step with cudaProfilerStart/Stop, so with
+# --profile-from-start off the launch indices are the step's own (bf16 mode, 224x224, nq 20):
+#   0 im2col, 1 patch-embed GEMM, 2 cls/pos rows, 3+7i.. encoder layer i = LN qkv attn proj LN fc1 fc2,
+#   87 final LN, 88 memory K/V GEMM, 89 split, 90+12l.. decoder layer l, 162 mask head, 163-167 objectness/features, 168-169 eval
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
-tail -c 600 gpurun_out/plain.log
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1100 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+TAG=${TAG:-prof}
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+tail -c 300 gpurun_out/plain.log
+CMD="python bench.py --ncu-step --warmup 3"
+$CMD > gpurun_out/plain_step.log 2>&1 || { echo "plain step run failed"; tail -5 gpurun_out/plain_step.log; exit 1; }
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tc -s 30 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
-echo "gemm rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:attn_tc|query_iou|mask_metrics|mask_head|layernorm" -s 40 -c 8 -o gpurun_out/prof_misc $CMD > gpurun_out/ncu_misc.log 2>&1
-echo "misc rc=$?"
+cap() { name=$1; skip=$2; count=$3
+  ncu --profile-from-start off --set full --clock-control none --import-source on -s $skip -c $count -f -o gpurun_out/${TAG}_$name $CMD > gpurun_out/ncu_$name.log 2>&1
+  echo "$name rc=$?"; }
+cap enc 10 7
+cap kv 87 2
+cap dec 102 12
+cap tail 162 8
 ls -la gpurun_out/*.ncu-rep

@@ -152,6 +152,43 @@ def test_evaluator_matches_reference_fixture(golden_dir, mode, tmp_path):
     assert worst <= tol, (worst, res, ref["result"])
 
 
+@pytest.mark.parametrize("mode,H,W", [("fp32", 224, 224), ("bf16", 224, 224), ("bf16", 200, 180)])
+def test_uint8_input_is_bit_identical_to_host_normalised_float(mode, H, W):
+    """Raw uint8 pixels normalised inside the im2col kernel == the reference loader's host-side
+    `TF.normalize(TF.to_tensor(img), mean, std)` (datasets/base_dataset.py:250) fed as float32: identical bits out."""
+    B = 3
+    model, sd, cfg = make_model(nq=20, mode=mode, max_batch=B)
+    u8 = O.synth_images_u8(B, H, W, seed=77)
+    a = model(O.normalize_images(u8).to(DEV))
+    b = model(torch.from_numpy(u8).to(DEV))
+    torch.cuda.synchronize()
+    for k in ("mask_pred", "objectness", "features"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_evaluator_pipeline_equals_batchwise_calls():
+    """The overlapped evaluator (copy stream / compute stream / finalisation thread, several batches in flight) returns
+    exactly what per-batch synchronous calls give, records in dataset order."""
+    B, n_batches = 4, 5
+    model, sd, cfg = make_model(nq=20, mode="bf16", max_batch=B)
+    xs = [torch.from_numpy(O.synth_images_u8(B, 224, 224, seed=100 + i)).pin_memory() for i in range(n_batches)]
+    gs = [torch.from_numpy(O.synth_gt(B, 224, 224, seed=200 + i, edge_every=3)).pin_memory() for i in range(n_batches)]
+    ev = S.Evaluator(network=model, dataset=[{"x": x, "m": g} for x, g in zip(xs, gs)])
+    res = ev(dataset_name="synthetic", dir_ckpt=None, batch_size=B, device=DEV)
+    counts, sums = [], []
+    for x, g in zip(xs, gs):
+        out = model(x.to(DEV))
+        rec = S.eval_batch(out["mask_pred"], out["objectness"], g.long().to(DEV))     # int64 GT like the reference loader
+        counts.append(rec.m_counts.cpu().numpy())
+        sums.append(rec.m_sums.cpu().numpy())
+    counts, sums = np.concatenate(counts), np.concatenate(sums)
+    assert np.array_equal(ev.records["m_counts"], counts)
+    assert np.array_equal(ev.records["m_sums"], sums, equal_nan=True)
+    ref = S.summarize(counts, sums)
+    for k, v in ref.items():
+        assert (np.isnan(v) and np.isnan(res[k])) or v == res[k], k
+
+
 def test_rejects_wrong_inputs():
     model, _, _ = make_model(nq=20, mode="fp32", max_batch=1)
     with pytest.raises(S.SmkError):

@@ -88,6 +88,34 @@ def test_finalize_reproduces_reference_metrics(golden_dir):
     np.testing.assert_allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=0, atol=2e-5)
 
 
+def test_vectorised_s_measure_equals_scalar_definition(golden_dir):
+    """The numpy-vectorised S-measure finalisation is bit-identical (NaNs included) to the per-record scalar version."""
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    recs = [numpy_record(p, gt) for p, gt in zip(g["preds"], g["gts"])]
+    rng = np.random.default_rng(5)
+    H, W = 40, 56
+    for kind in range(12):                  # empty / full GT, single pixel, centroid on the border, constant predictions
+        p = rng.random((H, W), dtype=np.float32)
+        gt = np.zeros((H, W), bool)
+        if kind == 1: gt[:] = True
+        elif kind == 2: gt[0, 0] = True
+        elif kind == 3: gt[:, 0] = True
+        elif kind == 4: gt[0, :] = True
+        elif kind == 5: gt[H - 1, W - 1] = True
+        elif kind == 6: gt[10:20, 10:30] = True; p[:] = 0.0
+        elif kind == 7: gt[10:20, 10:30] = True; p[:] = 1.0
+        elif kind == 8: gt[10:20, 10:30] = True; p = gt.astype(np.float32)
+        elif kind >= 9: gt = rng.random((H, W)) > 0.3 * (kind - 8)
+        recs.append(numpy_record(p, gt))
+    counts, sums = np.stack([r[0] for r in recs]), np.stack([r[1] for r in recs])
+    a, b = M.s_measure_from_sums(counts, sums), M._s_measure_from_sums_loop(counts, sums)
+    assert a.dtype == b.dtype == np.float64
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.isnan(a).any()
+    assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    a2 = M.s_measure_from_sums(counts.reshape(-1, 2, 528)[: len(recs) // 2], sums.reshape(-1, 2, 32)[: len(recs) // 2])
+    assert a2.shape == (len(recs) // 2, 2)
+
+
 def test_histogram_counts_equal_direct_threshold_counts():
     rng = np.random.default_rng(0)
     thr = O.fmax_thresholds()
