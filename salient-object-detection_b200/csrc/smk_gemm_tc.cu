@@ -70,6 +70,12 @@ struct TcCfg {
   static_assert((2 * kStages + 4 + 2 * TC_ARES_KB) * 8 + 8 <= TC_BAR_BYTES, "barrier area");
 };
 
+// Tuning instrumentation (wait-cycle trace, stage-isolation switches) is compiled in only with -DSMK_GEMM_TUNE=1
+// (SMK_BUILD_TUNE=1 python __graft_entry__.py build): it costs 2-5 % in registers and branches otherwise.
+#ifndef SMK_GEMM_TUNE
+#define SMK_GEMM_TUNE 0
+#endif
+
 // optional wait-cycle accounting (tuning scripts only): per CTA 16 counters
 //   [0] producer: cycles waiting for a free ring slot   [1] producer: total loop cycles
 //   [2] MMA: waiting for operands (full barriers)       [3] MMA: waiting for a free accumulator   [4] MMA: total
@@ -79,9 +85,9 @@ __device__ long long* g_gemm_trace = nullptr;
 struct WaitClock {
   long long acc = 0, t0 = 0;
   bool on;
-  __device__ explicit WaitClock(bool on_) : on(on_) {}
-  __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
-  __device__ __forceinline__ void end() { if (on) acc += clock64() - t0; }
+  __device__ explicit WaitClock(bool on_) : on(SMK_GEMM_TUNE && on_) {}
+  __device__ __forceinline__ void begin() { if (SMK_GEMM_TUNE && on) t0 = clock64(); }
+  __device__ __forceinline__ void end() { if (SMK_GEMM_TUNE && on) acc += clock64() - t0; }
 };
 
 // tuning-only switches in TcGemmParams::dbg (SMK_GEMM_DEBUG): results are garbage, timing isolates one pipeline stage
@@ -135,7 +141,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tile0 = kARes ? (int)((int64_t)cl * num_tiles / n_cl) : cl;
   const int tile_end = kARes ? (int)((int64_t)(cl + 1) * num_tiles / n_cl) : num_tiles;
   const int tile_step = kARes ? 1 : n_cl;
-  long long* trace = g_gemm_trace ? g_gemm_trace + 16 * blockIdx.x : nullptr;
+  long long* trace = (SMK_GEMM_TUNE && g_gemm_trace) ? g_gemm_trace + 16 * blockIdx.x : nullptr;
+  const int dbg = SMK_GEMM_TUNE ? p.dbg : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -174,7 +181,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         const bool new_m = kARes && m_blk != cur_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          if (new_m && !((p.dbg & TC_DBG_NOLOAD) && a_fills > 0)) {
+          if (new_m && !((dbg & TC_DBG_NOLOAD) && a_fills > 0)) {
             // slot kb is released when the last n-block of the previous m-block has consumed it
             mbar_wait(&a_empty[kb], (a_fills & 1) ^ 1);
             uint8_t* sa = smem_base + kb * Cfg::kABytes;
@@ -186,7 +193,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_2d(sa, &tmA, &a_full[kb], kb * TC_BK, m_blk * TC_BM);
             }
           }
-          if ((p.dbg & TC_DBG_NOLOAD) && n_loads++ >= Cfg::kStages) continue;
+          if ((dbg & TC_DBG_NOLOAD) && n_loads++ >= Cfg::kStages) continue;
           w_slot.begin();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           w_slot.end();
@@ -234,8 +241,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
           w_ops.begin();
-          const bool skip_wait = (p.dbg & TC_DBG_NOLOAD) && n_used++ >= Cfg::kStages;
-          if (new_m && !((p.dbg & TC_DBG_NOLOAD) && a_uses > 0)) mbar_wait(&a_full[kb], a_uses & 1);
+          const bool skip_wait = (dbg & TC_DBG_NOLOAD) && n_used++ >= Cfg::kStages;
+          if (new_m && !((dbg & TC_DBG_NOLOAD) && a_uses > 0)) mbar_wait(&a_full[kb], a_uses & 1);
           if (!skip_wait) mbar_wait(&full_bar[stage], phase);
           w_ops.end();
           tc_fence_after_sync();
@@ -248,7 +255,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (!(p.dbg & TC_DBG_NOCOMMIT)) {
+          if (!(dbg & TC_DBG_NOCOMMIT)) {
             if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
             else tc_commit(&empty_bar[stage]);
           }
@@ -290,7 +297,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full[acc], acc_phase);
       w_tm.end();
       tc_fence_after_sync();
-      if (p.dbg & TC_DBG_NOEPI) {
+      if (dbg & TC_DBG_NOEPI) {
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
@@ -357,7 +364,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
           const int row0 = m_blk * TC_BM + quarter * 32;
-          if (p.dbg & TC_DBG_NOSTORE) {
+          if (dbg & TC_DBG_NOSTORE) {
             float acc_sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc_sum += v[j];
@@ -415,7 +422,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && !(p.dbg & TC_DBG_NOTMA)) {
+            if (lane == 0 && !(dbg & TC_DBG_NOTMA)) {
               tma_store_2d(&tmC, buf, n0, row0);
               bulk_commit();
             }

@@ -396,19 +396,49 @@ template <> __device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* 
   return __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg(p), 255.0f), nc.mean[c]), nc.std[c]);
 }
 
+template <typename TIn> __device__ __forceinline__ void load_pixels4(const TIn* p, int c, const NormConst& nc, float (&v)[4]);
+template <> __device__ __forceinline__ void load_pixels4<float>(const float* p, int, const NormConst&, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load_pixels4<uint8_t>(const uint8_t* p, int c, const NormConst& nc, float (&v)[4]) {
+  const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+  const uint8_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u[e], 255.0f), nc.mean[c]), nc.std[c]);
+}
+__device__ __forceinline__ void store4(float* dst, const float (&v)[4]) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc) {
+im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc, bool vec_ok) {
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   T* strip = reinterpret_cast<T*>(im2col_smem);         // [3*P][ws], ws = wp*P + pad
   const int py = blockIdx.x, b = blockIdx.y;
   const int Wp = wp * P, ws = Wp + 16 / (int)sizeof(T);
   const TIn* src = x + (int64_t)b * 3 * H * W;
-  // phase 1: image rows → strip (zero beyond the image: make_input_divisible pads right/bottom)
-  for (int i = threadIdx.x; i < 3 * P * Wp; i += 256) {
-    const int r = i / Wp, xx = i - r * Wp, c = r / P, ky = r - c * P, yy = py * P + ky;
-    const float v = (yy < H && xx < W) ? load_pixel<TIn>(src + ((int64_t)c * H + yy) * W + xx, c, nc) : 0.f;
-    strip[r * ws + xx] = from_float<T>(v);
+  // phase 1: image rows → strip, 4 pixels per thread (zero beyond the image: make_input_divisible pads right/bottom)
+  const int Wq = Wp >> 2;
+  for (int i = threadIdx.x; i < 3 * P * Wq; i += 256) {
+    const int r = i / Wq, xx = (i - r * Wq) << 2, c = r / P, ky = r - c * P, yy = py * P + ky;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (yy < H) {
+      const TIn* row = src + ((int64_t)c * H + yy) * W;
+      if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, nc, v);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, nc);
+      }
+    }
+    store4(strip + r * ws + xx, v);
   }
   __syncthreads();
   // phase 2: strip → cols, 16-byte vectors (kV elements of one patch row); K = 3*P*P, P % kV == 0
@@ -438,7 +468,8 @@ int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, co
   }
   {
     ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + sizeof(T)), s);
-    im2col_kernel<TIn, T><<<dim3(hp, B), 256, smem, s>>>(x, cols, H, W, P, hp, wp, nc);
+    const bool vec_ok = (W & 3) == 0 && ((uintptr_t)x % (4 * sizeof(TIn))) == 0;   // 4-pixel vector loads stay aligned in every row
+    im2col_kernel<TIn, T><<<dim3(hp, B), 256, smem, s>>>(x, cols, H, W, P, hp, wp, nc, vec_ok);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
