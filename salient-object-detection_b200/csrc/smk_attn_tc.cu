@@ -92,6 +92,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after_sync();
   // through a warp reduction (REDUX → uniform register) so that ptxas can keep the MMA operands in uniform registers
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_ptr);
+  pdl_wait();      // PDL: the set-up above overlaps the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer (whole warp, one elected lane issues) =====
@@ -382,7 +384,7 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   const int grid = n_items < at_num_sms() ? n_items : at_num_sms();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AT_DH * heads * B, s);
-    attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, s>>>(tq, tk, tv, to, p);
+    SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;

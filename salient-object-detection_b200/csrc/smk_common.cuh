@@ -51,6 +51,31 @@ struct ProfScope {
     if (_s != SMK_OK) return _s; \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// A step is ~170 small-to-medium kernels in one stream.  Launched with the programmatic-stream-serialization attribute, a
+// kernel's CTAs may be scheduled while the previous kernel's last CTAs are still running: launch latency, barrier / TMEM
+// set-up and tensor-map prefetch overlap that tail.  Contract: a kernel launched through launch_pdl() executes
+// pdl_wait() before its first global-memory access (it returns once the previous grid has completed and flushed), and
+// pdl_trigger() right after (lets its own successor be scheduled as soon as SM resources free up).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // SMK_PDL=0 switches the attribute off (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

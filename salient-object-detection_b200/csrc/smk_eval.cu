@@ -291,6 +291,8 @@ mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, cons
 __global__ void __launch_bounds__(kEvalThreads)
 query_iou_x4_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
                     int nq, int hp, int wp, int H, int W, int32_t* __restrict__ q_counts) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float plane[];
   __shared__ int red[kEvalWarps];
   const int q = blockIdx.x, b = blockIdx.y;
@@ -331,6 +333,8 @@ mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, c
                        int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
                        int nq, int hp, int wp, int H, int W, const float* __restrict__ thresholds,
                        int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float dyn[];
   __shared__ int hist[kEvalWarps][512];
   __shared__ float thr[256];
@@ -571,7 +575,8 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     // algorithmic bytes "as if materialised" (SURVEY.md §8d): every full-resolution mask pixel (fp32) + the GT plane
     ProfScope prof(PROF_EVAL, (double)B * ((double)nq * H * W * 4.0 + (double)H * W), s);
     if (x4)
-      query_iou_x4_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, H, W, q_counts);
+      SMK_CHECK_CUDA(launch_pdl(query_iou_x4_kernel, dim3(nq, B), dim3(kEvalThreads), (size_t)plane_bytes, s, mask_pred, batch_stride, gt, nq, hp, wp, H, W,
+                                q_counts));
     else
       query_iou_kernel<<<dim3(nq, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, gt, nq, hp, wp, up, H, W, q_counts);
   }
@@ -579,8 +584,8 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
   {
     ProfScope prof(PROF_EVAL, (double)B * 2.0 * ((double)H * W * 4.0 + (double)H * W), s);
     if (x4)
-      mask_metrics_x4_kernel<<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq,
-                                                                          hp, wp, H, W, g_thresholds, idx, m_counts, m_sums);
+      SMK_CHECK_CUDA(launch_pdl(mask_metrics_x4_kernel, dim3(2, B), dim3(kEvalThreads), (size_t)plane_bytes, s, mask_pred, batch_stride, objectness,
+                                obj_stride, q_counts, gt, nq, hp, wp, H, W, g_thresholds, idx, m_counts, m_sums));
     else
       mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
           mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);

@@ -166,6 +166,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // tcgen05.mma in an ELECT / R2UR.BROADCAST / branch "waterfall" that costs ~100 cycles per MMA — more than a
   // 128 x 128 x 16 MMA (64 cycles) takes to execute, which made the issuing thread the bottleneck of every GEMM.
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_ptr);
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -534,13 +537,22 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (kCtas > 1) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = kCtas;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = kCtas > 1 ? 1 : 0;
+  cfg.numAttrs = n_attr;
   {
     ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
     SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes>, ta, tb, tcm, p));

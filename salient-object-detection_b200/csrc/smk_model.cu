@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "smk_kernels.h"
 
 namespace smk {
@@ -22,6 +24,14 @@ void set_error(const char* fmt, ...) {
 
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SMK_PDL");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  return on != 0;
+}
 
 // ---- event profiler -----------------------------------------------------------------------------
 static const int kProfMaxEvents = 16384;

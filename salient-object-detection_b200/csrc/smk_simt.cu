@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
                  const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
                  int64_t rows, int D, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -79,7 +81,7 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: layernorm_kernel<TOut, c><<<grid, 256, 0, s>>>(x, res, gamma, beta, y, y32, sum_out, rows, D, eps); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, rows, D, eps)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -120,6 +122,8 @@ dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __res
                      const float* __restrict__ pos, int period, __nv_bfloat16* __restrict__ a3a, __nv_bfloat16* __restrict__ a3b,
                      const float* __restrict__ gamma2, const float* __restrict__ beta2, float* __restrict__ y2,
                      __nv_bfloat16* __restrict__ y2s, int64_t rows, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -192,7 +196,7 @@ int dec_layernorm(float* x, const float* res, const float* gamma, const float* b
                                                      (y2s ? 6.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_DLN_CASE(c) \
-  case c: dec_layernorm_kernel<c><<<grid, 256, 0, s>>>(x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D)); break;
     SMK_DLN_CASE(1) SMK_DLN_CASE(2) SMK_DLN_CASE(3) SMK_DLN_CASE(4)
 #undef SMK_DLN_CASE
   }
@@ -419,6 +423,8 @@ __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&v)[4]) 
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc, bool vec_ok) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   T* strip = reinterpret_cast<T*>(im2col_smem);         // [3*P][ws], ws = wp*P + pad
   const int py = blockIdx.x, b = blockIdx.y;
@@ -469,7 +475,7 @@ int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, co
   {
     ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + sizeof(T)), s);
     const bool vec_ok = (W & 3) == 0 && ((uintptr_t)x % (4 * sizeof(TIn))) == 0;   // 4-pixel vector loads stay aligned in every row
-    im2col_kernel<TIn, T><<<dim3(hp, B), 256, smem, s>>>(x, cols, H, W, P, hp, wp, nc, vec_ok);
+    SMK_CHECK_CUDA(launch_pdl(im2col_kernel<TIn, T>, dim3(hp, B), dim3(256), (size_t)smem, s, x, cols, H, W, P, hp, wp, nc, vec_ok));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -483,6 +489,8 @@ template int im2col<uint8_t, __nv_bfloat16>(const uint8_t*, __nv_bfloat16*, int,
 __global__ void __launch_bounds__(128)
 assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
                        float* __restrict__ tokens, int hw, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int t = blockIdx.x, b = blockIdx.y;   // t in [0, hw]; a grid of (1, B) writes the cls rows only
   const float* src = (t == 0) ? cls : patch_out + ((int64_t)b * hw + t - 1) * D;
   float* dst = tokens + ((int64_t)b * (hw + 1) + t) * D;
@@ -493,7 +501,7 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
   if (B == 0) return SMK_OK;
   {
     ProfScope prof(PROF_OTHER, (double)B * (cls_only ? 1 : hw + 1) * D * 8.0, s);
-    assemble_tokens_kernel<<<dim3(cls_only ? 1 : hw + 1, B), 128, 0, s>>>(patch_out, cls, pos, tokens, hw, D);
+    SMK_CHECK_CUDA(launch_pdl(assemble_tokens_kernel, dim3(cls_only ? 1 : hw + 1, B), dim3(128), 0, s, patch_out, cls, pos, tokens, hw, D));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -556,6 +564,8 @@ __device__ __forceinline__ void split_hi_lo(float x, __nv_bfloat16& hi, __nv_bfl
 __global__ void __launch_bounds__(256)
 split3_act_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ pos, int period,
                   __nv_bfloat16* __restrict__ out_a, __nv_bfloat16* __restrict__ out_b, int64_t rows, int K) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K) return;
   const int64_t r = i / K;
@@ -578,7 +588,7 @@ int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_b
   if (rows == 0) return SMK_OK;
   {
     ProfScope prof(PROF_OTHER, (double)rows * K * (4.0 + (out_a ? 6.0 : 0.0) + (out_b ? 6.0 : 0.0)), s);
-    split3_act_kernel<<<(unsigned)((rows * K + 255) / 256), 256, 0, s>>>(x, ldx, pos, period > 0 ? period : 1, out_a, out_b, rows, K);
+    SMK_CHECK_CUDA(launch_pdl(split3_act_kernel, dim3((unsigned)((rows * K + 255) / 256)), dim3(256), 0, s, x, ldx, pos, period > 0 ? period : 1, out_a, out_b, rows, K));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -618,6 +628,8 @@ __global__ void __launch_bounds__(MH_THREADS, MH_MAXT == 1 ? 3 : 1)
 mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const float* __restrict__ tokens /*[B,N,D] final LN*/,
                  float* __restrict__ mask_pred /*[B,L,nq,hp*sf,wp*sf]*/, float* __restrict__ logits_out, int B, int L, int Lg, int nq,
                  int D, int hp, int wp, int sf, int layer0) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int hw = hp * wp, N = hw + 1;
   const int b = blockIdx.y, l0 = blockIdx.x * Lg;          // first output layer of this CTA
@@ -760,8 +772,8 @@ int mask_head(const float* queries, const float* tokens, float* mask_pred, float
   {
     // algorithmic bytes: read tokens + queries, write the [nq, hp*sf, wp*sf] probability planes
     ProfScope prof(PROF_MASK_HEAD, (double)B * L * ((double)(hp * wp + nq) * D + (double)nq * hp * sf * wp * sf) * 4.0, s);
-    kern<<<dim3((L + Lg - 1) / Lg, B), MH_THREADS, smem, s>>>(queries, tokens, mask_pred, logits_out, B, L, Lg, nq, D, hp, wp,
-                                                                           sf, layer0);
+    SMK_CHECK_CUDA(launch_pdl(kern, dim3((L + Lg - 1) / Lg, B), dim3(MH_THREADS), smem, s, queries, tokens, mask_pred, logits_out, B, L, Lg, nq,
+                              D, hp, wp, sf, layer0));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -771,6 +783,8 @@ int mask_head(const float* queries, const float* tokens, float* mask_pred, float
 __global__ void __launch_bounds__(256)
 rowdot_sigmoid_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ out, int64_t rows, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -783,7 +797,7 @@ int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out
   if (rows == 0) return SMK_OK;
   {
     ProfScope prof(PROF_OTHER, (double)rows * D * 4.0, s);
-    rowdot_sigmoid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h, w, bias, out, rows, D);
+    SMK_CHECK_CUDA(launch_pdl(rowdot_sigmoid_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, h, w, bias, out, rows, D));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -791,6 +805,8 @@ int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out
 
 // objectness comes out as [L,B,nq]; the interface wants [B,L,nq] (maskformer.py:238 permute)
 __global__ void permute_lb_kernel(const float* __restrict__ in, float* __restrict__ out, int L, int B, int n) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)L * B * n) return;
   const int e = (int)(i % n);
@@ -803,7 +819,7 @@ int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s)
   if (tot == 0) return SMK_OK;
   {
     ProfScope prof(PROF_OTHER, (double)tot * 8.0, s);
-    permute_lb_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(in, out, L, B, n);
+    SMK_CHECK_CUDA(launch_pdl(permute_lb_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, in, out, L, B, n));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -811,6 +827,8 @@ int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s)
 
 // features[b,:] = mean_q queries_last[b,q,:]   (maskformer.py:203)
 __global__ void query_mean_kernel(const float* __restrict__ qlast, float* __restrict__ out, int nq, int D) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float s = 0.f;
@@ -822,7 +840,7 @@ int query_mean(const float* qlast, float* out, int B, int nq, int D, cudaStream_
   if (B == 0) return SMK_OK;
   {
     ProfScope prof(PROF_OTHER, (double)B * (nq + 1) * D * 4.0, s);
-    query_mean_kernel<<<B, 128, 0, s>>>(qlast, out, nq, D);
+    SMK_CHECK_CUDA(launch_pdl(query_mean_kernel, dim3(B), dim3(128), 0, s, qlast, out, nq, D));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
