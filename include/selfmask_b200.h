@@ -172,6 +172,12 @@ int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t 
  * memory); NULL switches it off. */
 int smk_debug_attn_trace(long long* buf);
 int smk_debug_gemm_trace(long long* buf);   /* tuning aid: per-CTA wait-cycle counters of the tcgen05 GEMM (16 per CTA); NULL = off */
+/* Few-query attention (decoder self / cross attention, transformer_decoder.py:271-291): Lq <= 32 queries and Lk <= 256 keys per
+ * (image, head), head dim 64, bf16 inputs.  Image b: queries at rows b*Lq.., keys / values at rows b*kv_rows + kv_row0 ..
+ * out_mode: 0 bf16 [B*Lq, heads*64], 1 fp32, 2 bf16x3 split [hi | hi | lo] (3*heads*64 columns). */
+int smk_attention_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_rows,
+                        int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale, void* stream);
+
 /* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
  * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */
 int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream);

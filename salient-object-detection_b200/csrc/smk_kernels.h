@@ -25,6 +25,10 @@ int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int
 int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
                          int64_t kv_total_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk,
                          int heads, float scale, cudaStream_t s);
+// few-query attention (decoder): Lq <= 32, Lk <= 256; out_mode 0 bf16, 1 fp32, 2 bf16x3 split (smk_attn_small.cu)
+int attention_small(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
+                    int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
+                    cudaStream_t s);
 int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_bfloat16* out_a, __nv_bfloat16* out_b, int64_t rows,
                int K, cudaStream_t s);
 int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s);

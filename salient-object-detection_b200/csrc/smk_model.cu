@@ -470,6 +470,8 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
     };
     const __nv_bfloat16* KVb = (const __nv_bfloat16*)m->KV;
+    // few queries against <= 256 keys: the 2-warp mma.sync kernel (a 128-row tcgen05 tile would be 84 % padding at nq = 20)
+    const bool small_attn = nq <= 32 && hw <= 256;
     // Every producer writes the bf16x3 split its consumer GEMM needs (LayerNorm, attention and ReLU-GEMM epilogues), so a
     // decoder layer is 12 launches: 7 split GEMMs, 2 attentions, 3 fused add+LayerNorm(+final norm) kernels.
     SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, m->a3a, m->a3b, R, D, s));   // layer 0 input: tgt = 0
@@ -479,13 +481,15 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       // self-attention: q = k = tgt + query_pos, v = tgt
       SMK_PROPAGATE(gemm3(m->a3b, d3.saw, w + d.sab, m->dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
       SMK_PROPAGATE(gemm3(m->a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, m->dv_b, D, R, D, D, SMK_EPI_NONE, 0));
-      SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
+      if (small_attn) SMK_PROPAGATE(attention_small(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
+      else SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
       SMK_PROPAGATE(gemm3(m->a3c, d3.saow, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
       SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, m->a3b, nullptr, nullptr, nullptr, nullptr, R, D, s));
       // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
       SMK_PROPAGATE(gemm3(m->a3b, d3.caqw, w + d.cab, m->cq_b, D, R, D, D, SMK_EPI_NONE, 0));
       const __nv_bfloat16* kl = KVb + (int64_t)l * 2 * D;
-      SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
+      if (small_attn) SMK_PROPAGATE(attention_small(m->cq_b, D, kl, ldkv, kl + D, ldkv, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
+      else SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
       SMK_PROPAGATE(gemm3(m->a3c, d3.caow, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
       SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, m->a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s));
       // FFN (ReLU); the shared final norm on every layer's output (transformer_decoder.py:138-145) rides on the last LayerNorm

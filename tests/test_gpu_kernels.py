@@ -250,6 +250,40 @@ def test_attention_tcgen05_general_layout(Lq, Lk, kv_rows, kv_row0):
     assert (out - ref).abs().max().item() <= 0.03
 
 
+@pytest.mark.parametrize("Lq,Lk,kv_rows,kv_row0,out_mode", [(20, 196, 197, 1, 1), (20, 20, 20, 0, 1), (10, 196, 197, 1, 0), (10, 10, 10, 0, 2),
+                                                             (20, 196, 197, 1, 2), (32, 256, 256, 0, 1), (1, 1, 3, 2, 1), (17, 100, 120, 5, 1),
+                                                             (20, 144, 145, 1, 2)])
+def test_attention_small_matches_torch(Lq, Lk, kv_rows, kv_row0, out_mode):
+    """Few-query decoder attention (mma.sync kernel): separate q / k / v matrices, per-image key offset (cls skipped),
+    bf16 / fp32 / bf16x3-split outputs; B*heads is large enough to cover several CTAs per SM."""
+    torch.manual_seed(16)
+    B, H, dh = 37, 6, 64
+    D = H * dh
+    q = torch.randn(B * Lq, D, device=DEV).to(torch.bfloat16)
+    kv = torch.randn(B * kv_rows, 2 * D, device=DEV).to(torch.bfloat16)       # k | v interleaved per row (ld = 2D)
+    k_view, v_view = kv[:, :D], kv[:, D:]
+    if out_mode == 1:
+        out = torch.full((B * Lq, D), 7.0, device=DEV, dtype=torch.float32)
+    else:
+        out = torch.full((B * Lq, D * (3 if out_mode == 2 else 1)), 7.0, device=DEV, dtype=torch.bfloat16)
+    check(lib().smk_attention_small(ptr(q), D, C.c_void_p(k_view.data_ptr()), 2 * D, C.c_void_p(v_view.data_ptr()), 2 * D,
+                                    kv_rows, kv_row0, ptr(out), out.shape[1], out_mode, B, Lq, Lk, H, 0.125, stream_ptr()))
+    torch.cuda.synchronize()
+    qh = q.float().view(B, Lq, H, dh).transpose(1, 2)
+    kk = kv.float().view(B, kv_rows, 2 * D)[:, kv_row0:kv_row0 + Lk]
+    kh = kk[..., :D].reshape(B, Lk, H, dh).transpose(1, 2)
+    vh = kk[..., D:].reshape(B, Lk, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    if out_mode == 2:
+        hi, hi2, lo = out[:, :D].float(), out[:, D:2 * D].float(), out[:, 2 * D:].float()
+        assert torch.equal(hi, hi2)
+        got = hi + lo
+    else:
+        got = out.float()
+    tol = 0.03 if out_mode != 0 else 0.05
+    assert (got - ref).abs().max().item() <= tol
+
+
 def test_gemm_bf16_tcgen05_split3_output():
     """out_f32 = 2: the epilogue writes the bf16x3 split [hi | hi | lo] of the fp32 result (decoder FFN hidden, objectness hidden)."""
     torch.manual_seed(7)
