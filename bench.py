@@ -218,7 +218,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = n_total * K / (ms / 1e3)
-    res = S.summarize(counts.cpu().numpy(), sums.cpu().numpy())        # metric of the last step (sanity; outside the timed region)
+    res = S.summarize(counts, sums)        # metric of the last step (sanity; outside the timed region)
 
     # ---- end to end through the public API: pinned host batches → Evaluator.__call__ → 14 averages ----------
     ev = S.Evaluator(network=model)
@@ -230,7 +230,7 @@ def main():
             c = torch.from_numpy(ev.records["m_counts"]).to(dev)
             s_ = torch.from_numpy(ev.records["m_sums"]).to(dev)
             fc, fs = S.allreduce_records(c, s_, rank * B * K, world * B * K)
-            r = S.summarize(fc.cpu().numpy(), fs.cpu().numpy())
+            r = S.summarize(fc, fs)             # finalised on the device: the host only forms the ordered running means
         return r
     e2e_pass()                                   # warm-up (allocator, page-locked paths)
     barrier()
@@ -242,7 +242,7 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = n_total * K / float(dt.item())
     h2d = x_host.numel() * x_host.element_size() + g_host.numel() * g_host.element_size()
-    d2h = B * 2 * (528 * 4 + 32 * 8) + B * 2 * 4 + B * args.nq * 2 * 4
+    d2h = B * 2 * (528 * 4 + 32 * 8) + B * 2 * 4 + B * args.nq * 2 * 4 + B * 2 * 8 * 8     # integer records + finalised metric values
 
     # ---- per-stage device time with CUDA events on the launching stream (roofline block) -------------------------
     pk = peaks()

@@ -136,6 +136,14 @@ int smk_eval_batch(const float* mask_pred, int64_t batch_stride, const float* ob
 int smk_mask_metrics(const float* pred, const uint8_t* gt, int n, int H, int W,
                      int32_t* m_counts, double* m_sums, void* stream);
 
+/* Records → metric values on the device, bit-identical to the host finalisation (metrics.py::finalize, i.e. iou.py:31,
+ * pixel_acc.py:10-14, f_measure.py:24-81, mae.py:9 in float32 and s_measure.py:108-124 in float64).
+ * m_counts int32 [n_masks,528], m_sums double [n_masks,32] → out double [n_masks,8] =
+ * {iou, pixel_acc, F@0.5, F-max, F@2·mean, MAE (each an exact float32 value), S-measure (float64), 0}.
+ * c1 = float32(1 + beta_square**2), c2 = float32(beta_square**2), eps = float32(1e-7) (f_measure.py:49,80). */
+int smk_finalize_records(const int32_t* m_counts, const double* m_sums, int64_t n_masks, float c1, float c2, float eps,
+                         double* out, void* stream);
+
 /* in [n,h,w] fp32 → out [n,H,W], H <= h*scale, W <= w*scale; ATen bilinear, align_corners=False */
 int smk_upsample_bilinear(const float* in, float* out, int64_t n, int h, int w, int scale, int H, int W, void* stream);
 

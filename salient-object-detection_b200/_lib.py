@@ -44,6 +44,7 @@ SIGNATURES = {
     "smk_model_forward_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "smk_model_tap": (_I, [_P, _I, _P, _L, _P]),
     "smk_eval_batch": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "smk_finalize_records": (_I, [_P, _P, _L, _F, _F, _F, _P, _P]),
     "smk_mask_metrics": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "smk_upsample_bilinear": (_I, [_P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_gemm_f32": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),

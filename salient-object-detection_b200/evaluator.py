@@ -10,7 +10,6 @@ all metric reductions on the GPU; the host only turns integer counts into ratios
 means in dataset order (bit-compatible with `AverageMeter`).
 """
 import os
-from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Iterable, Optional
 
 import numpy as np
@@ -18,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
-from .metrics import METRIC_KEYS, finalize, running_mean
+from .metrics import METRIC_KEYS, finalize, finalize_device, running_mean, values_from_device
 
 
 class BatchRecords:
@@ -58,10 +57,14 @@ def eval_batch(mask_pred: torch.Tensor, objectness: torch.Tensor, gt: torch.Tens
     return rec
 
 
-def summarize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, float]:
+def summarize(m_counts, m_sums) -> Dict[str, float]:
     """[n_img,2,528] / [n_img,2,32] records in dataset order → the reference's 14-key result
-    (evaluator.pyc@L294-308)."""
-    vals = finalize(m_counts, m_sums)
+    (evaluator.pyc@L294-308).  Device tensors are finalised on the GPU (smk_finalize_records), numpy arrays on the
+    host (metrics.finalize); both give identical bits."""
+    if isinstance(m_counts, torch.Tensor) and m_counts.is_cuda:
+        vals = values_from_device(finalize_device(m_counts, m_sums).cpu().numpy())
+    else:
+        vals = finalize(np.asarray(m_counts), np.asarray(m_sums))
     res = {k: running_mean(vals[k][:, 0]) for k in METRIC_KEYS}
     res.update({k + "_ub": running_mean(vals[k][:, 1]) for k in METRIC_KEYS})
     return res
@@ -87,7 +90,6 @@ class Evaluator:
         self.dataset = dataset
         self.records = None
         self._copy_stream = None
-        self._pinned = {}
 
     def _batches(self, dataset_name: str, batch_size: int) -> Iterable[dict]:
         if self.dataset is None:
@@ -101,14 +103,14 @@ class Evaluator:
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.SmkError("the B200 evaluator runs on CUDA devices only")
-        # Three overlapped stages per batch (the reference does them serially, with >= 16 syncs per image):
+        # Two overlapped streams per batch (the reference does everything serially, with >= 16 syncs per image):
         #   copy stream   : host → device of batch i+1 (pinned host memory makes it asynchronous)
-        #   compute stream: model forward + fused evaluation of batch i, then device → host of its records
-        #   worker thread : integer counts → float32 metric values of batch i-1 (numpy, releases the GIL)
+        #   compute stream: model forward, fused evaluation and metric finalisation of batch i (all on the device)
+        # The host sees one device → host copy at the end of the sweep: 8 doubles per evaluated mask (+ the integer records).
         compute = torch.cuda.current_stream(device)
-        copy = self._copy_stream if getattr(self, "_copy_stream", None) is not None and self._copy_stream.device == device \
-            else torch.cuda.Stream(device)
-        self._copy_stream = copy
+        if self._copy_stream is None or self._copy_stream.device != device:
+            self._copy_stream = torch.cuda.Stream(device)
+        copy = self._copy_stream
 
         def stage(dict_data):
             x, gt = dict_data["x"], dict_data["m"]
@@ -121,27 +123,8 @@ class Evaluator:
                 ev.record(copy)
             return xd, gd, ev
 
-        ring = 4                                               # pinned record buffers, reused round-robin
-
-        def fetch(rec, i):
-            slot = self._pinned.setdefault((i % ring, rec.m_counts.shape[0], rec.q_counts.shape[1]), {})
-            if not slot:       # page-locked allocations are slow and synchronise the device: made once, then recycled
-                for k in ("m_counts", "m_sums", "idx", "q_counts"):
-                    t = getattr(rec, k)
-                    slot[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            for k, t in slot.items():
-                t.copy_(getattr(rec, k), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            return slot, ev
-
-        def reduce(host, ev):
-            ev.synchronize()
-            arrs = {k: t.numpy().copy() for k, t in host.items()}      # frees the pinned slot for batch i + ring
-            return arrs, finalize(arrs["m_counts"], arrs["m_sums"])
-
-        pending = []
-        with torch.cuda.device(device), ThreadPoolExecutor(max_workers=1) as pool:
+        recs, vals = [], []
+        with torch.cuda.device(device):
             it = iter(self._batches(dataset_name, batch_size))
             first = next(it, None)
             nxt = stage(first) if first is not None else None
@@ -154,16 +137,15 @@ class Evaluator:
                 gt.record_stream(compute)
                 out = self.model(x, encoder_only=False, skip_decoder=False)     # BaseStructure._forward contract
                 rec = eval_batch(out["mask_pred"], out["objectness"], gt, up=4)
-                if len(pending) >= ring:
-                    pending[len(pending) - ring].result()      # the slot about to be overwritten has been copied out
-                pending.append(pool.submit(reduce, *fetch(rec, len(pending))))
-            if not pending:
+                recs.append(rec)
+                vals.append(finalize_device(rec.m_counts, rec.m_sums))
+            if not recs:
                 raise _lib.SmkError("empty dataset")
-            done = [f.result() for f in pending]
-        self.records = {k: np.concatenate([d[0][k] for d in done]) for k in ("m_counts", "m_sums", "idx", "q_counts")}
-        vals = {k: np.concatenate([d[1][k] for d in done]) for k in METRIC_KEYS}
-        res = {k: running_mean(vals[k][:, 0]) for k in METRIC_KEYS}
-        res.update({k + "_ub": running_mean(vals[k][:, 1]) for k in METRIC_KEYS})
+            # one synchronising read-back for the whole sweep
+            self.records = {k: torch.cat([getattr(r, k) for r in recs]).cpu().numpy() for k in ("m_counts", "m_sums", "idx", "q_counts")}
+            v = values_from_device(torch.cat(vals).cpu().numpy())
+        res = {k: running_mean(v[k][:, 0]) for k in METRIC_KEYS}
+        res.update({k + "_ub": running_mean(v[k][:, 1]) for k in METRIC_KEYS})
         if dir_ckpt is not None:
             os.makedirs(dir_ckpt, exist_ok=True)
             with open(f"{dir_ckpt}/metrics_{dataset_name}.txt", "w") as f:

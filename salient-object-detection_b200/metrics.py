@@ -173,6 +173,27 @@ def finalize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, np.ndarray]:
     }
 
 
+def finalize_device(m_counts: torch.Tensor, m_sums: torch.Tensor) -> torch.Tensor:
+    """`finalize` on the GPU (smk_finalize_records): device records [..., 528] int32 / [..., 32] float64 → float64
+    tensor [..., 8] = the METRIC_KEYS values in order (the six float32 metrics as exact float32 values) + one pad."""
+    _lib.require_cuda(m_counts, "m_counts", torch.int32)
+    _lib.require_cuda(m_sums, "m_sums", torch.float64)
+    m_counts, m_sums = m_counts.contiguous(), m_sums.contiguous()
+    n = m_counts.numel() // _lib.MCOUNT_STRIDE
+    out = torch.empty(*m_counts.shape[:-1], 8, dtype=torch.float64, device=m_counts.device)
+    b2 = 0.3 ** 2
+    with torch.cuda.device(m_counts.device):
+        check(lib().smk_finalize_records(ptr(m_counts), ptr(m_sums), n, float(F32(1 + b2)), float(F32(b2)), float(EPS), ptr(out),
+                                         stream_ptr()), "smk_finalize_records")
+    return out
+
+
+def values_from_device(vals: np.ndarray) -> Dict[str, np.ndarray]:
+    """[..., 8] float64 array of `finalize_device` → the dict `finalize` returns (float32 metrics, float64 S-measure)."""
+    vals = np.asarray(vals)
+    return {k: (vals[..., i] if k == "s_measure" else vals[..., i].astype(F32)) for i, k in enumerate(METRIC_KEYS)}
+
+
 def running_mean(vals: np.ndarray) -> float:
     """AverageMeter (average_meter.py:12-16): sequential accumulation in the dtype of the values
     (float32 for the tensor-valued metrics, float64 for S-measure's python floats), dataset order."""

@@ -120,6 +120,46 @@ def test_eval_batch_counts_bit_exact_vs_oracle(B, nq, hp, wp, H, W):
             assert (np.isnan(sa) and np.isnan(sb)) or abs(sa - sb) <= 2e-5
 
 
+def test_device_finalisation_is_bit_identical_to_host(golden_dir):
+    """smk_finalize_records == metrics.finalize (numpy) on real records (golden masks, edge-case GTs incl. the reference's
+    NaN S-measure cases) and on randomised records: every float32 metric and the float64 S-measure, bit for bit."""
+    from selfmask_b200 import metrics as M
+    from tests.helpers import numpy_record
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    recs = [numpy_record(p, gt) for p, gt in zip(g["preds"], g["gts"])]
+    rng = np.random.default_rng(5)
+    H, W = 40, 56
+    for kind in range(14):
+        p = rng.random((H, W), dtype=np.float32)
+        gt = np.zeros((H, W), bool)
+        if kind == 1: gt[:] = True
+        elif kind == 2: gt[0, 0] = True
+        elif kind == 3: gt[:, 0] = True
+        elif kind == 4: gt[0, :] = True
+        elif kind == 5: gt[H - 1, W - 1] = True
+        elif kind == 6: gt[10:20, 10:30] = True; p[:] = 0.0
+        elif kind == 7: gt[10:20, 10:30] = True; p[:] = 1.0
+        elif kind == 8: gt[10:20, 10:30] = True; p = gt.astype(np.float32)
+        elif kind >= 9: gt = rng.random((H, W)) > 0.15 * (kind - 8)
+        recs.append(numpy_record(p, gt))
+    counts, sums = np.stack([r[0] for r in recs]), np.stack([r[1] for r in recs])
+    # randomised but self-consistent histogram records
+    n_rand = 300
+    rc = np.zeros((n_rand, 528), np.int32)
+    rs = np.zeros((n_rand, 32), np.float64)
+    for i in range(n_rand):
+        p = rng.random((24, 32), dtype=np.float32) ** rng.uniform(0.3, 3.0)
+        gt = rng.random((24, 32)) < rng.uniform(0.02, 0.98)
+        rc[i], rs[i] = numpy_record(p, gt)
+    counts, sums = np.concatenate([counts, rc]), np.concatenate([sums, rs])
+    host = M.finalize(counts, sums)
+    dev = M.values_from_device(M.finalize_device(torch.from_numpy(counts).to(DEV), torch.from_numpy(sums).to(DEV)).cpu().numpy())
+    assert np.isnan(host["s_measure"]).any()
+    for k in M.METRIC_KEYS:
+        assert host[k].dtype == dev[k].dtype, k
+        assert np.array_equal(host[k], dev[k], equal_nan=True), (k, np.nonzero(~((host[k] == dev[k]) | (np.isnan(host[k]) & np.isnan(dev[k]))))[0][:5])
+
+
 def test_layernorm_matches_torch():
     torch.manual_seed(0)
     x = torch.randn(1000, 384, device=DEV) * 3 + 1
