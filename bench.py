@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--nq", type=int, default=20)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=48, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--ncu-step", action="store_true",
@@ -283,7 +283,7 @@ def main():
     if rank == 0:
         line = {"metric": f"SelfMask nq{args.nq} {args.size}x{args.size} images/sec", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic", "config": workload_config(args),
+                "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic", "config": workload_config(args),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "sanity": {"iou": res["iou"], "f_max": res["f_max"], "e2e_iou": e2e_res["iou"]}}

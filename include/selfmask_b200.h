@@ -41,7 +41,9 @@ typedef enum {
 
 /* numeric modes */
 enum { SMK_MODE_FP32 = 0,  /* validation: every contraction in fp32 on CUDA cores          */
-       SMK_MODE_BF16 = 1   /* throughput: tcgen05 bf16 operands, fp32 accumulate/residual/LN */ };
+       SMK_MODE_BF16 = 1,  /* throughput: tcgen05 bf16 operands, fp32 accumulate/residual/LN */
+       SMK_MODE_BF16X3 = 2 /* parity on tensor cores: every GEMM as a 3-term bf16 split (hi·hi + hi·lo + lo·hi, K' = 3K) on
+                              tcgen05 with fp32 accumulate; LayerNorm / softmax attention / residual in fp32 */ };
 
 typedef struct {
   int32_t patch;        /* 16 (or 8)                                    */

@@ -11,7 +11,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libselfmask_b200.so")
 
-SMK_MODE_FP32, SMK_MODE_BF16 = 0, 1
+SMK_MODE_FP32, SMK_MODE_BF16, SMK_MODE_BF16X3 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RELU, EPI_RESIDUAL = 0, 1, 2, 4
 QCOUNT_STRIDE, MCOUNT_STRIDE, MSUM_STRIDE = 2, 528, 32
 

@@ -141,6 +141,7 @@ struct smk_model {
   float* pos;                     // [N, D] position embedding at this geometry
   float *kvw32, *kvb;             // decoder memory K/V projection, all layers concatenated: [L*2D, D], [L*2D]
   __nv_bfloat16 *wb, *kvwb;       // bf16 copies (bf16 mode)
+  __nv_bfloat16 *w3, *kvw3, *A3;  // bf16x3 mode: split copies of every weight ([N,3K] at 3x the fp32 offset) and the split-A scratch
   float* X;                       // [B*N, D] residual stream (fp32)
   void *Xn, *QKV, *AO, *Hm, *KV;  // activations in the mode's GEMM input type
   float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
@@ -177,6 +178,10 @@ static void plan(smk_model& m, Plan& pl) {
   m.kvb = pl.take<float>(L * 2 * D);
   m.wb = bf ? pl.take<__nv_bfloat16>(wnumel) : nullptr;
   m.kvwb = bf ? pl.take<__nv_bfloat16>(L * 2 * D * D) : nullptr;
+  const bool x3 = m.mode == SMK_MODE_BF16X3;
+  m.w3 = x3 ? pl.take<__nv_bfloat16>(3 * wnumel) : nullptr;
+  m.kvw3 = x3 ? pl.take<__nv_bfloat16>(3 * L * 2 * D * D) : nullptr;
+  m.A3 = x3 ? pl.take<__nv_bfloat16>(M * 3 * std::max<int64_t>(c.mlp_dim, 3 * c.patch * c.patch)) : nullptr;
   m.X = pl.take<float>(M * D);
   m.Xn = pl.take<uint8_t>(M * D * esz);
   m.QKV = pl.take<uint8_t>(M * 3 * D * 4);          // fp32-sized: doubles as the fp32 patch-embed output
@@ -272,7 +277,7 @@ extern "C" int64_t smk_weights_numel(const smk_config* cfg) {
 
 static int geometry(smk_model& m, const smk_config* cfg, int mode, int max_batch, int H, int W) {
   SMK_PROPAGATE(check_config(cfg));
-  SMK_REQUIRE(mode == SMK_MODE_FP32 || mode == SMK_MODE_BF16, "mode %d unknown", mode);
+  SMK_REQUIRE(mode == SMK_MODE_FP32 || mode == SMK_MODE_BF16 || mode == SMK_MODE_BF16X3, "mode %d unknown", mode);
   SMK_REQUIRE(max_batch > 0 && max_batch <= 65535 && H > 0 && W > 0, "bad batch / image size");
   m.cfg = *cfg;
   m.mode = mode;
@@ -355,6 +360,24 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
     cudaError_t e2 = cudaMemcpyAsync(m->kvb + (int64_t)l * 2 * D, weights + m->dec[l].cab + D, (size_t)2 * D * 4, cudaMemcpyDeviceToDevice, s);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("kv weight copy failed"); return fail(SMK_ERR_CUDA); }
   }
+  if (mode == SMK_MODE_BF16X3) {
+    // [N,K] fp32 at offset o → [N,3K] bf16 ([hi | lo | hi]) at offset 3·o, for every matrix a GEMM reads
+    auto sp = [&](int64_t off, int64_t rows, int64_t K) { return split3_weight(weights + off, m->w3 + 3 * off, rows, (int)K, s); };
+    const int64_t F = cfg->mlp_dim, FD = cfg->dec_ffn, Kpe = 3 * cfg->patch * cfg->patch;
+    if ((st = sp(m->o_pew, D, Kpe)) != SMK_OK) return fail(st);
+    for (const BlockW& b : m->blk) {
+      if ((st = sp(b.qkvw, 3 * D, D)) != SMK_OK || (st = sp(b.pw, D, D)) != SMK_OK || (st = sp(b.f1w, F, D)) != SMK_OK ||
+          (st = sp(b.f2w, D, F)) != SMK_OK)
+        return fail(st);
+    }
+    for (const DecW& d : m->dec) {
+      if ((st = sp(d.saw, 3 * D, D)) != SMK_OK || (st = sp(d.saow, D, D)) != SMK_OK || (st = sp(d.caw, 3 * D, D)) != SMK_OK ||
+          (st = sp(d.caow, D, D)) != SMK_OK || (st = sp(d.l1w, FD, D)) != SMK_OK || (st = sp(d.l2w, D, FD)) != SMK_OK)
+        return fail(st);
+    }
+    if ((st = sp(m->o_f0w, D, D)) != SMK_OK || (st = sp(m->o_f1w, D, D)) != SMK_OK) return fail(st);
+    if ((st = split3_weight(m->kvw32, m->kvw3, (int64_t)cfg->dec_layers * 2 * D, (int)D, s)) != SMK_OK) return fail(st);
+  }
   if (mode == SMK_MODE_BF16) {
     if ((st = cast_bf16(weights, m->wb, table_numel(t), s)) != SMK_OK) return fail(st);
     if ((st = cast_bf16(m->kvw32, m->kvwb, (int64_t)cfg->dec_layers * 2 * D * D, s)) != SMK_OK) return fail(st);
@@ -412,6 +435,19 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   const float scale = 0.125f;   // head_dim^-0.5, head_dim = 64
   m->last_B = B;
 
+  // fp32 validation mode: CUDA-core GEMM.  bf16x3 mode: the same call sites run on tcgen05 — A is split into
+  // [hi | hi | lo] bf16 (K' = 3K) against the pre-split weights [hi | lo | hi], fp32 accumulate: hi·hi + hi·lo + lo·hi
+  const bool x3 = m->mode == SMK_MODE_BF16X3;
+  auto gemm_hp = [m, w, s, x3, L, D](const float* A, int64_t lda, const float* Wp, int64_t ldw, const float* bias, float* Cc, int64_t ldc,
+                                       int M_, int N_, int K_, int epi, cudaStream_t) -> int {
+    if (!x3) return smk::gemm_f32(A, lda, Wp, ldw, bias, Cc, ldc, M_, N_, K_, epi, s);
+    SMK_REQUIRE(ldw == K_, "bf16x3 GEMM: weight rows must be contiguous");
+    const bool is_kv = Wp >= m->kvw32 && Wp < m->kvw32 + (int64_t)L * 2 * D * D;
+    const __nv_bfloat16* w3 = is_kv ? m->kvw3 + 3 * (Wp - m->kvw32) : m->w3 + 3 * (Wp - w);
+    SMK_PROPAGATE(split3_act(A, lda, nullptr, 0, m->A3, nullptr, M_, K_, s));
+    return gemm_bf16_tc(m->A3, 3 * (int64_t)K_, w3, 3 * (int64_t)K_, bias, Cc, ldc, M_, N_, 3 * K_, epi, 1, 0, nullptr, s);
+  };
+
   // ---- encoder ------------------------------------------------------------------------------------
   if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
@@ -440,21 +476,21 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     float *Xn = (float*)m->Xn, *QKV = (float*)m->QKV, *AO = (float*)m->AO, *Hm = (float*)m->Hm;
     if (x_u8) SMK_PROPAGATE((im2col<uint8_t, float>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s)));
     else SMK_PROPAGATE((im2col<float, float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s)));
-    SMK_PROPAGATE(gemm_f32(Hm, Kpe, w + m->o_pew, Kpe, w + m->o_peb, QKV, D, B * hw, D, Kpe, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(Hm, Kpe, w + m->o_pew, Kpe, w + m->o_peb, QKV, D, B * hw, D, Kpe, SMK_EPI_NONE, s));
     SMK_PROPAGATE(assemble_tokens(QKV, w + m->o_cls, m->pos, m->X, B, hw, D, false, s));
     for (int i = 0; i < c.depth; ++i) {
       const BlockW& b = m->blk[i];
       SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, M, D, 1e-6f, s));
-      SMK_PROPAGATE(gemm_f32(Xn, D, w + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, s));
+      SMK_PROPAGATE(gemm_hp(Xn, D, w + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, s));
       SMK_PROPAGATE((attention<float, float>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D,
                                              3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
-      SMK_PROPAGATE(gemm_f32(AO, D, w + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, s));
+      SMK_PROPAGATE(gemm_hp(AO, D, w + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, s));
       SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, M, D, 1e-6f, s));
-      SMK_PROPAGATE(gemm_f32(Xn, D, w + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, s));
-      SMK_PROPAGATE(gemm_f32(Hm, F, w + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, s));
+      SMK_PROPAGATE(gemm_hp(Xn, D, w + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, s));
+      SMK_PROPAGATE(gemm_hp(Hm, F, w + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, s));
     }
     SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tok32, nullptr, M, D, 1e-6f, s));
-    SMK_PROPAGATE(gemm_f32(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
   }
 
   // ---- decoder (transformer_decoder.py:260-297, post-norm) ---------------------------------------------------
@@ -503,23 +539,23 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     const DecW& d = m->dec[l];
     // self-attention: q = k = tgt + query_pos, v = tgt
     SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
-    SMK_PROPAGATE(gemm_f32(m->qin, D, w + d.saw, D, w + d.sab, m->dqk, 2 * D, R, 2 * D, D, SMK_EPI_NONE, s));
-    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.saw + (int64_t)2 * D * D, D, w + d.sab + 2 * D, m->dv, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->qin, D, w + d.saw, D, w + d.sab, m->dqk, 2 * D, R, 2 * D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->tgt, D, w + d.saw + (int64_t)2 * D * D, D, w + d.sab + 2 * D, m->dv, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE((attention<float, float>(m->dqk, m->dqk + D, m->dv, m->dao, B, c.heads, 64, nq, nq, (int64_t)nq * 2 * D, 2 * D,
                                            (int64_t)nq * 2 * D, 2 * D, (int64_t)nq * D, D, (int64_t)nq * D, D, scale, s)));
-    SMK_PROPAGATE(gemm_f32(m->dao, D, w + d.saow, D, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->dao, D, w + d.saow, D, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n1w, w + d.n1b, m->tgt, nullptr, R, D, 1e-5f, s));
     // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
     SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
-    SMK_PROPAGATE(gemm_f32(m->qin, D, w + d.caw, D, w + d.cab, m->dqk, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->qin, D, w + d.caw, D, w + d.cab, m->dqk, D, R, D, D, SMK_EPI_NONE, s));
     const float* kv = (const float*)m->KV + ldkv + (int64_t)l * 2 * D;
     SMK_PROPAGATE((attention<float, float>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv, ldkv,
                                            (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
-    SMK_PROPAGATE(gemm_f32(m->dao, D, w + d.caow, D, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->dao, D, w + d.caow, D, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
     // FFN
-    SMK_PROPAGATE(gemm_f32(m->tgt, D, w + d.l1w, D, w + d.l1b, m->ffh, FD, R, FD, D, SMK_EPI_RELU, s));
-    SMK_PROPAGATE(gemm_f32(m->ffh, FD, w + d.l2w, FD, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, s));
+    SMK_PROPAGATE(gemm_hp(m->tgt, D, w + d.l1w, D, w + d.l1b, m->ffh, FD, R, FD, D, SMK_EPI_RELU, s));
+    SMK_PROPAGATE(gemm_hp(m->ffh, FD, w + d.l2w, FD, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n3w, w + d.n3b, m->tgt, nullptr, R, D, 1e-5f, s));
     // shared final norm on every layer's output (transformer_decoder.py:138-145)
     SMK_PROPAGATE(layernorm_f32(m->tgt, nullptr, w + m->o_dnw, w + m->o_dnb, m->queries + (int64_t)l * R * D, nullptr, R, D, 1e-5f, s));
@@ -538,8 +574,8 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       SMK_PROPAGATE(gemm_bf16_tc(q3, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->a3f, 3 * D, rows, D, 3 * D, SMK_EPI_RELU, 2, 0, nullptr, s));
       SMK_PROPAGATE(gemm_bf16_tc(m->a3f, 3 * D, m->f1w3, 3 * D, w + m->o_f1b, m->oh2, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s));
     } else {
-      SMK_PROPAGATE(gemm_f32(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
-      SMK_PROPAGATE(gemm_f32(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
+      SMK_PROPAGATE(gemm_hp(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
+      SMK_PROPAGATE(gemm_hp(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
     }
     SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
     SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));

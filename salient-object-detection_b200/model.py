@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import SmkConfig, SmkError, check, lib, ptr, stream_ptr
 
-_MODES = {"fp32": _lib.SMK_MODE_FP32, "bf16": _lib.SMK_MODE_BF16}
+_MODES = {"fp32": _lib.SMK_MODE_FP32, "bf16": _lib.SMK_MODE_BF16, "bf16x3": _lib.SMK_MODE_BF16X3}
 
 
 def weight_table(cfg: SmkConfig):
