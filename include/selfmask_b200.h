@@ -69,6 +69,9 @@ int64_t smk_launch_count(void);
  * 7 tcgen05 attention. */
 int smk_prof_enable(int enable);
 int smk_prof_read(double* ms, double* work, int64_t* launches);
+/* per-launch timeline of the recorded launches in launch order (tuning aid): duration, category and start time relative to the
+ * first recorded launch; returns the number of entries written (<= cap) or a negative status */
+int smk_prof_timeline(float* ms, int* cat, float* start_ms, int cap);
 
 /* ---- weights: one fp32 device blob in a canonical order --------------------------------------
  * The table maps the reference's state_dict keys (SURVEY.md §8b, 267 tensors) to blob offsets. */
@@ -187,6 +190,13 @@ int smk_debug_gemm_trace(long long* buf);   /* tuning aid: per-CTA wait-cycle co
  * out_mode: 0 bf16 [B*Lq, heads*64], 1 fp32, 2 bf16x3 split [hi | hi | lo] (3*heads*64 columns). */
 int smk_attention_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_rows,
                         int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale, void* stream);
+
+/* Online-softmax attention (64 queries x 64-key blocks per step, mma.sync) for any sequence length: 384x384 images (577 tokens),
+ * ViT-S/8 (785 tokens) and, with q_lo / k_lo / v_lo non-NULL, the bf16x3 split mode (3-term products, ~fp32 accuracy).
+ * Image b: queries at rows b*q_rows .. +Lq, keys / values at rows b*kv_rows + kv_row0 .. +Lk; out_mode as smk_attention_small. */
+int smk_attention_fa(const void* q, const void* q_lo, int64_t ldq, const void* k, const void* k_lo, int64_t ldk, const void* v,
+                     const void* v_lo, int64_t ldv, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode,
+                     int B, int Lq, int Lk, int heads, float scale, void* stream);
 
 /* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
  * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "smk_launch_count": (_L, []),
     "smk_prof_enable": (_I, [_I]),
     "smk_prof_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)]),
+    "smk_prof_timeline": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), _I]),
     "smk_model_debug_logits": (_I, [_P, _P]),
     "smk_weight_count": (_I, [C.POINTER(SmkConfig)]),
     "smk_weight_entry": (_I, [C.POINTER(SmkConfig), _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_L)]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "smk_attention_tc": (_I, [_P, _P, _I, _I, _I, _F, _P]),
     "smk_attention_tc_general": (_I, [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_attention_small": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, C.c_float, _P]),
+    "smk_attention_fa": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_debug_attn_trace": (_I, [_P]),
     "smk_debug_gemm_trace": (_I, [_P]),
     "smk_split3": (_I, [_P, _L, _I, _P, _I, _P]),

@@ -9,11 +9,13 @@
 //   softmax     in registers (quad shuffles), exp2 with the scale folded in
 //   O = P·V     P re-used straight from the S accumulator fragments (bf16), V fragments by ldmatrix.trans
 // 1536 CTAs, 3 per SM: the op becomes HBM-bound on the K/V read (77 MB per layer).
-#include "smk_common.cuh"
+#include "smk_mma.cuh"
 
 namespace smk {
 
 namespace {
+
+using namespace mma;
 
 constexpr int AS_DH = 64, AS_LD = 72;          // smem row stride in bf16 elements (144 B: conflict-free ldmatrix)
 constexpr int AS_THREADS = 64, AS_MAXQ = 32;
@@ -25,31 +27,6 @@ struct AttnSmallParams {
   int Lq, Lk, kv_rows, kv_row0, heads, out_mode;   // out_mode: 0 bf16, 1 fp32, 2 bf16x3 split [hi | hi | lo]
   float scale_log2e;
 };
-
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 // NT = number of 8-key score tiles held in registers (keys padded to 8*NT, a multiple of 16)
 template <int NT>

@@ -29,6 +29,10 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
 int attention_small(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
                     int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
                     cudaStream_t s);
+// online-softmax attention for long sequences / the bf16x3 split mode (smk_attn_fa.cu); *_lo == nullptr → plain bf16 operands
+int attention_fa(const __nv_bfloat16* q, const __nv_bfloat16* q_lo, int64_t ldq, const __nv_bfloat16* k, const __nv_bfloat16* k_lo, int64_t ldk,
+                 const __nv_bfloat16* v, const __nv_bfloat16* v_lo, int64_t ldv, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo,
+                 int out_mode, int B, int Lq, int Lk, int heads, float scale, cudaStream_t s);
 int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_bfloat16* out_a, __nv_bfloat16* out_b, int64_t rows,
                int K, cudaStream_t s);
 int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s);

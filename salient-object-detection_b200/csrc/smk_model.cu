@@ -166,6 +166,8 @@ struct Plan {
   }
 };
 
+static bool x3_mode(const smk_model& m) { return m.mode == SMK_MODE_BF16X3; }
+
 // Single source of truth for the workspace layout (sizing pass: m.base == nullptr).
 static void plan(smk_model& m, Plan& pl) {
   const smk_config& c = m.cfg;
@@ -181,12 +183,14 @@ static void plan(smk_model& m, Plan& pl) {
   const bool x3 = m.mode == SMK_MODE_BF16X3;
   m.w3 = x3 ? pl.take<__nv_bfloat16>(3 * wnumel) : nullptr;
   m.kvw3 = x3 ? pl.take<__nv_bfloat16>(3 * L * 2 * D * D) : nullptr;
-  m.A3 = x3 ? pl.take<__nv_bfloat16>(M * 3 * std::max<int64_t>(c.mlp_dim, 3 * c.patch * c.patch)) : nullptr;
+  m.A3 = x3 ? pl.take<__nv_bfloat16>(std::max(M * 3 * std::max<int64_t>(D, 3 * c.patch * c.patch), B * nq * 3 * (int64_t)c.dec_ffn)) : nullptr;
   m.X = pl.take<float>(M * D);
   m.Xn = pl.take<uint8_t>(M * D * esz);
-  m.QKV = pl.take<uint8_t>(M * 3 * D * 4);          // fp32-sized: doubles as the fp32 patch-embed output
-  m.AO = pl.take<uint8_t>(M * D * esz);
-  m.Hm = pl.take<uint8_t>(M * (int64_t)c.mlp_dim * esz);   // doubles as the im2col buffer (3*P*P <= 2*mlp_dim)
+  // fp32-sized: doubles as the fp32 patch-embed output; bf16x3: the split q|k|v [M, 3·3D] bf16
+  m.QKV = pl.take<uint8_t>(x3_mode(m) ? M * 9 * D * 2 : M * 3 * D * 4);
+  m.AO = pl.take<uint8_t>(x3_mode(m) ? M * 3 * D * 2 : M * D * esz);            // bf16x3: split attention output [M, 3D] bf16
+  // doubles as the im2col buffer (3*P*P <= 2*mlp_dim); bf16x3: the split GELU(fc1) output [M, 3F] bf16
+  m.Hm = pl.take<uint8_t>(x3_mode(m) ? M * 3 * (int64_t)c.mlp_dim * 2 : M * (int64_t)c.mlp_dim * esz);
   m.KV = pl.take<uint8_t>(M * L * 2 * D * esz);
   m.tok32 = pl.take<float>(M * D);
   m.tokb = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
@@ -255,6 +259,19 @@ extern "C" int smk_prof_read(double* ms, double* work, int64_t* launches) {
     ms[g_prof_cat[i]] += t;
   }
   return SMK_OK;
+}
+
+// per-launch timeline of the recorded launches, in launch order: ms[i], cat[i], start_ms[i] (relative to the first launch)
+extern "C" int smk_prof_timeline(float* ms, int* cat, float* start_ms, int cap) {
+  SMK_REQUIRE(ms && cat && start_ms && cap >= 0, "smk_prof_timeline: bad arguments");
+  const int n = g_prof_used < cap ? g_prof_used : cap;
+  for (int i = 0; i < n; ++i) {
+    SMK_CHECK_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+    SMK_CHECK_CUDA(cudaEventElapsedTime(&ms[i], g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    SMK_CHECK_CUDA(cudaEventElapsedTime(&start_ms[i], g_prof_ev[0], g_prof_ev[2 * i]));
+    cat[i] = g_prof_cat[i];
+  }
+  return n;
 }
 
 extern "C" int smk_weight_count(const smk_config* cfg) {
@@ -461,9 +478,9 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
       if (N <= 256) {
         SMK_PROPAGATE(attention_tc(QKV, AO, B, N, c.heads, scale, s));
-      } else {   // longer sequences (384x384 → 577 tokens): CUDA-core online-softmax kernel
-        SMK_PROPAGATE((attention<__nv_bfloat16, __nv_bfloat16>(QKV, QKV + D, QKV + 2 * D, AO, B, c.heads, 64, N, N, (int64_t)N * 3 * D, 3 * D,
-                                                               (int64_t)N * 3 * D, 3 * D, (int64_t)N * 3 * D, 3 * D, (int64_t)N * D, D, scale, s)));
+      } else {   // longer sequences (384x384 → 577 tokens, ViT-S/8 → 785): online-softmax mma.sync kernel
+        SMK_PROPAGATE(attention_fa(QKV, nullptr, 3 * D, QKV + D, nullptr, 3 * D, QKV + 2 * D, nullptr, 3 * D, N, N, 0, AO, D, 0, B, N, N, c.heads,
+                                   scale, s));
       }
       SMK_PROPAGATE(gemm_bf16_tc(AO, D, wb + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
       SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
@@ -478,7 +495,24 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     else SMK_PROPAGATE((im2col<float, float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s)));
     SMK_PROPAGATE(gemm_hp(Hm, Kpe, w + m->o_pew, Kpe, w + m->o_peb, QKV, D, B * hw, D, Kpe, SMK_EPI_NONE, s));
     SMK_PROPAGATE(assemble_tokens(QKV, w + m->o_cls, m->pos, m->X, B, hw, D, false, s));
-    for (int i = 0; i < c.depth; ++i) {
+    for (int i = 0; i < c.depth && x3; ++i) {
+      // bf16x3: producers write the [hi | hi | lo] split their consumer needs (qkv → attention, attention → proj, fc1 → fc2)
+      const BlockW& b = m->blk[i];
+      __nv_bfloat16 *Q3 = (__nv_bfloat16*)m->QKV, *AO3 = (__nv_bfloat16*)m->AO, *H3 = (__nv_bfloat16*)m->Hm;
+      const __nv_bfloat16* w3 = m->w3;
+      const int64_t lo = 2 * 3 * (int64_t)D;      // column of the lo part in the split q|k|v rows
+      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(split3_act(Xn, D, nullptr, 0, m->A3, nullptr, M, D, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->A3, 3 * D, w3 + 3 * b.qkvw, 3 * D, w + b.qkvb, Q3, 9 * D, M, 3 * D, 3 * D, SMK_EPI_NONE, 2, 0, nullptr, s));
+      SMK_PROPAGATE(attention_fa(Q3, Q3 + lo, 9 * D, Q3 + D, Q3 + lo + D, 9 * D, Q3 + 2 * D, Q3 + lo + 2 * D, 9 * D, N, N, 0, AO3, 3 * D, 2, B, N, N,
+                                 c.heads, scale, s));
+      SMK_PROPAGATE(gemm_bf16_tc(AO3, 3 * D, w3 + 3 * b.pw, 3 * D, w + b.pb, m->X, D, M, D, 3 * D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, M, D, 1e-6f, s));
+      SMK_PROPAGATE(split3_act(Xn, D, nullptr, 0, m->A3, nullptr, M, D, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->A3, 3 * D, w3 + 3 * b.f1w, 3 * D, w + b.f1b, H3, 3 * F, M, F, 3 * D, SMK_EPI_GELU, 2, 0, nullptr, s));
+      SMK_PROPAGATE(gemm_bf16_tc(H3, 3 * F, w3 + 3 * b.f2w, 3 * F, w + b.f2b, m->X, D, M, D, 3 * F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+    }
+    for (int i = 0; i < c.depth && !x3; ++i) {
       const BlockW& b = m->blk[i];
       SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_hp(Xn, D, w + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, s));
@@ -501,39 +535,54 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   if (bf) {
     // bf16 mode: every B·nq-row GEMM on tcgen05 with the 3-term bf16 split folded into K (K' = 3K, ~fp32 accuracy:
     // the objectness ranking downstream has top-1 gaps of 1e-7…3e-3), attention on the tcgen05 kernel.
-    auto gemm3 = [&](const __nv_bfloat16* a3, const __nv_bfloat16* w3, const float* bias, void* C, int64_t ldc, int rows, int N_, int K_,
-                     int epi, int out_f32) {
-      return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
-    };
+    const int64_t Rall = R;
     const __nv_bfloat16* KVb = (const __nv_bfloat16*)m->KV;
     // few queries against <= 256 keys: the 2-warp mma.sync kernel (a 128-row tcgen05 tile would be 84 % padding at nq = 20)
     const bool small_attn = nq <= 32 && hw <= 256;
     // Every producer writes the bf16x3 split its consumer GEMM needs (LayerNorm, attention and ReLU-GEMM epilogues), so a
     // decoder layer is 12 launches: 7 split GEMMs, 2 attentions, 3 fused add+LayerNorm(+final norm) kernels.
-    SMK_PROPAGATE(split3_act(m->tgt, D, qpos, nq, m->a3a, m->a3b, R, D, s));   // layer 0 input: tgt = 0
-    for (int l = 0; l < L; ++l) {
-      const DecW& d = m->dec[l];
-      const Dec3& d3 = m->dec3[l];
-      // self-attention: q = k = tgt + query_pos, v = tgt
-      SMK_PROPAGATE(gemm3(m->a3b, d3.saw, w + d.sab, m->dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
-      SMK_PROPAGATE(gemm3(m->a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, m->dv_b, D, R, D, D, SMK_EPI_NONE, 0));
-      if (small_attn) SMK_PROPAGATE(attention_small(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
-      else SMK_PROPAGATE(attention_tc_general(m->dqk_b, 2 * D, m->dqk_b + D, 2 * D, m->dv_b, D, R, nq, 0, m->a3c, 3 * D, 2, B, nq, nq, c.heads, scale, s));
-      SMK_PROPAGATE(gemm3(m->a3c, d3.saow, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, m->a3b, nullptr, nullptr, nullptr, nullptr, R, D, s));
-      // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
-      SMK_PROPAGATE(gemm3(m->a3b, d3.caqw, w + d.cab, m->cq_b, D, R, D, D, SMK_EPI_NONE, 0));
-      const __nv_bfloat16* kl = KVb + (int64_t)l * 2 * D;
-      if (small_attn) SMK_PROPAGATE(attention_small(m->cq_b, D, kl, ldkv, kl + D, ldkv, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
-      else SMK_PROPAGATE(attention_tc_general(m->cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)M, N, 1, m->a3c, 3 * D, 2, B, nq, hw, c.heads, scale, s));
-      SMK_PROPAGATE(gemm3(m->a3c, d3.caow, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, m->a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s));
-      // FFN (ReLU); the shared final norm on every layer's output (transformer_decoder.py:138-145) rides on the last LayerNorm
-      SMK_PROPAGATE(gemm3(m->a3a, d3.l1w, w + d.l1b, m->a3f, 3 * FD, R, FD, D, SMK_EPI_RELU, 2));
-      SMK_PROPAGATE(gemm3(m->a3f, d3.l2w, w + d.l2b, m->t2, D, R, D, FD, SMK_EPI_NONE, 1));
-      SMK_PROPAGATE(dec_layernorm(m->tgt, m->t2, w + d.n3w, w + d.n3b, 1e-5f, qpos, nq, m->a3a, m->a3b, w + m->o_dnw, w + m->o_dnb,
-                                  m->queries + (int64_t)l * R * D, m->a3q + (int64_t)l * R * 3 * D, R, D, s));
-    }
+    // One image group = one independent launch chain.  Measured on B200 (profiles/r01_decoder_fanout.md): running 4 groups of 64
+    // images concurrently on 4 streams does not shorten the decoder — every kernel of the chain costs ~20 us of fixed latency
+    // whatever its row count, so the chain length (72 launches), not the occupancy, is what bounds it.
+    auto dec_group = [&](int b0, int nb, cudaStream_t s) -> int {
+      const int R = nb * nq;                               // rows of this group (shadows the batch-wide R)
+      const int64_t r0 = (int64_t)b0 * nq;
+      float *tgt = m->tgt + r0 * D, *t2 = m->t2 + r0 * D;
+      __nv_bfloat16 *a3a = m->a3a + r0 * 3 * D, *a3b = m->a3b + r0 * 3 * D, *a3c = m->a3c + r0 * 3 * D, *a3f = m->a3f + r0 * 3 * FD;
+      __nv_bfloat16 *dqk_b = m->dqk_b + r0 * 2 * D, *dv_b = m->dv_b + r0 * D, *cq_b = m->cq_b + r0 * D;
+      const __nv_bfloat16* KVg = KVb + (int64_t)b0 * N * ldkv;
+      auto gemm3 = [&](const __nv_bfloat16* a3, const __nv_bfloat16* w3, const float* bias, void* C, int64_t ldc, int rows, int N_, int K_,
+                       int epi, int out_f32) {
+        return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
+      };
+      SMK_PROPAGATE(split3_act(tgt, D, qpos, nq, a3a, a3b, R, D, s));   // layer 0 input: tgt = 0
+      for (int l = 0; l < L; ++l) {
+        const DecW& d = m->dec[l];
+        const Dec3& d3 = m->dec3[l];
+        // self-attention: q = k = tgt + query_pos, v = tgt
+        SMK_PROPAGATE(gemm3(a3b, d3.saw, w + d.sab, dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
+        SMK_PROPAGATE(gemm3(a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, dv_b, D, R, D, D, SMK_EPI_NONE, 0));
+        if (small_attn) SMK_PROPAGATE(attention_small(dqk_b, 2 * D, dqk_b + D, 2 * D, dv_b, D, nq, 0, a3c, 3 * D, 2, nb, nq, nq, c.heads, scale, s));
+        else SMK_PROPAGATE(attention_tc_general(dqk_b, 2 * D, dqk_b + D, 2 * D, dv_b, D, R, nq, 0, a3c, 3 * D, 2, nb, nq, nq, c.heads, scale, s));
+        SMK_PROPAGATE(gemm3(a3c, d3.saow, w + d.saob, t2, D, R, D, D, SMK_EPI_NONE, 1));
+        SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, a3b, nullptr, nullptr, nullptr, nullptr, R, D, s));
+        // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
+        SMK_PROPAGATE(gemm3(a3b, d3.caqw, w + d.cab, cq_b, D, R, D, D, SMK_EPI_NONE, 0));
+        const __nv_bfloat16* kl = KVg + (int64_t)l * 2 * D;
+        if (small_attn) SMK_PROPAGATE(attention_small(cq_b, D, kl, ldkv, kl + D, ldkv, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
+        else if (hw <= 256) SMK_PROPAGATE(attention_tc_general(cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)nb * N, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
+        else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));   // 384x384: 576 memory keys
+        SMK_PROPAGATE(gemm3(a3c, d3.caow, w + d.caob, t2, D, R, D, D, SMK_EPI_NONE, 1));
+        SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s));
+        // FFN (ReLU); the shared final norm on every layer's output (transformer_decoder.py:138-145) rides on the last LayerNorm
+        SMK_PROPAGATE(gemm3(a3a, d3.l1w, w + d.l1b, a3f, 3 * FD, R, FD, D, SMK_EPI_RELU, 2));
+        SMK_PROPAGATE(gemm3(a3f, d3.l2w, w + d.l2b, t2, D, R, D, FD, SMK_EPI_NONE, 1));
+        SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n3w, w + d.n3b, 1e-5f, qpos, nq, a3a, a3b, w + m->o_dnw, w + m->o_dnb,
+                                    m->queries + ((int64_t)l * Rall + r0) * D, m->a3q + ((int64_t)l * Rall + r0) * 3 * D, R, D, s));
+      }
+      return SMK_OK;
+    };
+    SMK_PROPAGATE(dec_group(0, B, s));
   } else {
   for (int l = 0; l < L; ++l) {
     const DecW& d = m->dec[l];

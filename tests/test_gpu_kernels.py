@@ -359,3 +359,43 @@ def test_attention_tcgen05_split3_output():
     assert torch.equal(hi, hi2)
     assert (hi + lo - ref).abs().max().item() <= 0.03
     assert (lo.abs() <= hi.abs() * 2.0 ** -7 + 1e-30).all()          # lo is the rounding residue of hi
+
+
+@pytest.mark.parametrize("Lq,Lk,split,out_mode", [(577, 577, False, 0), (785, 785, False, 1), (197, 197, True, 2), (577, 577, True, 2),
+                                                   (64, 64, False, 1), (1, 1, True, 1), (130, 67, True, 1)])
+def test_attention_fa_matches_torch(Lq, Lk, split, out_mode):
+    """Online-softmax mma.sync attention (smk_attn_fa.cu): long sequences (384x384 → 577 tokens, ViT-S/8 → 785) with bf16
+    operands, and the bf16x3 split mode (hi + lo operands, 3-term products) which must be ~fp32-accurate."""
+    torch.manual_seed(21)
+    B, H, dh = 3, 6, 64
+    D = H * dh
+    q32 = torch.randn(B * Lq, D, device=DEV)
+    k32 = torch.randn(B * Lk, D, device=DEV)
+    v32 = torch.randn(B * Lk, D, device=DEV)
+
+    def parts(x):
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        return hi.contiguous(), lo.contiguous()
+
+    (qh, ql), (kh, kl), (vh, vl) = parts(q32), parts(k32), parts(v32)
+    width = D * (3 if out_mode == 2 else 1)
+    out = torch.full((B * Lq, width), 7.0, device=DEV, dtype=torch.float32 if out_mode == 1 else torch.bfloat16)
+    lo_ptr = (lambda t: ptr(t)) if split else (lambda t: None)
+    check(lib().smk_attention_fa(ptr(qh), lo_ptr(ql), D, ptr(kh), lo_ptr(kl), D, ptr(vh), lo_ptr(vl), D, Lq, Lk, 0, ptr(out), width,
+                                 out_mode, B, Lq, Lk, H, 0.125, stream_ptr()))
+    torch.cuda.synchronize()
+    src = (qh.float() + ql.float(), kh.float() + kl.float(), vh.float() + vl.float()) if split else (qh.float(), kh.float(), vh.float())
+    qq, kk, vv = (t.double().view(B, -1, H, dh).transpose(1, 2) for t in src)
+    ref = (torch.softmax(qq @ kk.transpose(-1, -2) * 0.125, -1) @ vv).transpose(1, 2).reshape(B * Lq, D).float()
+    if out_mode == 2:
+        hi, hi2, lo = out[:, :D].float(), out[:, D:2 * D].float(), out[:, 2 * D:].float()
+        assert torch.equal(hi, hi2)
+        got = hi + lo
+    else:
+        got = out.float()
+    err = (got - ref).abs().max().item()
+    if split:
+        assert err <= (3e-4 if out_mode == 2 else 5e-5), err      # 3-term products: fp32-like; the split output keeps ~16 bits
+    else:
+        assert err <= (0.03 if out_mode == 1 else 0.05), err

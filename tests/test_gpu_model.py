@@ -122,6 +122,23 @@ def test_bf16_mode_parity_envelope():
     assert stats["logits_maxabs"] <= 1.5, stats
 
 
+def test_bf16_mode_long_sequence_384():
+    """384x384 (577 tokens, 576 memory keys): encoder attention and decoder cross-attention leave the single-tile tcgen05 /
+    few-key kernels for the online-softmax kernel (smk_attn_fa.cu); same parity envelope as 224x224."""
+    B = 2
+    model, sd, cfg = make_model(nq=20, mode="bf16", max_batch=B)
+    x = O.normalize_images(O.synth_images_u8(B, 384, 384, seed=98))
+    ref = _oracle(sd, x, cfg)
+    out, logits = forward_with_logits(model, x.to(DEV))
+    agree = binarised_iou_agreement(out["mask_pred"][:, -1].cpu().numpy(), ref["mask_pred"][:, -1].numpy())
+    stats = {"logits_maxabs": float((logits.cpu() - ref["mask_logits"]).abs().max()),
+             "iou_agreement_mean": float(agree.mean()), "iou_agreement_min": float(agree.min()),
+             "objectness_maxabs": float((out["objectness"].cpu() - ref["objectness"]).abs().max())}
+    _report("bf16_nq20_384x384_B2", stats)
+    assert stats["iou_agreement_mean"] >= 0.98, stats
+    assert stats["logits_maxabs"] <= 1.5, stats
+
+
 @pytest.mark.parametrize("nq,B,H,W", [(20, 8, 224, 224), (10, 4, 224, 224), (20, 2, 200, 180), (20, 2, 384, 384)])
 def test_bf16x3_mode_meets_the_north_star_tolerance(nq, B, H, W):
     """bf16x3 = every GEMM on tcgen05 as a 3-term bf16 split with fp32 accumulate.  north_star's bf16 criteria hold in this
