@@ -6,6 +6,8 @@
 // (SURVEY.md §8a').  All integer outputs are exact; the host forms the float32 ratios from them.
 // HBM-bound byte work: the full-resolution masks [B,nq,H,W] are never written — each CTA keeps one
 // low-resolution probability plane in shared memory and re-creates full-resolution pixels on the fly.
+#include <stdlib.h>
+
 #include "smk_common.cuh"
 
 namespace smk {
@@ -327,6 +329,257 @@ query_iou_x4_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// E1 by source cells (up == 4), one warp per query.  The x4 bilinear map (align_corners = False) cuts the output into cells:
+// columns {0,1}, then {4u-2 .. 4u+1} for u = 1 .. wp-1, then the last two columns (same along y); every pixel of cell (v, u) is
+// a blend, with non-negative dyadic weights that sum to 1, of the 4 plane samples at rows {max(v-1,0), min(v,hp-1)} x columns
+// {max(u-1,0), min(u,wp-1)}.  Round-to-nearest is monotone, so bilerp() is monotone in each corner, and bilerp(c,c,c,c) is
+// exactly 0.5 for c = 0.5 and > 0.5 for c = nextafter(0.5) (checked for every weight pair in tests/test_host_cpu.py).
+// Hence: 4 corners > 0.5 → every pixel > 0.5; no corner > 0.5 → no pixel > 0.5.  Only cells with mixed corners (2-5 % of the
+// cells of a real mask) are evaluated pixel by pixel, with the same make_tap() + bilerp() arithmetic as the generic kernel, so
+// every count stays bit-identical to the reference.
+// Everything else is bit-vector work: the ground truth is packed to one bit per pixel once per CTA; a warp turns its plane
+// into "sample > 0.5" bit rows with ballots, classifies a whole row of cells with shifts / and / or, expands the "all four
+// corners" bits to pixel masks (one bit → one nibble, shifted by the 2-pixel cell offset) and counts with popc against the
+// ground-truth words.  grid (ceil(nq / 8), B), 8 warps = 8 queries per CTA, no block barrier after the packing.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCellMaxWords = 4;     // plane width <= 127 samples (bit rows of <= 4 words)
+
+// 8 bits → 8 nibbles (bit j → bits 4j .. 4j+3)
+__device__ __forceinline__ uint32_t expand_nibbles(uint32_t x) {
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x * 0xFu;
+}
+// bits [x, x + n) (n <= 6) of a bit-packed row of ww words
+__device__ __forceinline__ unsigned row_bits(const uint32_t* row, int ww, int x, int n) {
+  const int w = x >> 5;
+  const uint32_t lo = row[w], hi = (w + 1 < ww) ? row[w + 1] : 0u;
+  return __funnelshift_r(lo, hi, x & 31) & ((1u << n) - 1u);
+}
+// 32-bit window starting at bit `pos` of a bit row of nw words (zero beyond the row)
+__device__ __forceinline__ uint32_t bit_window(const uint32_t* row, int nw, int pos) {
+  const int w = pos >> 5;
+  const uint32_t lo = w < nw ? row[w] : 0u, hi = (w + 1 < nw) ? row[w + 1] : 0u;
+  return __funnelshift_r(lo, hi, pos & 31);
+}
+
+__global__ void __launch_bounds__(kEvalThreads)
+query_iou_cells_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
+                       int nq, int hp, int wp, int H, int W, int32_t* __restrict__ q_counts) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ uint32_t dyn_cells[];
+  __shared__ int red[kEvalWarps];
+  const int ww = (W + 31) >> 5, aw = (wp + 31) >> 5, fw = (wp + 32) >> 5, n_cells = (hp + 1) * (wp + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* gbits = dyn_cells;                                            // [H][ww] ground truth, one bit per pixel
+  uint32_t* abits = gbits + H * ww + warp * (hp * aw + 2 * (hp + 1) * fw);   // [hp][aw]  sample > 0.5
+  uint32_t* fullw = abits + hp * aw;                                      // [hp+1][fw] cell: all 4 corners above
+  uint32_t* mixw = fullw + (hp + 1) * fw;                                 // [hp+1][fw] cell: some, not all, corners above
+  uint16_t* mixed = reinterpret_cast<uint16_t*>(gbits + H * ww + kEvalWarps * (hp * aw + 2 * (hp + 1) * fw)) + warp * n_cells;
+  const int b = blockIdx.y;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+
+  // ---- ground truth → one bit per pixel (W % 4 == 0: rows are 4-byte aligned) ----
+  int ngt = 0;
+  auto nibble = [](uint32_t px4) { return ((__vcmpne4(px4, 0u) & 0x08040201u) * 0x01010101u) >> 24; };   // byte j non-zero → bit j
+  if ((W & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    // 16 pixels → one 16-bit half word; 4 independent 16-byte loads in flight per thread
+    const int w16 = W >> 4, n16 = H * w16;
+    uint16_t* gb16 = reinterpret_cast<uint16_t*>(gbits);
+    const uint4* g16 = reinterpret_cast<const uint4*>(g);
+    for (int i0 = threadIdx.x; i0 < n16; i0 += 4 * kEvalThreads) {
+      uint4 px[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kEvalThreads;
+        px[j] = i < n16 ? __ldg(g16 + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kEvalThreads;
+        if (i < n16) {
+          const uint32_t bits = nibble(px[j].x) | (nibble(px[j].y) << 4) | (nibble(px[j].z) << 8) | (nibble(px[j].w) << 12);
+          const int y = i / w16, x16 = i - y * w16;
+          gb16[y * (2 * ww) + x16] = (uint16_t)bits;
+          ngt += __popc(bits);
+        }
+      }
+    }
+    if (W & 16)       // odd number of half words per row: clear the padding half of the last word
+      for (int y = threadIdx.x; y < H; y += kEvalThreads) gb16[y * (2 * ww) + 2 * ww - 1] = 0;
+  } else {
+    for (int i = threadIdx.x; i < H * ww; i += kEvalThreads) {
+      const int y = i / ww, x0 = (i - y * ww) * 32;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(g + (int64_t)y * W + x0);
+      uint32_t bits = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (x0 + 4 * k < W) bits |= nibble(__ldg(src + k)) << (4 * k);
+      gbits[i] = bits;
+      ngt += __popc(bits);
+    }
+  }
+  ngt = block_sum_int(ngt, red);         // (contains the barrier that publishes gbits)
+  const int q = blockIdx.x * kEvalWarps + warp;
+  if (q >= nq) return;
+  const float* src = mask_pred + (int64_t)b * batch_stride + (int64_t)q * hp * wp;
+
+  // ---- phase 1: sample > 0.5 bit rows ----
+  if ((wp & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 4 consecutive samples of one row per 16-byte load → one nibble, OR-ed into the row's word; 8 loads in flight per lane
+    for (int i = lane; i < hp * aw; i += 32) abits[i] = 0u;
+    __syncwarp();
+    const int w4 = wp >> 2, n4 = hp * w4;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (int i0 = lane; i0 < n4; i0 += 8 * 32) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = i0 + 32 * j < n4 ? __ldg(src4 + i0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + 32 * j;
+        const uint32_t nib = (v[j].x > 0.5f ? 1u : 0u) | (v[j].y > 0.5f ? 2u : 0u) | (v[j].z > 0.5f ? 4u : 0u) | (v[j].w > 0.5f ? 8u : 0u);
+        if (i < n4 && nib) {
+          const int r = i / w4, c = 4 * (i - r * w4);
+          atomicOr(&abits[r * aw + (c >> 5)], nib << (c & 31));
+        }
+      }
+    }
+  } else {
+    // (8 rows of loads in flight before the first ballot: the plane comes from L2 / HBM, one latency per batch instead of per word)
+    for (int rb = 0; rb < hp; rb += 8) {
+      float v[8][kCellMaxWords];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < kCellMaxWords; ++k) {
+          const int r = rb + j, c = 32 * k + lane;
+          v[j][k] = (r < hp && c < wp) ? __ldg(src + r * wp + c) : 0.f;
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < kCellMaxWords; ++k) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, v[j][k] > 0.5f);
+          if (lane == 0 && rb + j < hp && k < aw) abits[(rb + j) * aw + k] = bal;
+        }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: one lane per row of cells: corner combinations as shifted bit rows ----
+  for (int v = lane; v <= hp; v += 32) {
+    const uint32_t* a0 = abits + max(v - 1, 0) * aw;
+    const uint32_t* a1 = abits + min(v, hp - 1) * aw;
+    uint32_t all_[kCellMaxWords + 1], any_[kCellMaxWords + 1];
+#pragma unroll
+    for (int k = 0; k <= kCellMaxWords; ++k) {
+      all_[k] = k < aw ? (a0[k] & a1[k]) : 0u;
+      any_[k] = k < aw ? (a0[k] | a1[k]) : 0u;
+    }
+    // cell u uses columns max(u-1,0) and min(u,wp-1):  L = (S << 1) | S[0],  R = S | (S[wp-1] << wp)
+    const uint32_t last0 = a0[(wp - 1) >> 5] >> ((wp - 1) & 31), last1 = a1[(wp - 1) >> 5] >> ((wp - 1) & 31);
+    const uint32_t last_all = last0 & last1 & 1u, last_any = (last0 | last1) & 1u;
+    uint32_t carry_all = all_[0] & 1u, carry_any = any_[0] & 1u;
+#pragma unroll
+    for (int k = 0; k <= kCellMaxWords; ++k) {
+      if (k < fw) {
+        const uint32_t l_all = (all_[k] << 1) | carry_all, l_any = (any_[k] << 1) | carry_any;
+        carry_all = all_[k] >> 31;
+        carry_any = any_[k] >> 31;
+        uint32_t r_all = all_[k], r_any = any_[k];
+        if (k == (wp >> 5)) { r_all |= last_all << (wp & 31); r_any |= last_any << (wp & 31); }
+        const uint32_t full = l_all & r_all, some = l_any | r_any;
+        // keep bits 0 .. wp only
+        const int hi_bit = wp - 32 * k;      // index of the last valid bit in this word (>= 0 since k < fw)
+        const uint32_t keep = hi_bit >= 31 ? 0xffffffffu : ((2u << hi_bit) - 1u);
+        fullw[v * fw + k] = full & keep;
+        mixw[v * fw + k] = some & ~full & keep;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 3: (cell row, pixel word) items: popc of the expanded "full" cells, collection of the mixed ones ----
+  int inter = 0, npred = 0, n_mixed = 0;
+  const int n_items = (hp + 1) * ww, dv = 32 / ww, dl = 32 - dv * ww;
+  int v = lane / ww, l = lane - v * ww;
+  for (int it0 = 0; it0 < n_items; it0 += 32, v += dv, l += dl) {
+    const int it = it0 + lane;
+    uint32_t own = 0;
+    if (l >= ww) { l -= ww; ++v; }
+    if (it < n_items) {
+      const int ya = v == 0 ? 0 : min(4 * v - 2, H), yb = v == 0 ? min(2, H) : min(4 * v + 2, H);
+      const uint32_t fwin = bit_window(fullw + v * fw, fw, 8 * l), mwin = bit_window(mixw + v * fw, fw, 8 * l);
+      // pixel x of this word lies in cell u = (x + 2) >> 2: nibble expansion in x' = x + 2, shifted back by 2
+      uint32_t pm = (expand_nibbles(fwin & 0xFFu) >> 2) | ((fwin & 0x100u) ? 0xC0000000u : 0u);
+      if (32 * l + 32 > W) pm &= (1u << (W - 32 * l)) - 1u;
+      if (ya < yb) {
+        npred += __popc(pm) * (yb - ya);
+        for (int y = ya; y < yb; ++y) inter += __popc(pm & gbits[y * ww + l]);
+        // a mixed cell belongs to the word that holds its first pixel: u = 8l+1 .. 8l+8 (and u = 0 for l = 0)
+        own = ((mwin >> 1) & 0xFFu) << 1 | (l == 0 ? (mwin & 1u) : 0u);
+      }
+    }
+    // warp-aggregated append of (v, u) pairs to this warp's list
+    const int cnt = __popc(own);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    int pos = n_mixed + pre - cnt;
+    while (own) {
+      const int j = __ffs(own) - 1;
+      own &= own - 1;
+      mixed[pos++] = (uint16_t)((v << 8) | (8 * l + j));
+    }
+    n_mixed += total;
+  }
+  __syncwarp();
+
+  // ---- phase 4: mixed cells, pixel by pixel (shared taps: <= 4 columns x <= 4 rows per cell) ----
+  for (int it = lane; it < n_mixed; it += 32) {
+    const int v = mixed[it] >> 8, u = mixed[it] & 0xFF;
+    const int ya = v == 0 ? 0 : min(4 * v - 2, H), yb = v == 0 ? min(2, H) : min(4 * v + 2, H);
+    const int xa = u == 0 ? 0 : min(4 * u - 2, W), xb = u == 0 ? min(2, W) : min(4 * u + 2, W);
+    float top[4], bot[4];
+    const Tap t0 = make_tap(ya, 0.25f, hp);           // every row of the cell has the same source rows
+    const float* r0 = src + t0.i0 * wp;
+    const float* r1 = src + t0.i1 * wp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Tap tx = make_tap(min(xa + j, W - 1), 0.25f, wp);
+      const float a = __ldg(r0 + tx.i0), bb = __ldg(r0 + tx.i1), c = __ldg(r1 + tx.i0), d = __ldg(r1 + tx.i1);
+      top[j] = __fmaf_rn(a, tx.l0, __fmul_rn(bb, tx.l1));
+      bot[j] = __fmaf_rn(c, tx.l0, __fmul_rn(d, tx.l1));
+    }
+    const int nx = xb - xa;
+    for (int y = ya; y < yb; ++y) {
+      const Tap ty = make_tap(y, 0.25f, hp);
+      const unsigned tb = row_bits(gbits + y * ww, ww, xa, nx);
+      unsigned pb = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nx && __fmaf_rn(top[j], ty.l0, __fmul_rn(bot[j], ty.l1)) > 0.5f) pb |= 1u << j;
+      inter += __popc(pb & tb);
+      npred += __popc(pb);
+    }
+  }
+  inter = warp_sum(inter);
+  npred = warp_sum(npred);
+  if (lane == 0) {
+    int32_t* o = q_counts + ((int64_t)b * nq + q) * SMK_QCOUNT_STRIDE;
+    o[0] = inter;
+    o[1] = npred + ngt - inter;   // |p ∪ g|
+  }
+}
+
 // all reductions for the objectness-selected (blockIdx.x == 0) and best-IoU (1) mask of image blockIdx.y
 __global__ void __launch_bounds__(kEvalThreads)
 mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
@@ -571,10 +824,21 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
     SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
+  // cell-classified IoU kernel (one warp per query): bit-packed GT + per-warp bit rows and mixed-cell lists in shared memory
+  const int n_cells = (hp + 1) * (wp + 1);
+  const size_t cells_bytes = (size_t)H * ((W + 31) / 32) * 4 +
+                             (size_t)kEvalWarps * (((size_t)hp * ((wp + 31) / 32) + 2 * (size_t)(hp + 1) * ((wp + 32) / 32)) * 4 + (size_t)n_cells * 2);
+  static const bool cells_on = !(getenv("SMK_EVAL_CELLS") && atoi(getenv("SMK_EVAL_CELLS")) == 0);   // A/B switch (tuning)
+  const bool cells = x4 && cells_on && wp <= 32 * kCellMaxWords - 1 && hp <= 255 && cells_bytes <= 200 * 1024;
+  if (cells && cells_bytes > 40 * 1024)
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cells_bytes));
   {
     // algorithmic bytes "as if materialised" (SURVEY.md §8d): every full-resolution mask pixel (fp32) + the GT plane
     ProfScope prof(PROF_EVAL, (double)B * ((double)nq * H * W * 4.0 + (double)H * W), s);
-    if (x4)
+    if (cells)
+      SMK_CHECK_CUDA(launch_pdl(query_iou_cells_kernel, dim3((nq + kEvalWarps - 1) / kEvalWarps, B), dim3(kEvalThreads), cells_bytes, s, mask_pred,
+                                batch_stride, gt, nq, hp, wp, H, W, q_counts));
+    else if (x4)
       SMK_CHECK_CUDA(launch_pdl(query_iou_x4_kernel, dim3(nq, B), dim3(kEvalThreads), (size_t)plane_bytes, s, mask_pred, batch_stride, gt, nq, hp, wp, H, W,
                                 q_counts));
     else

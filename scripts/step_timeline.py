@@ -25,8 +25,11 @@ cfg = O.make_config(n_queries=args.nq)
 sd = O.synth_state_dict(cfg, seed=0)
 model = S.SelfMaskB200(n_queries=args.nq, mode=args.mode, max_batch=args.batch).to(dev)
 model.load_state_dict(sd)
-x = torch.randint(0, 256, (args.batch, 3, args.size, args.size), dtype=torch.uint8, device=dev)
-gt = (torch.rand(args.batch, 1, args.size, args.size, device=dev) > 0.7).to(torch.uint8)
+from selfmask_b200 import synthetic as Y  # noqa: E402  (same synthetic images / ground truth as bench.py)
+uniq = min(args.batch, 32)
+rep = (args.batch + uniq - 1) // uniq
+x = torch.from_numpy(Y.synth_images_u8(uniq, args.size, args.size, seed=1234)).repeat(rep, 1, 1, 1)[:args.batch].to(dev)
+gt = torch.from_numpy(Y.synth_gt(uniq, args.size, args.size, seed=4321)).repeat(rep, 1, 1, 1)[:args.batch].to(dev)
 for _ in range(3):
     out = model(x)
     rec = S.eval_batch(out["mask_pred"], out["objectness"], gt)

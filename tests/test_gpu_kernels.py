@@ -120,6 +120,32 @@ def test_eval_batch_counts_bit_exact_vs_oracle(B, nq, hp, wp, H, W):
             assert (np.isnan(sa) and np.isnan(sb)) or abs(sa - sb) <= 2e-5
 
 
+@pytest.mark.parametrize("B,nq,hp,wp,H,W", [(2, 20, 56, 56, 224, 224), (2, 7, 52, 48, 200, 180), (1, 5, 96, 96, 384, 384), (2, 4, 3, 2, 12, 8),
+                                            (1, 9, 56, 56, 222, 220)])
+def test_query_iou_cells_bit_exact_on_threshold_hugging_planes(B, nq, hp, wp, H, W):
+    """Cell-classified per-query IoU (query_iou_cells_kernel): planes whose samples sit at 0.5, one ulp either side of it, or are
+    noisy — so almost every cell is a boundary cell or a constant field at the threshold — with cropped / tiny geometries."""
+    rng = np.random.default_rng(hp * 7 + W)
+    half = np.float32(0.5)
+    vals = np.array([half, np.nextafter(half, np.float32(1)), np.nextafter(half, np.float32(0)), 0.0, 1.0, 0.49, 0.51], np.float32)
+    probs = vals[rng.integers(0, len(vals), (B, nq, hp, wp))]
+    noisy = rng.random((B, nq, hp, wp)).astype(np.float32)
+    use_noise = rng.random((B, nq, 1, 1)) < 0.3
+    probs = np.where(use_noise, noisy, probs).astype(np.float32)
+    probs[:, 0] = half                                   # a whole plane exactly at the threshold: nothing is predicted
+    probs[:, -1] = np.nextafter(half, np.float32(1))     # ... and one ulp above it: everything is
+    obj = rng.random((B, nq)).astype(np.float32)
+    gt = (rng.random((B, 1, H, W)) < 0.4).astype(np.uint8)
+    rec = S.eval_batch(dev(probs), dev(obj), dev(gt), up=4)
+    torch.cuda.synchronize()
+    qc = rec.q_counts.cpu().numpy()
+    full = O.upsample_bilinear(probs, 4)[..., :H, :W]
+    for b in range(B):
+        inter, union = O.iou_counts(full[b], np.broadcast_to(gt[b, 0], full[b].shape))
+        assert np.array_equal(qc[b, :, 0], inter) and np.array_equal(qc[b, :, 1], union), b
+        assert qc[b, 0, 0] == 0 and qc[b, -1, 1] == H * W
+
+
 def test_device_finalisation_is_bit_identical_to_host(golden_dir):
     """smk_finalize_records == metrics.finalize (numpy) on real records (golden masks, edge-case GTs incl. the reference's
     NaN S-measure cases) and on randomised records: every float32 metric and the float64 S-measure, bit for bit."""

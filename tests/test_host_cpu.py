@@ -181,3 +181,30 @@ def test_package_synthetic_generators_match_the_oracle():
     assert all(a[k].shape == b[k].shape and torch.equal(a[k], b[k]) for k in a)
     assert np.array_equal(O.synth_images_u8(2, 64, 48, 5), Y.synth_images_u8(2, 64, 48, 5))
     assert np.array_equal(O.synth_gt(7, 64, 48, 6, edge_every=3), Y.synth_gt(7, 64, 48, 6, edge_every=3))
+
+
+def test_x4_bilinear_cell_shortcut_premise():
+    """smk_eval.cu's cell-classified IoU kernel skips cells whose 4 corner samples are all > 0.5 (or all <= 0.5).  That is exact
+    iff the ATen-order bilinear blend f(a,b,c,d) = fma(top, ly0, bot*ly1), top = fma(a, lx0, b*lx1), is monotone in its corners
+    (round-to-nearest is) and maps the constant field c to 0.5 for c = 0.5 and to > 0.5 for c = nextafter(0.5): checked here for
+    every x4 weight pair, with float32 fma emulated exactly in float64."""
+    f32 = np.float32
+
+    def fma(a, b, c):          # a*b + c rounded once (a*b needs <= 27 bits, the f64 sum is exact)
+        return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    def blend(c, lx1, ly1):
+        lx0, ly0 = f32(1) - f32(lx1), f32(1) - f32(ly1)
+        top = fma(c, lx0, f32(c * f32(lx1)))
+        bot = top
+        return fma(top, ly0, f32(bot * f32(ly1)))
+
+    weights = [0.0, 0.125, 0.375, 0.625, 0.875]     # l1 of make_tap() at scale 4 (0 where the source index is clamped)
+    half, above = f32(0.5), np.nextafter(f32(0.5), f32(1))
+    rng = np.random.default_rng(0)
+    for lx1 in weights:
+        for ly1 in weights:
+            assert blend(half, lx1, ly1) == half
+            assert blend(above, lx1, ly1) > half
+            for c in rng.random(64).astype(np.float32):          # constant fields never cross 0.5 from their own side
+                assert (blend(c, lx1, ly1) > half) == (c > half)
