@@ -365,24 +365,9 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t* row, int nw, int 
   return __funnelshift_r(lo, hi, pos & 31);
 }
 
-__global__ void __launch_bounds__(kEvalThreads)
-query_iou_cells_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
-                       int nq, int hp, int wp, int H, int W, int32_t* __restrict__ q_counts) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ uint32_t dyn_cells[];
-  __shared__ int red[kEvalWarps];
-  const int ww = (W + 31) >> 5, aw = (wp + 31) >> 5, fw = (wp + 32) >> 5, n_cells = (hp + 1) * (wp + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* gbits = dyn_cells;                                            // [H][ww] ground truth, one bit per pixel
-  uint32_t* abits = gbits + H * ww + warp * (hp * aw + 2 * (hp + 1) * fw);   // [hp][aw]  sample > 0.5
-  uint32_t* fullw = abits + hp * aw;                                      // [hp+1][fw] cell: all 4 corners above
-  uint32_t* mixw = fullw + (hp + 1) * fw;                                 // [hp+1][fw] cell: some, not all, corners above
-  uint16_t* mixed = reinterpret_cast<uint16_t*>(gbits + H * ww + kEvalWarps * (hp * aw + 2 * (hp + 1) * fw)) + warp * n_cells;
-  const int b = blockIdx.y;
-  const uint8_t* g = gt + (int64_t)b * H * W;
-
-  // ---- ground truth → one bit per pixel (W % 4 == 0: rows are 4-byte aligned) ----
+// Ground truth [H,W] bytes → one bit per pixel, rows of ww 32-bit words in shared memory (W % 4 == 0, g 4-byte aligned).
+// Block-cooperative; returns this thread's share of the foreground count.  The caller's next barrier publishes gbits.
+__device__ __forceinline__ int pack_gt_bits(const uint8_t* __restrict__ g, uint32_t* gbits, int H, int W, int ww) {
   int ngt = 0;
   auto nibble = [](uint32_t px4) { return ((__vcmpne4(px4, 0u) & 0x08040201u) * 0x01010101u) >> 24; };   // byte j non-zero → bit j
   if ((W & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
@@ -422,6 +407,27 @@ query_iou_cells_kernel(const float* __restrict__ mask_pred, int64_t batch_stride
       ngt += __popc(bits);
     }
   }
+  return ngt;
+}
+
+__global__ void __launch_bounds__(kEvalThreads)
+query_iou_cells_kernel(const float* __restrict__ mask_pred, int64_t batch_stride, const uint8_t* __restrict__ gt,
+                       int nq, int hp, int wp, int H, int W, int32_t* __restrict__ q_counts) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ uint32_t dyn_cells[];
+  __shared__ int red[kEvalWarps];
+  const int ww = (W + 31) >> 5, aw = (wp + 31) >> 5, fw = (wp + 32) >> 5, n_cells = (hp + 1) * (wp + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* gbits = dyn_cells;                                            // [H][ww] ground truth, one bit per pixel
+  uint32_t* abits = gbits + H * ww + warp * (hp * aw + 2 * (hp + 1) * fw);   // [hp][aw]  sample > 0.5
+  uint32_t* fullw = abits + hp * aw;                                      // [hp+1][fw] cell: all 4 corners above
+  uint32_t* mixw = fullw + (hp + 1) * fw;                                 // [hp+1][fw] cell: some, not all, corners above
+  uint16_t* mixed = reinterpret_cast<uint16_t*>(gbits + H * ww + kEvalWarps * (hp * aw + 2 * (hp + 1) * fw)) + warp * n_cells;
+  const int b = blockIdx.y;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+
+  int ngt = pack_gt_bits(g, gbits, H, W, ww);
   ngt = block_sum_int(ngt, red);         // (contains the barrier that publishes gbits)
   const int q = blockIdx.x * kEvalWarps + warp;
   if (q >= nq) return;
@@ -580,7 +586,118 @@ query_iou_cells_kernel(const float* __restrict__ mask_pred, int64_t batch_stride
   }
 }
 
-// all reductions for the objectness-selected (blockIdx.x == 0) and best-IoU (1) mask of image blockIdx.y
+// Block-cooperative count of the pixels above `thr` (and of those that are also foreground) of the plane in shared memory,
+// by source cells like query_iou_cells_kernel.  A general threshold is not a power of two, so bilerp(c,c,c,c) may differ from
+// c by an ulp: cells are skipped only behind a guard band — all 4 corners > t_hi = thr·(1+2e-6) (every pixel is a convex
+// blend with <= 3 roundings of relative error 2^-24, hence > thr) or all 4 corners <= t_lo = thr·(1-2e-6) (no pixel > thr);
+// every other cell is evaluated pixel by pixel with the exact compare.  Scratch: bit rows / lists in shared memory.
+struct CellScratch {
+  uint32_t *hi, *lo;        // [hp][aw] sample > t_hi / sample > t_lo
+  uint32_t *fullw, *mixw;   // [hp+1][fw]
+  uint16_t* mixed;          // [(hp+1)*(wp+1)]
+  int* n_mixed;
+};
+__device__ __forceinline__ void block_cells_count(const float* plane, const uint32_t* gbits, int hp, int wp, int H, int W, float thr,
+                                                  const CellScratch& sc, int& inter_out, int& npred_out) {
+  const int ww = (W + 31) >> 5, aw = (wp + 31) >> 5, fw = (wp + 32) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool guard_ok = thr > 1e-20f && thr < 1e20f;
+  const float t_hi = guard_ok ? thr * (1.0f + 2e-6f) : 3.0e38f, t_lo = guard_ok ? thr * (1.0f - 2e-6f) : -3.0e38f;
+  if (threadIdx.x == 0) *sc.n_mixed = 0;
+  for (int r = warp; r < hp; r += kEvalWarps)
+    for (int k = 0; k < aw; ++k) {
+      const int c = 32 * k + lane;
+      const float v = c < wp ? plane[r * wp + c] : -3.0e38f;
+      const uint32_t bh = __ballot_sync(0xffffffffu, v > t_hi), bl = __ballot_sync(0xffffffffu, v > t_lo);
+      if (lane == 0) { sc.hi[r * aw + k] = bh; sc.lo[r * aw + k] = bl; }
+    }
+  __syncthreads();
+  for (int v = threadIdx.x; v <= hp; v += kEvalThreads) {
+    const int ra = max(v - 1, 0) * aw, rb = min(v, hp - 1) * aw;
+    const int lw = (wp - 1) >> 5, ls = (wp - 1) & 31;
+    const uint32_t last_all = (sc.hi[ra + lw] >> ls) & (sc.hi[rb + lw] >> ls) & 1u, last_any = ((sc.lo[ra + lw] | sc.lo[rb + lw]) >> ls) & 1u;
+    uint32_t carry_all = sc.hi[ra] & sc.hi[rb] & 1u, carry_any = (sc.lo[ra] | sc.lo[rb]) & 1u;
+    for (int k = 0; k < fw; ++k) {
+      const uint32_t all_k = k < aw ? (sc.hi[ra + k] & sc.hi[rb + k]) : 0u, any_k = k < aw ? (sc.lo[ra + k] | sc.lo[rb + k]) : 0u;
+      const uint32_t l_all = (all_k << 1) | carry_all, l_any = (any_k << 1) | carry_any;
+      carry_all = all_k >> 31;
+      carry_any = any_k >> 31;
+      uint32_t r_all = all_k, r_any = any_k;
+      if (k == (wp >> 5)) { r_all |= last_all << (wp & 31); r_any |= last_any << (wp & 31); }
+      const uint32_t full = l_all & r_all, some = l_any | r_any;
+      const int hi_bit = wp - 32 * k;
+      const uint32_t keep = hi_bit >= 31 ? 0xffffffffu : ((2u << hi_bit) - 1u);
+      sc.fullw[v * fw + k] = full & keep;
+      sc.mixw[v * fw + k] = some & ~full & keep;
+    }
+  }
+  __syncthreads();
+  int inter = 0, npred = 0;
+  const int n_items = (hp + 1) * ww;
+  for (int it = threadIdx.x; it < n_items; it += kEvalThreads) {
+    const int v = it / ww, l = it - v * ww;
+    const int ya = v == 0 ? 0 : min(4 * v - 2, H), yb = v == 0 ? min(2, H) : min(4 * v + 2, H);
+    if (ya >= yb) continue;
+    const uint32_t fwin = bit_window(sc.fullw + v * fw, fw, 8 * l), mwin = bit_window(sc.mixw + v * fw, fw, 8 * l);
+    uint32_t pm = (expand_nibbles(fwin & 0xFFu) >> 2) | ((fwin & 0x100u) ? 0xC0000000u : 0u);
+    if (32 * l + 32 > W) pm &= (1u << (W - 32 * l)) - 1u;
+    npred += __popc(pm) * (yb - ya);
+    for (int y = ya; y < yb; ++y) inter += __popc(pm & gbits[y * ww + l]);
+    uint32_t own = ((mwin >> 1) & 0xFFu) << 1 | (l == 0 ? (mwin & 1u) : 0u);
+    if (own) {
+      int pos = atomicAdd(sc.n_mixed, __popc(own));
+      while (own) {
+        const int j = __ffs(own) - 1;
+        own &= own - 1;
+        sc.mixed[pos++] = (uint16_t)((v << 8) | (8 * l + j));
+      }
+    }
+  }
+  __syncthreads();
+  const int n_mixed = *sc.n_mixed;
+  for (int it = threadIdx.x; it < n_mixed; it += kEvalThreads) {
+    const int v = sc.mixed[it] >> 8, u = sc.mixed[it] & 0xFF;
+    const int ya = v == 0 ? 0 : min(4 * v - 2, H), yb = v == 0 ? min(2, H) : min(4 * v + 2, H);
+    const int xa = u == 0 ? 0 : min(4 * u - 2, W), xb = u == 0 ? min(2, W) : min(4 * u + 2, W);
+    float top[4], bot[4];
+    const Tap t0 = make_tap(ya, 0.25f, hp);
+    const float* r0 = plane + t0.i0 * wp;
+    const float* r1 = plane + t0.i1 * wp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Tap tx = make_tap(min(xa + j, W - 1), 0.25f, wp);
+      top[j] = __fmaf_rn(r0[tx.i0], tx.l0, __fmul_rn(r0[tx.i1], tx.l1));
+      bot[j] = __fmaf_rn(r1[tx.i0], tx.l0, __fmul_rn(r1[tx.i1], tx.l1));
+    }
+    const int nx = xb - xa;
+    for (int y = ya; y < yb; ++y) {
+      const Tap ty = make_tap(y, 0.25f, hp);
+      const unsigned tb = row_bits(gbits + y * ww, ww, xa, nx);
+      unsigned pb = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nx && __fmaf_rn(top[j], ty.l0, __fmul_rn(bot[j], ty.l1)) > thr) pb |= 1u << j;
+      inter += __popc(pb & tb);
+      npred += __popc(pb);
+    }
+  }
+  inter_out = inter;
+  npred_out = npred;
+}
+
+// sum of the positions of the set bits of a word
+__device__ __forceinline__ int bitpos_sum(uint32_t w) {
+  return __popc(w & 0xAAAAAAAAu) + 2 * __popc(w & 0xCCCCCCCCu) + 4 * __popc(w & 0xF0F0F0F0u) + 8 * __popc(w & 0xFF00FF00u) +
+         16 * __popc(w & 0xFFFF0000u);
+}
+
+// All reductions for the objectness-selected (blockIdx.x == 0) and best-IoU (1) mask of image blockIdx.y, x4 path.
+// A thread owns the 4 pixels x = 4qi .. 4qi+3 and walks rows of source cells: the horizontal blends (top / bot) are shared by
+// the <= 4 pixel rows of a cell row, the ground truth comes from the bit-packed copy, histogram updates are run-length
+// aggregated per thread (neighbouring pixels of a smooth mask fall into the same bin), the float64 moments are kept for the
+// regions {rows above / below the centroid} x {all / left-of-centroid columns} and everything else is derived from them:
+//   sum|p-g| = (n_fg - S_fg p) + (S p - S_fg p),  S_bg (1-p) = n_bg - (S p - S_fg p),  S_bg (1-p)^2 = n_bg - 2 S_bg p + S_bg p^2.
+// Same pixel arithmetic as the generic kernel (make_tap + bilerp) → identical integer outputs.
 __global__ void __launch_bounds__(kEvalThreads)
 mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
                        int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
@@ -588,15 +705,26 @@ mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, c
                        int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float dyn[];
+  extern __shared__ uint32_t dyn_mm[];
   __shared__ int hist[kEvalWarps][512];
-  __shared__ float thr[256];
-  __shared__ int red_i[kEvalWarps];
-  __shared__ double red_d[kEvalWarps];
-  __shared__ int s_sel;
+  __shared__ float thr[258];
+  constexpr int kND = 13, kNI = 8;
+  __shared__ double red_d[kND][kEvalWarps];
+  __shared__ int red_i[kNI][kEvalWarps];
+  __shared__ int s_sel, s_nmixed;
   const int which = blockIdx.x, b = blockIdx.y;
   const int n_masks = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ww = (W + 31) >> 5, aw = (wp + 31) >> 5, fw = (wp + 32) >> 5;
+  float* plane = reinterpret_cast<float*>(dyn_mm);            // [hp*wp]
+  uint32_t* gbits = dyn_mm + hp * wp;                         // [H][ww]
+  CellScratch sc;
+  sc.hi = gbits + H * ww;
+  sc.lo = sc.hi + hp * aw;
+  sc.fullw = sc.lo + hp * aw;
+  sc.mixw = sc.fullw + (hp + 1) * fw;
+  sc.mixed = reinterpret_cast<uint16_t*>(sc.mixw + (hp + 1) * fw);
+  sc.n_mixed = &s_nmixed;
 
   if (threadIdx.x == 0) {
     int sel = 0;
@@ -617,36 +745,30 @@ mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, c
     s_sel = sel;
   }
   for (int i = threadIdx.x; i < kEvalWarps * 512; i += kEvalThreads) (&hist[0][0])[i] = 0;
-  if (threadIdx.x < 255) thr[threadIdx.x] = thresholds[threadIdx.x];
-  if (threadIdx.x == 255) thr[255] = 3.0e38f;
+  for (int i = threadIdx.x; i < 258; i += kEvalThreads) thr[i] = i < 255 ? thresholds[i] : 3.0e38f;
+  const uint8_t* g = gt + (int64_t)b * H * W;
+  int ng = pack_gt_bits(g, gbits, H, W, ww);
   __syncthreads();
   const int sel = s_sel;
   const float* src = planes + (int64_t)b * batch_stride + (int64_t)sel * hp * wp;
-  for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) dyn[i] = src[i];
-  __syncthreads();
-  const float* pl = dyn;
-  const uint8_t* g = gt + (int64_t)b * H * W;
-  const int Q4 = W >> 2, YS = kEvalThreads / Q4;
-  const int qi = threadIdx.x % Q4, ys = threadIdx.x / Q4;
-  const bool active = ys < YS;
-  const int n_iter = (H + YS - 1) / YS;        // uniform trip count: the histogram uses warp collectives
-  const int x0 = 4 * qi;
+  for (int i = threadIdx.x; i < hp * wp; i += kEvalThreads) plane[i] = src[i];
 
-  // ---- pass A over the ground truth: area and centroid (s_measure.py:11-31) -----------------
-  int ng = 0, sxg = 0, syg = 0;
-  if (active) {
-    for (int y = ys; y < H; y += YS) {
-      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
-      const int t0 = gq.x != 0, t1 = gq.y != 0, t2 = gq.z != 0, t3 = gq.w != 0;
-      const int rowc = t0 + t1 + t2 + t3;
-      ng += rowc;
-      sxg += rowc * x0 + t1 + 2 * t2 + 3 * t3;
-      syg += rowc * y;
+  // ---- pass A over the packed ground truth: area and centroid (s_measure.py:11-31) -----------------
+  int sxg = 0, syg = 0;
+  for (int i = threadIdx.x; i < H * ww; i += kEvalThreads) {
+    const uint32_t w = gbits[i];
+    if (w) {
+      const int y = i / ww, c = __popc(w);
+      sxg += c * ((i - y * ww) * 32) + bitpos_sum(w);
+      syg += c * y;
     }
   }
-  ng = block_sum_int(ng, red_i);
-  sxg = block_sum_int(sxg, red_i);
-  syg = block_sum_int(syg, red_i);
+  ng = warp_sum(ng); sxg = warp_sum(sxg); syg = warp_sum(syg);
+  if (lane == 0) { red_i[0][warp] = ng; red_i[1][warp] = sxg; red_i[2][warp] = syg; }
+  __syncthreads();               // also publishes the plane
+  ng = sxg = syg = 0;
+#pragma unroll
+  for (int w = 0; w < kEvalWarps; ++w) { ng += red_i[0][w]; sxg += red_i[1][w]; syg += red_i[2][w]; }
   int X, Y;
   if (ng == 0) {   // python round(cols / 2): half-to-even
     X = (int)rint((double)W / 2.0);
@@ -655,100 +777,124 @@ mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, c
     X = (int)rintf(__fdiv_rn((float)sxg, (float)ng));
     Y = (int)rintf(__fdiv_rn((float)syg, (float)ng));
   }
-  const int n_left = min(max(X - x0, 0), 4);   // how many of this thread's 4 pixels lie left of the centroid column
+  __syncthreads();               // red_i is reused below
 
-  // ---- pass B: histograms, counts at 0.5, moments ---------------------------------------------
-  const QuadX qx = make_quadx(active ? qi : 0, wp);
-  double sabs = 0, fg_p = 0, fg_p2 = 0, bg_q = 0, bg_q2 = 0;
-  double p_all = 0, p_l = 0, p_t = 0, p_tl = 0, p2_all = 0, p2_l = 0, p2_t = 0, p2_tl = 0, pg_all = 0, pg_l = 0, pg_t = 0, pg_tl = 0;
+  // ---- pass B: histograms, counts at 0.5, float64 moments ---------------------------------------
+  const int Q4 = W >> 2, YS = kEvalThreads / Q4;
+  const int qi = threadIdx.x % Q4, ys = threadIdx.x / Q4;
+  const int x0 = 4 * qi;
+  const int n_left = min(max(X - x0, 0), 4);   // how many of this thread's 4 pixels lie left of the centroid column
+  const unsigned lmask = (1u << n_left) - 1u;
+  double Tp = 0, Tp2 = 0, Tpg = 0, TLp = 0, TLp2 = 0, TLpg = 0, Bp = 0, Bp2 = 0, Bpg = 0, BLp = 0, BLp2 = 0, BLpg = 0, fgp2 = 0;
   int g_l = 0, g_t = 0, g_tl = 0, tp05 = 0, tpfp05 = 0;
+  int cur_key = 0, cur_cnt = 0;
   int* myhist = hist[warp];
-  for (int k = 0; k < n_iter; ++k) {
-    const int y = ys + k * YS;
-    const bool valid = active && y < H;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    unsigned tm = 0;
-    if (valid) {
-      const Tap ty = make_tap(y, 0.25f, hp);
-      quad4(pl + ty.i0 * wp, pl + ty.i1 * wp, qx, ty.l0, ty.l1, v);
-      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
-      tm = (gq.x ? 1u : 0u) | (gq.y ? 2u : 0u) | (gq.z ? 4u : 0u) | (gq.w ? 8u : 0u);
-    }
-    double qp = 0, qp2 = 0, qpg = 0, lp = 0, lp2 = 0, lpg = 0;
-    int lg_ = 0;
+  if (ys < YS) {
+    const QuadX qx = make_quadx(qi, wp);
+    for (int v = ys; v <= hp; v += YS) {
+      const int ya = v == 0 ? 0 : min(4 * v - 2, H), yb = v == 0 ? min(2, H) : min(4 * v + 2, H);
+      if (ya >= yb) break;
+      const float* r0 = plane + max(v - 1, 0) * wp;
+      const float* r1 = plane + min(v, hp - 1) * wp;
+      const float am = r0[qx.cm], ac = r0[qx.cc], ap = r0[qx.cp], bm = r1[qx.cm], bc = r1[qx.cc], bp = r1[qx.cp];
+      float top[4], bot[4];
+      top[0] = __fmaf_rn(am, qx.l0[0], __fmul_rn(ac, qx.l1[0])); bot[0] = __fmaf_rn(bm, qx.l0[0], __fmul_rn(bc, qx.l1[0]));
+      top[1] = __fmaf_rn(am, qx.l0[1], __fmul_rn(ac, qx.l1[1])); bot[1] = __fmaf_rn(bm, qx.l0[1], __fmul_rn(bc, qx.l1[1]));
+      top[2] = __fmaf_rn(ac, qx.l0[2], __fmul_rn(ap, qx.l1[2])); bot[2] = __fmaf_rn(bc, qx.l0[2], __fmul_rn(bp, qx.l1[2]));
+      top[3] = __fmaf_rn(ac, qx.l0[3], __fmul_rn(ap, qx.l1[3])); bot[3] = __fmaf_rn(bc, qx.l0[3], __fmul_rn(bp, qx.l1[3]));
+      for (int y = ya; y < yb; ++y) {
+        const Tap ty = make_tap(y, 0.25f, hp);
+        const unsigned tm = (gbits[y * ww + (x0 >> 5)] >> (x0 & 31)) & 0xFu;
+        double qp = 0, qp2 = 0, qpg = 0, lp = 0, lp2 = 0, lpg = 0;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const float vv = v[f];
-      const int t = (tm >> f) & 1;
-      // bin = #{k : t_k < v}, exact float32 thresholds, strict compare (f_measure.py:65, :45)
-      int kb = min(max((int)(vv * 255.0f), 0), 255);
-      while (kb < 255 && thr[kb] < vv) ++kb;
-      while (kb > 0 && !(thr[kb - 1] < vv)) --kb;
-      const int key = valid ? (t ? kb : 256 + kb) : 1024;
-      const int first = __shfl_sync(0xffffffffu, key, 0);
-      if (__all_sync(0xffffffffu, key == first)) {       // saturated regions: one add for the whole warp
-        if (lane == 0 && first < 512) atomicAdd(&myhist[first], 32);
-      } else {
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&myhist[key], __popc(peers));
-      }
-      if (valid) {
-        const int p = vv > 0.5f;
-        tp05 += p & t;
-        tpfp05 += p;
-        const double dv = (double)vv, dv2 = dv * dv, dg = t ? dv : 0.0;
-        if (t) { fg_p += dv; fg_p2 += dv2; sabs += 1.0 - dv; }
-        else   { const double w = 1.0 - dv; bg_q += w; bg_q2 += w * w; sabs += dv; }
-        qp += dv; qp2 += dv2; qpg += dg;
-        if (f < n_left) { lp += dv; lp2 += dv2; lpg += dg; lg_ += t; }
+        for (int f = 0; f < 4; ++f) {
+          const float vv = __fmaf_rn(top[f], ty.l0, __fmul_rn(bot[f], ty.l1));
+          const int t = (tm >> f) & 1;
+          // bin = #{k : t_k < v}, exact float32 thresholds, strict compare (f_measure.py:65, :45); trunc(v*255) is at most 2 low
+          const int k0 = min(max((int)(vv * 255.0f), 0), 255);
+          const int key = k0 + (thr[k0] < vv ? 1 : 0) + (thr[k0 + 1] < vv ? 1 : 0) + (t ? 0 : 256);
+          if (key == cur_key) {
+            ++cur_cnt;
+          } else {
+            if (cur_cnt) atomicAdd(&myhist[cur_key], cur_cnt);
+            cur_key = key;
+            cur_cnt = 1;
+          }
+          const int p = vv > 0.5f;
+          tp05 += p & t;
+          tpfp05 += p;
+          const double dv = (double)vv;
+          qp += dv;
+          qp2 = fma(dv, dv, qp2);
+          if (t) { qpg += dv; fgp2 = fma(dv, dv, fgp2); }
+          if (f == n_left - 1) { lp = qp; lp2 = qp2; lpg = qpg; }     // prefix over the pixels left of the centroid column
+        }
+        const int gl = __popc(tm & lmask);
+        g_l += gl;
+        if (y < Y) { Tp += qp; Tp2 += qp2; Tpg += qpg; TLp += lp; TLp2 += lp2; TLpg += lpg; g_t += __popc(tm); g_tl += gl; }
+        else       { Bp += qp; Bp2 += qp2; Bpg += qpg; BLp += lp; BLp2 += lp2; BLpg += lpg; }
       }
     }
-    if (valid) {
-      const int qg = __popc(tm);
-      p_all += qp; p2_all += qp2; pg_all += qpg;
-      p_l += lp; p2_l += lp2; pg_l += lpg; g_l += lg_;
-      if (y < Y) { p_t += qp; p2_t += qp2; pg_t += qpg; g_t += qg; p_tl += lp; p2_tl += lp2; pg_tl += lpg; g_tl += lg_; }
+    if (cur_cnt) atomicAdd(&myhist[cur_key], cur_cnt);
+  }
+  {
+    const double dv_[kND] = {Tp, Tp2, Tpg, TLp, TLp2, TLpg, Bp, Bp2, Bpg, BLp, BLp2, BLpg, fgp2};
+#pragma unroll
+    for (int i = 0; i < kND; ++i) {
+      const double r = warp_sum(dv_[i]);
+      if (lane == 0) red_d[i][warp] = r;
+    }
+    const int iv_[5] = {g_l, g_t, g_tl, tp05, tpfp05};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int r = warp_sum(iv_[i]);
+      if (lane == 0) red_i[i][warp] = r;
     }
   }
+  __syncthreads();
+  double sd[kND];
+#pragma unroll
+  for (int i = 0; i < kND; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalWarps; ++w) t += red_d[i][w];     // fixed order → run-to-run deterministic
+    sd[i] = t;
+  }
+  int si[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalWarps; ++w) t += red_i[i][w];
+    si[i] = t;
+  }
+  const double p_all = sd[0] + sd[6], p2_all = sd[1] + sd[7], pg_all = sd[2] + sd[8];
+  const double p_t = sd[0], p2_t = sd[1], pg_t = sd[2], p_tl = sd[3], p2_tl = sd[4], pg_tl = sd[5];
+  const double p_l = sd[3] + sd[9], p2_l = sd[4] + sd[10], pg_l = sd[5] + sd[11];
+  const double sp = p_all, fg_p = pg_all, fg_p2 = sd[12];
+  g_l = si[0]; g_t = si[1]; g_tl = si[2]; tp05 = si[3]; tpfp05 = si[4];
+  const int npix = H * W;
+  const double n_fg = (double)ng, n_bg = (double)(npix - ng), bg_p = sp - fg_p;
+  const double sabs = (n_fg - fg_p) + bg_p, bg_q = n_bg - bg_p, bg_q2 = n_bg - 2.0 * bg_p + (p2_all - fg_p2);
+
+  // F-mean threshold (f_measure.py:76): 2 * mean(p) in float32
+  const float tau = 2.0f * (float)(sp / (double)npix);
+
+  // ---- pass C: counts at the adaptive threshold (cells behind a guard band, the rest per pixel) -----
+  int tpm = 0, tpfpm = 0;
+  block_cells_count(plane, gbits, hp, wp, H, W, tau, sc, tpm, tpfpm);
+  tpm = warp_sum(tpm);
+  tpfpm = warp_sum(tpfpm);
+  __syncthreads();
+  if (lane == 0) { red_i[5][warp] = tpm; red_i[6][warp] = tpfpm; }
+  __syncthreads();
+  tpm = tpfpm = 0;
+#pragma unroll
+  for (int w = 0; w < kEvalWarps; ++w) { tpm += red_i[5][w]; tpfpm += red_i[6][w]; }
+
   const int64_t mrow = (int64_t)b * n_masks + which;
   int32_t* oc = m_counts + mrow * SMK_MCOUNT_STRIDE;
   double* os = m_sums + mrow * SMK_MSUM_STRIDE;
-
-  const double sp = block_sum_double(p_all, red_d);
-  sabs = block_sum_double(sabs, red_d);
-  fg_p = block_sum_double(fg_p, red_d); fg_p2 = block_sum_double(fg_p2, red_d);
-  bg_q = block_sum_double(bg_q, red_d); bg_q2 = block_sum_double(bg_q2, red_d);
-  p_l = block_sum_double(p_l, red_d); p_t = block_sum_double(p_t, red_d); p_tl = block_sum_double(p_tl, red_d);
-  p2_all = block_sum_double(p2_all, red_d); p2_l = block_sum_double(p2_l, red_d);
-  p2_t = block_sum_double(p2_t, red_d); p2_tl = block_sum_double(p2_tl, red_d);
-  pg_all = block_sum_double(pg_all, red_d); pg_l = block_sum_double(pg_l, red_d);
-  pg_t = block_sum_double(pg_t, red_d); pg_tl = block_sum_double(pg_tl, red_d);
-  g_l = block_sum_int(g_l, red_i); g_t = block_sum_int(g_t, red_i); g_tl = block_sum_int(g_tl, red_i);
-  tp05 = block_sum_int(tp05, red_i); tpfp05 = block_sum_int(tpfp05, red_i);
-  p_all = sp;
-
-  // F-mean threshold (f_measure.py:76): 2 * mean(p) in float32
-  const int npix = H * W;
-  const float tau = 2.0f * (float)(sp / (double)npix);
-
-  // ---- pass C: counts at the adaptive threshold -----------------------------------------------
-  int tpm = 0, tpfpm = 0;
-  if (active) {
-    for (int y = ys; y < H; y += YS) {
-      const Tap ty = make_tap(y, 0.25f, hp);
-      float v[4];
-      quad4(pl + ty.i0 * wp, pl + ty.i1 * wp, qx, ty.l0, ty.l1, v);
-      const uchar4 gq = *reinterpret_cast<const uchar4*>(g + (int64_t)y * W + x0);
-      const unsigned pm = (v[0] > tau ? 1u : 0u) | (v[1] > tau ? 2u : 0u) | (v[2] > tau ? 4u : 0u) | (v[3] > tau ? 8u : 0u);
-      const unsigned tm = (gq.x ? 1u : 0u) | (gq.y ? 2u : 0u) | (gq.z ? 4u : 0u) | (gq.w ? 8u : 0u);
-      tpm += __popc(pm & tm);
-      tpfpm += __popc(pm);
-    }
-  }
-  tpm = block_sum_int(tpm, red_i);
-  tpfpm = block_sum_int(tpfpm, red_i);
-
-  __syncthreads();
   for (int i = threadIdx.x; i < 512; i += kEvalThreads) {
     int s = 0;
 #pragma unroll
@@ -820,10 +966,14 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
   }
   const bool x4 = up == 4 && (W % 4) == 0 && W <= 4 * kEvalThreads && ((uintptr_t)gt % 4) == 0;
-  if (x4 && plane_bytes > 24 * 1024) {
+  if (x4 && plane_bytes > 24 * 1024)
     SMK_CHECK_CUDA(cudaFuncSetAttribute(query_iou_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes));
-  }
+  // x4 metrics kernel: plane + bit-packed GT + cell bit rows + mixed-cell list (static: 16 KB of histograms + reductions)
+  const size_t mm_bytes = plane_bytes + (size_t)H * ((W + 31) / 32) * 4 + (2 * (size_t)hp * ((wp + 31) / 32) + 2 * (size_t)(hp + 1) * ((wp + 32) / 32)) * 4 +
+                          (size_t)(hp + 1) * (wp + 1) * 2;
+  const bool x4m = x4 && wp <= 255 && hp <= 255 && mm_bytes <= 180 * 1024;
+  if (x4m && mm_bytes > 24 * 1024)
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_metrics_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mm_bytes));
   // cell-classified IoU kernel (one warp per query): bit-packed GT + per-warp bit rows and mixed-cell lists in shared memory
   const int n_cells = (hp + 1) * (wp + 1);
   const size_t cells_bytes = (size_t)H * ((W + 31) / 32) * 4 +
@@ -847,8 +997,8 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
   SMK_CHECK_LAUNCH();
   {
     ProfScope prof(PROF_EVAL, (double)B * 2.0 * ((double)H * W * 4.0 + (double)H * W), s);
-    if (x4)
-      SMK_CHECK_CUDA(launch_pdl(mask_metrics_x4_kernel, dim3(2, B), dim3(kEvalThreads), (size_t)plane_bytes, s, mask_pred, batch_stride, objectness,
+    if (x4m)
+      SMK_CHECK_CUDA(launch_pdl(mask_metrics_x4_kernel, dim3(2, B), dim3(kEvalThreads), mm_bytes, s, mask_pred, batch_stride, objectness,
                                 obj_stride, q_counts, gt, nq, hp, wp, H, W, g_thresholds, idx, m_counts, m_sums));
     else
       mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
