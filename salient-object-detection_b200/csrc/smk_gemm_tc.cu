@@ -561,8 +561,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return SMK_OK;
 }
 
-// Tile width: minimise (waves over the SMs) x BN, i.e. the tensor-pipe time of the busiest SM; ties go to the wider
-// tile (fewer operand bytes per MMA cycle).  `slots` = resident CTAs (or CTA pairs), `bm` = rows per tile.
+// Tile width: minimise (waves over the SMs) x (BN + 64): measured, a k-block of MMAs costs a fixed part plus a part
+// proportional to BN (SS-mode MMA floor and the A-tile feed do not shrink with BN; profiles/r01_gemm_experiments.md), so
+// narrow tiles only pay off when they save whole waves; ties go to the wider tile (fewer operand bytes per MMA cycle).
+// `slots` = resident CTAs (or CTA pairs), `bm` = rows per tile.
 static int pick_bn(int M, int N, int bm, int slots) {
   static int forced = -1;                      // SMK_GEMM_BN=128|192|256 forces the tile width (tuning aid)
   if (forced < 0) {
@@ -575,21 +577,23 @@ static int pick_bn(int M, int N, int bm, int slots) {
   int64_t best_cost = -1;
   for (int bn : {128, 192, 256}) {
     if (N % bn) continue;
-    const int64_t tiles = (N / bn) * mb, cost = (tiles + slots - 1) / slots * bn;
+    const int64_t tiles = (N / bn) * mb, cost = (tiles + slots - 1) / slots * (bn + 64);
     if (best_cost < 0 || cost <= best_cost) { best = bn; best_cost = cost; }
   }
   return best;
 }
 
-// 0 = single-CTA tiles only (default: measured faster on every shape of this model), 1 = CTA pairs where the problem is
-// large enough (wins from K >= 1024 with N >= 512); SMK_GEMM_CTA_PAIR overrides (tuning)
-static int cta_pair_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+// CTA pairs (cta_group::2, 256-row tiles, each CTA loads half of the weight tile): measured slower at K = 384 (the extra
+// cross-CTA hand-shakes per k-block are not amortised) and faster from K >= 1024 on many-row problems, where the GEMM sits at
+// the L2→SM operand-feed limit (fc2: 73.0 → 66.8 us).  SMK_GEMM_CTA_PAIR = 0 / 1 forces single CTAs / pairs (tuning).
+static bool use_cta_pair(int M, int K) {
+  static int mode = -2;
+  if (mode == -2) {
     const char* e = getenv("SMK_GEMM_CTA_PAIR");
-    mode = e ? atoi(e) : 0;
+    mode = e ? atoi(e) : -1;
   }
-  return mode;
+  if (mode >= 0) return mode != 0 && M > TC_BM;
+  return K >= 1024 && M >= 16384;
 }
 
 // SMK_GEMM_ARES=1 enables the A-resident schedule for K <= 384.  Default off: measured 5-10 % slower on this model's shapes
@@ -620,12 +624,13 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
-  const bool pair = tok_hw == 0 && cta_pair_mode() != 0 && M > TC_BM;
+  const bool pair = tok_hw == 0 && use_cta_pair(M, K);
   const bool ares = tok_hw == 0 && ares_mode() != 0 && K <= TC_ARES_KB * TC_BK;
   const int kc = pair ? 2 : 1;
   // A-resident: work is split by tile ranges, perfectly balanced for any width → the widest tile (fewest epilogue hand-overs)
   int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
   if (ares && !getenv("SMK_GEMM_BN")) BN = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
+  if (tok_hw > 0 && !getenv("SMK_GEMM_BN")) BN = 128;   // direct-store epilogue (patch embed): per-thread row stores favour narrow tiles (78 vs 82 us)
   CUtensorMap ta, tb, tcm;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));

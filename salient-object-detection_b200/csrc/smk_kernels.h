@@ -43,6 +43,7 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
                     cudaStream_t s);
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s1, int row_bytes1, int64_t rows, int period, cudaStream_t s);
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D,
               int hp, int wp, int sf, cudaStream_t s);
 int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s);

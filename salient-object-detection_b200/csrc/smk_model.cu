@@ -151,6 +151,10 @@ struct smk_model {
   __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *a3c, *a3f, *a3q, *dqk_b, *dv_b, *cq_b;
   float* debug_logits;
   int last_B;
+  // decoder state after layer 0's self-attention block (image-independent: tgt = 0), filled by the first forward pass
+  float* dec0_tgt;                // [nq, D]
+  __nv_bfloat16* dec0_a3b;        // [nq, 3D] split(tgt + query_pos)
+  bool dec0_ready = false;
 };
 
 namespace smk {
@@ -223,6 +227,8 @@ static void plan(smk_model& m, Plan& pl) {
     m.a3b = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(tgt + query_pos)
     m.a3c = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(attention output)
     m.a3f = pl.take<__nv_bfloat16>(std::max(R * 3 * FD, L * R * 3 * D));   // split(FFN hidden) / split(objectness hidden)
+    m.dec0_tgt = pl.take<float>(nq * D);
+    m.dec0_a3b = pl.take<__nv_bfloat16>(nq * 3 * D);
     m.a3q = pl.take<__nv_bfloat16>(L * R * 3 * D);                     // split(final-norm queries), all layers
     m.dqk_b = pl.take<__nv_bfloat16>(R * 2 * D);
     m.dv_b = pl.take<__nv_bfloat16>(R * D);
@@ -531,7 +537,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   const float* qpos = w + m->o_query;
   const int64_t ldkv = (int64_t)L * 2 * D;
   const int FD = c.dec_ffn;
-  SMK_CHECK_CUDA(cudaMemsetAsync(m->tgt, 0, (size_t)R * D * 4, s));
+  if (!bf) SMK_CHECK_CUDA(cudaMemsetAsync(m->tgt, 0, (size_t)R * D * 4, s));
   if (bf) {
     // bf16 mode: every B·nq-row GEMM on tcgen05 with the 3-term bf16 split folded into K (K' = 3K, ~fp32 accuracy:
     // the objectness ranking downstream has top-1 gaps of 1e-7…3e-3), attention on the tcgen05 kernel.
@@ -555,10 +561,20 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
                        int epi, int out_f32) {
         return gemm_bf16_tc(a3, 3 * K_, w3, 3 * K_, bias, C, ldc, rows, N_, 3 * K_, epi, out_f32, 0, nullptr, s);
       };
-      SMK_PROPAGATE(split3_act(tgt, D, qpos, nq, a3a, a3b, R, D, s));   // layer 0 input: tgt = 0
+      // Layer 0 starts from tgt = 0, so its whole self-attention block (q/k/v projections, attention, out-projection, add +
+      // LayerNorm: 6 launches) yields the same [nq, D] rows for every image: the first forward pass computes them with the
+      // regular kernels and keeps image 0's rows, later passes (same stream) tile them over the batch — bit-identical.
+      const bool reuse0 = m->dec0_ready;
+      if (!reuse0) {
+        SMK_CHECK_CUDA(cudaMemsetAsync(tgt, 0, (size_t)R * D * 4, s));
+        SMK_PROPAGATE(split3_act(tgt, D, qpos, nq, a3a, a3b, R, D, s));   // layer 0 input: tgt = 0
+      }
       for (int l = 0; l < L; ++l) {
         const DecW& d = m->dec[l];
         const Dec3& d3 = m->dec3[l];
+        if (l == 0 && reuse0) {
+          SMK_PROPAGATE(tile_rows2(tgt, m->dec0_tgt, D * 4, a3b, m->dec0_a3b, 3 * D * 2, R, nq, s));
+        } else {
         // self-attention: q = k = tgt + query_pos, v = tgt
         SMK_PROPAGATE(gemm3(a3b, d3.saw, w + d.sab, dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
         SMK_PROPAGATE(gemm3(a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, dv_b, D, R, D, D, SMK_EPI_NONE, 0));
@@ -566,6 +582,16 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         else SMK_PROPAGATE(attention_tc_general(dqk_b, 2 * D, dqk_b + D, 2 * D, dv_b, D, R, nq, 0, a3c, 3 * D, 2, nb, nq, nq, c.heads, scale, s));
         SMK_PROPAGATE(gemm3(a3c, d3.saow, w + d.saob, t2, D, R, D, D, SMK_EPI_NONE, 1));
         SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, a3b, nullptr, nullptr, nullptr, nullptr, R, D, s));
+        if (l == 0 && b0 == 0) {
+          cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+          cudaStreamIsCapturing(s, &cap);
+          if (cap == cudaStreamCaptureStatusNone) {
+            SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_tgt, tgt, (size_t)nq * D * 4, cudaMemcpyDeviceToDevice, s));
+            SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_a3b, a3b, (size_t)nq * 3 * D * 2, cudaMemcpyDeviceToDevice, s));
+            m->dec0_ready = true;
+          }
+        }
+        }
         // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
         SMK_PROPAGATE(gemm3(a3b, d3.caqw, w + d.cab, cq_b, D, R, D, D, SMK_EPI_NONE, 0));
         const __nv_bfloat16* kl = KVg + (int64_t)l * 2 * D;

@@ -394,22 +394,20 @@ SMK_ATT_INST(float, __nv_bfloat16)
 // ------------------------------------------------------------------------------------------------
 struct NormConst { float mean[3], std[3]; };
 
-template <typename TIn> __device__ __forceinline__ float load_pixel(const TIn* p, int c, const NormConst& nc);
-template <> __device__ __forceinline__ float load_pixel<float>(const float* p, int, const NormConst&) { return __ldg(p); }
-template <> __device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* p, int c, const NormConst& nc) {
-  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)__ldg(p), 255.0f), nc.mean[c]), nc.std[c]);
-}
+// `lut` (uint8 input only): the 3 x 256 possible normalised values, computed per CTA with the exact expression above
+template <typename TIn> __device__ __forceinline__ float load_pixel(const TIn* p, int c, const float* lut);
+template <> __device__ __forceinline__ float load_pixel<float>(const float* p, int, const float*) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* p, int c, const float* lut) { return lut[c * 256 + __ldg(p)]; }
 
-template <typename TIn> __device__ __forceinline__ void load_pixels4(const TIn* p, int c, const NormConst& nc, float (&v)[4]);
-template <> __device__ __forceinline__ void load_pixels4<float>(const float* p, int, const NormConst&, float (&v)[4]) {
+template <typename TIn> __device__ __forceinline__ void load_pixels4(const TIn* p, int c, const float* lut, float (&v)[4]);
+template <> __device__ __forceinline__ void load_pixels4<float>(const float* p, int, const float*, float (&v)[4]) {
   const float4 t = __ldg(reinterpret_cast<const float4*>(p));
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
-template <> __device__ __forceinline__ void load_pixels4<uint8_t>(const uint8_t* p, int c, const NormConst& nc, float (&v)[4]) {
+template <> __device__ __forceinline__ void load_pixels4<uint8_t>(const uint8_t* p, int c, const float* lut, float (&v)[4]) {
   const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
-  const uint8_t u[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u[e], 255.0f), nc.mean[c]), nc.std[c]);
+  const float* l = lut + c * 256;
+  v[0] = l[t.x]; v[1] = l[t.y]; v[2] = l[t.z]; v[3] = l[t.w];
 }
 __device__ __forceinline__ void store4(float* dst, const float (&v)[4]) { *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&v)[4]) {
@@ -426,6 +424,14 @@ im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t im2col_smem[];
+  __shared__ float lut[sizeof(TIn) == 1 ? 3 * 256 : 1];
+  if constexpr (sizeof(TIn) == 1) {      // every value a uint8 pixel can normalise to (two IEEE divisions each, done 768 times per CTA)
+    for (int i = threadIdx.x; i < 3 * 256; i += 256) {
+      const int c = i >> 8;
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), nc.mean[c]), nc.std[c]);
+    }
+    __syncthreads();
+  }
   T* strip = reinterpret_cast<T*>(im2col_smem);         // [3*P][ws], ws = wp*P + pad
   const int py = blockIdx.x, b = blockIdx.y;
   const int Wp = wp * P, ws = Wp + 16 / (int)sizeof(T);
@@ -437,11 +443,11 @@ im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (yy < H) {
       const TIn* row = src + ((int64_t)c * H + yy) * W;
-      if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, nc, v);
+      if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, lut, v);
       else {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, nc);
+          if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, lut);
       }
     }
     store4(strip + r * ws + xx, v);
@@ -521,6 +527,34 @@ int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, 
   {
     ProfScope prof(PROF_OTHER, (double)rows * D * 8.0, s);
     add_rows_kernel<<<(unsigned)((rows * D + 255) / 256), 256, 0, s>>>(a, pos, out, rows, D, period);
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
+// dst[r] = src[r % period] for two row-periodic buffers at once (16-byte vectors): the decoder state after layer 0's
+// self-attention block does not depend on the image (tgt = 0), so it is computed once and tiled over the batch.
+__global__ void __launch_bounds__(256)
+tile_rows2_kernel(uint4* __restrict__ d0, const uint4* __restrict__ s0, int v0, uint4* __restrict__ d1, const uint4* __restrict__ s1, int v1,
+                  int64_t rows, int period) {
+  pdl_wait();
+  pdl_trigger();
+  const int vt = v0 + v1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * vt) return;
+  const int64_t r = i / vt;
+  const int c = (int)(i - r * vt), pr = (int)(r % period);
+  if (c < v0) d0[r * v0 + c] = __ldg(s0 + (int64_t)pr * v0 + c);
+  else d1[r * v1 + (c - v0)] = __ldg(s1 + (int64_t)pr * v1 + (c - v0));
+}
+int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s1, int row_bytes1, int64_t rows, int period, cudaStream_t s) {
+  SMK_REQUIRE(row_bytes0 % 16 == 0 && row_bytes1 % 16 == 0 && period > 0, "tile_rows2: rows must be multiples of 16 bytes");
+  if (rows == 0) return SMK_OK;
+  const int v0 = row_bytes0 / 16, v1 = row_bytes1 / 16;
+  {
+    ProfScope prof(PROF_OTHER, (double)rows * (row_bytes0 + row_bytes1), s);
+    SMK_CHECK_CUDA(launch_pdl(tile_rows2_kernel, dim3((unsigned)((rows * (v0 + v1) + 255) / 256)), dim3(256), 0, s, (uint4*)d0, (const uint4*)s0, v0,
+                              (uint4*)d1, (const uint4*)s1, v1, rows, period));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
