@@ -23,7 +23,7 @@ namespace smk {
 
 using namespace tc;
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_BM = 128, TC_BK = 64;   // epilogue warps: 8 (default) or 16 (kEW template parameter); threads = 64 + 32 * kEW
 constexpr int TC_STAGING_PER_WARP = 4096;   // 32 rows x 128 B (fp32 chunk) or 2 x (32 rows x 64 B) (bf16 chunks, double-buffered)
 
 // exact-GELU (vision_transformer.py:78 nn.GELU, erf form) as  relu(x) − 0.5·|x|·(1 − erf(|x|/√2))  with
@@ -54,14 +54,21 @@ constexpr int TC_BAR_BYTES = 512;
 // (128 + BN)·K·2 per tile to BN·K·2 (qkv: 695 MB → 387 MB per launch).  Measured on B200 it is 5-10 % slower than the
 // strided order on this model's shapes: those GEMMs are bound by the epilogue (GELU / TMA stores) and by the ~150-cycle
 // floor of an SS-mode M = 128 MMA, not by the L2→SM operand feed (profiles/r01_gemm_experiments.md).
-template <int BN, int kCtas, bool kARes>
+// kEW = 16: bf16-output tiles of 256 columns with four epilogue warps per scheduler instead of two.  The GELU / bias / pack
+// epilogue is a ~300-instruction dependent-latency stream per 32-column chunk; two warps per scheduler issue only ~50 % of the
+// cycles (ncu: long-scoreboard + fixed-latency waits), which made fc1 epilogue-bound (73 us vs 40 us of MMAs).  Each warp then
+// owns 64 columns (2 chunks) and a single 2 KB staging buffer, so the operand ring keeps its depth.
+template <int BN, int kCtas, bool kARes, int kEW = 8>
 struct TcCfg {
+  static_assert(kEW == 8 || (kEW == 16 && BN % 128 == 0), "16 epilogue warps need whole 32-column chunks per warp");
+  static constexpr int kThreads = 64 + 32 * kEW;
+  static constexpr int kStagingPerWarp = kEW == 16 ? 2048 : TC_STAGING_PER_WARP;
   static constexpr int kBNL = BN / kCtas;                          // B-tile rows loaded by one CTA
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = kBNL * TC_BK * 2;
   static constexpr int kAResBytes = kARes ? TC_ARES_KB * kABytes : 0;
   static constexpr int kStageBytes = kARes ? kBBytes : kABytes + kBBytes;
-  static constexpr int kStagingBytes = TC_EPI_WARPS * TC_STAGING_PER_WARP;
+  static constexpr int kStagingBytes = kEW * kStagingPerWarp;
   static constexpr int kRingBudget = 227 * 1024 - kStagingBytes - 1024 - TC_BAR_BYTES - kAResBytes;
   static constexpr int kStages = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
@@ -114,11 +121,11 @@ struct TcGemmParams {
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
 // M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
 // the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
-template <int BN, bool kDirect, int kCtas, bool kARes>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, bool kDirect, int kCtas, bool kARes, int kEW = 8>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const TcGemmParams p) {
-  using Cfg = TcCfg<BN, kCtas, kARes>;
+  using Cfg = TcCfg<BN, kCtas, kARes, kEW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem = smem_base + Cfg::kAResBytes;   // operand ring (the resident A block, if any, sits in front of it)
@@ -149,7 +156,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     if (!kDirect) tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], TC_EPI_WARPS * kCtas); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEW * kCtas); }
     for (int i = 0; i < TC_ARES_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     fence_barrier_init();
   }
@@ -278,11 +285,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (trace) { trace[2] = w_ops.acc; trace[3] = w_acc.acc; trace[4] = w_all.acc; }
     }
   } else {
-    // ===== epilogue: warps 2..9; lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4 =====
+    // ===== epilogue: warps 2..; lane quarter = warp % 4 (hardware rule), column group = (warp - 2) / 4 =====
     const int quarter = warp & 3;
     const int col_half = (warp - 2) >> 2;
-    constexpr int kChunks = BN / 64;             // 32-column chunks per warp per tile
-    uint8_t* stg = staging + (warp - 2) * TC_STAGING_PER_WARP;
+    constexpr int kChunks = BN / (8 * kEW);      // 32-column chunks per warp per tile
+    uint8_t* stg = staging + (warp - 2) * Cfg::kStagingPerWarp;
     const uint32_t stg_u32 = smem_u32(stg);
     auto r4 = [](float f) { return __float_as_uint(f); };
     int acc = 0;
@@ -318,10 +325,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = n_blk * BN + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
-        float4 bv[8];
-        if (p.bias) {                            // L1 hits after the first tile; in flight under the TMEM load
+        float4 bv[kEW == 16 ? 1 : 8];
+        if (kEW != 16 && p.bias) {               // L1 hits after the first tile; in flight under the TMEM load
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+          for (int j = 0; j < (kEW == 16 ? 1 : 8); ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
         }
         w_ld.begin();
         tmem_ld_wait();
@@ -340,7 +347,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b = bv[j >> 2];
+            // 16-warp variant (<= 112 registers): no prefetched copy, the (L1-resident, warp-uniform) bias is read at use
+            const float4 b = kEW == 16 ? __ldg(reinterpret_cast<const float4*>(p.bias + n0) + (j >> 2)) : bv[kEW == 16 ? 0 : (j >> 2)];
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
@@ -375,7 +383,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             continue;
           }
           w_st.begin();
-          if (p.out_f32 == 1) {
+          if (kEW != 16 && p.out_f32 == 1) {
             // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -390,7 +398,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               else tma_store_2d(&tmC, stg, n0, row0);
               bulk_commit();
             }
-          } else if (p.out_f32 == 2) {
+          } else if (kEW != 16 && p.out_f32 == 2) {
             // bf16x3 split output: hi tile → columns n0 and N + n0, lo tile → 2N + n0 (two 32 x 64 B staging tiles)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -414,9 +422,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
             // staging tile: 32 rows x 64 B, 64-byte swizzle (16-byte chunk index ^= (row >> 1) & 3), two buffers
-            uint8_t* buf = stg + (it & 1) * 2048;
+            uint8_t* buf = kEW == 16 ? stg : stg + (it & 1) * 2048;      // 16-warp variant: one buffer per warp
             ++it;
-            if (lane == 0) bulk_wait_read<1>();
+            if (lane == 0) {
+              if constexpr (kEW == 16) bulk_wait_read<0>();
+              else bulk_wait_read<1>();
+            }
             __syncwarp();
             const uint32_t srow = stg_u32 + (uint32_t)(buf - stg) + lane * 64;
 #pragma unroll
@@ -520,12 +531,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool kDirect, int kCtas, bool kARes>
+template <int BN, bool kDirect, int kCtas, bool kARes, int kEW = 8>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, kCtas, kARes>;
+  using Cfg = TcCfg<BN, kCtas, kARes, kEW>;
   static bool attr_set = false;
   if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -534,7 +545,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   const int grid = (tiles < slots ? tiles : slots) * kCtas;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
@@ -555,7 +566,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.numAttrs = n_attr;
   {
     ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
-    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes>, ta, tb, tcm, p));
+    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes, kEW>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -607,8 +618,22 @@ static int ares_mode() {
   return mode;
 }
 
+// 16 epilogue warps: bf16-output 256-column tiles of many-row problems (fc1, memory K/V); SMK_GEMM_EPI16 = 0 / 1 overrides (tuning)
+static bool use_epi16(const TcGemmParams& p) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("SMK_GEMM_EPI16");
+    mode = e ? atoi(e) : -1;
+  }
+  if (p.out_f32 != 0) return false;
+  return mode >= 0 ? mode != 0 : p.M >= 16384;
+}
+
 template <bool kDirect, int kCtas, bool kARes>
 static int launch_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
+  if constexpr (!kDirect && !kARes) {
+    if (BN == 256 && use_epi16(p)) return launch_tc<256, false, kCtas, false, 16>(ta, tb, tcm, p, s);
+  }
   return BN == 256 ? launch_tc<256, kDirect, kCtas, kARes>(ta, tb, tcm, p, s)
                    : (BN == 192 ? launch_tc<192, kDirect, kCtas, kARes>(ta, tb, tcm, p, s) : launch_tc<128, kDirect, kCtas, kARes>(ta, tb, tcm, p, s));
 }
