@@ -7,7 +7,7 @@ namespace smk {
 int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out, int64_t rows,
                   int D, float eps, cudaStream_t s);
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
-                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s);
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr);
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
                   int64_t rows, int D, cudaStream_t s);
@@ -44,6 +44,9 @@ int assemble_tokens(const float* patch_out, const float* cls, const float* pos, 
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
 int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s1, int row_bytes1, int64_t rows, int period, cudaStream_t s);
+// bf16 tensor-core mode, scale factor 4 (smk_mask_mma.cu): logits on mma.sync with the 3-term split, then upsample + sigmoid
+int mask_head_mma(const __nv_bfloat16* q3, int64_t Rall, const __nv_bfloat16* tok_hi, const __nv_bfloat16* tok_lo, float* logits_lowres,
+                  float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D, int hp, int wp, cudaStream_t s);
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D,
               int hp, int wp, int sf, cudaStream_t s);
 int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s);

@@ -145,7 +145,8 @@ struct smk_model {
   float* X;                       // [B*N, D] residual stream (fp32)
   void *Xn, *QKV, *AO, *Hm, *KV;  // activations in the mode's GEMM input type
   float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
-  __nv_bfloat16* tokb;            // bf16 copy (bf16 mode)
+  __nv_bfloat16 *tokb, *tokl;     // bf16 copy and its rounding residue (bf16 mode)
+  float* mlog;                    // [B, L*nq, hw] mask logits at patch resolution (bf16 mode)
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
   std::vector<Dec3> dec3;         // bf16 mode only
   __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *a3c, *a3f, *a3q, *dqk_b, *dv_b, *cq_b;
@@ -198,6 +199,8 @@ static void plan(smk_model& m, Plan& pl) {
   m.KV = pl.take<uint8_t>(M * L * 2 * D * esz);
   m.tok32 = pl.take<float>(M * D);
   m.tokb = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
+  m.tokl = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
+  m.mlog = bf ? pl.take<float>(B * L * nq * (N - 1)) : nullptr;
   const int64_t R = B * nq;
   m.tgt = pl.take<float>(R * D);
   m.qin = pl.take<float>(R * D);
@@ -493,7 +496,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, 0, 0, nullptr, s));
       SMK_PROPAGATE(gemm_bf16_tc(Hm, F, wb + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
     }
-    SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tokb, m->tok32, nullptr, M, D, 1e-6f, s));
+    SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tokb, m->tok32, nullptr, M, D, 1e-6f, s, m->tokl));
     SMK_PROPAGATE(gemm_bf16_tc(m->tokb, D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
   } else {
     float *Xn = (float*)m->Xn, *QKV = (float*)m->QKV, *AO = (float*)m->AO, *Hm = (float*)m->Hm;
@@ -639,8 +642,12 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
 
   // ---- heads ----------------------------------------------------------------------------------------
   const int Lout = all_layers ? L : 1, layer0 = all_layers ? 0 : L - 1;
-  if (mask_pred)
-    SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
+  if (mask_pred) {
+    if (bf && c.scale_factor == 4)
+      SMK_PROPAGATE(mask_head_mma(m->a3q, R, m->tokb, m->tokl, m->mlog, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, s));
+    else
+      SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
+  }
   if (objectness) {
     const float* qsrc = m->queries + (int64_t)layer0 * R * D;
     const int rows = Lout * R;

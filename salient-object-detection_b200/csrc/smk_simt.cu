@@ -15,7 +15,7 @@ template <typename TOut, int kChunks>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
                  const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
-                 int64_t rows, int D, float eps) {
+                 TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */, int64_t rows, int D, float eps) {
   pdl_wait();
   pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -67,6 +67,14 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         reinterpret_cast<uint2*>(y + row * D)[i] = pk;
+        if (y_lo) {
+          const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+          __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), r1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+          uint2 pr;
+          pr.x = *reinterpret_cast<uint32_t*>(&r0);
+          pr.y = *reinterpret_cast<uint32_t*>(&r1);
+          reinterpret_cast<uint2*>(y_lo + row * D)[i] = pr;
+        }
       }
     }
   }
@@ -74,14 +82,14 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
 
 template <typename TOut>
 static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
-                            float* sum_out, int64_t rows, int D, float eps, cudaStream_t s) {
+                            float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s) {
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, rows, D, eps)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -91,11 +99,11 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
 
 int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out,
                   int64_t rows, int D, float eps, cudaStream_t s) {
-  return launch_layernorm<float>(x, res, gamma, beta, y, nullptr, sum_out, rows, D, eps, s);
+  return launch_layernorm<float>(x, res, gamma, beta, y, nullptr, sum_out, nullptr, rows, D, eps, s);
 }
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
-                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s) {
-  return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, rows, D, eps, s);
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo) {
+  return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -931,7 +939,7 @@ extern "C" int smk_gemm_f32(const float* A, int64_t lda, const float* W, const f
 extern "C" int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
                              int out_bf16, void* stream) {
   SMK_REQUIRE(x && gamma && beta && y && rows >= 0, "smk_layernorm: bad arguments");
-  if (out_bf16) return layernorm_bf16(x, nullptr, gamma, beta, (__nv_bfloat16*)y, nullptr, nullptr, rows, D, eps, (cudaStream_t)stream);
+  if (out_bf16) return layernorm_bf16(x, nullptr, gamma, beta, (__nv_bfloat16*)y, nullptr, nullptr, rows, D, eps, (cudaStream_t)stream, nullptr);
   return layernorm_f32(x, nullptr, gamma, beta, (float*)y, nullptr, rows, D, eps, (cudaStream_t)stream);
 }
 

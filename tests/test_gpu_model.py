@@ -237,3 +237,29 @@ def test_rejects_wrong_inputs():
         model(torch.zeros(1, 1, 224, 224, device=DEV))
     with pytest.raises(S.SmkError):
         S.eval_batch(torch.zeros(1, 20, 56, 56, device=DEV), torch.zeros(1, 20, device=DEV), torch.zeros(1, 1, 300, 300, device=DEV))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_small_patch8_shipped_config(mode):
+    """The configuration the reference ships (configs/*.yaml: ViT-S/8, scale_factor 2): 785 tokens per image, so
+    encoder attention and decoder cross-attention run on the online-softmax kernel; 28x28 patch grid, masks at 56x56."""
+    B, H, W = 1, 224, 224
+    cfg = O.make_config(n_queries=20, patch_size=8, scale_factor=2, pos_grid=28)
+    sd = O.synth_state_dict(cfg, seed=3)
+    model = S.SelfMaskB200(n_queries=20, patch_size=8, scale_factor=2, mode=mode, max_batch=B).to(DEV)
+    model.load_state_dict(sd)
+    x = O.normalize_images(O.synth_images_u8(B, H, W, seed=55))
+    ref = _oracle(sd, x, cfg)
+    out, logits = forward_with_logits(model, x.to(DEV))
+    assert out["mask_pred"].shape == ref["mask_pred"].shape == (B, 6, 20, 56, 56)
+    agree = binarised_iou_agreement(out["mask_pred"][:, -1].cpu().numpy(), ref["mask_pred"][:, -1].numpy())
+    stats = {"logits_maxabs": float((logits.cpu() - ref["mask_logits"]).abs().max()),
+             "prob_maxabs": float((out["mask_pred"].cpu() - ref["mask_pred"]).abs().max()),
+             "objectness_maxabs": float((out["objectness"].cpu() - ref["objectness"]).abs().max()),
+             "iou_agreement_mean": float(agree.mean()), "iou_agreement_min": float(agree.min())}
+    _report(f"{mode}_vits8_sf2_nq20_224x224_B1", stats)
+    if mode == "fp32":
+        assert stats["logits_maxabs"] <= 2e-4, stats
+        assert stats["iou_agreement_min"] >= 0.999, stats
+    else:
+        assert stats["iou_agreement_mean"] >= 0.98, stats
