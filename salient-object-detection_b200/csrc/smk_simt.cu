@@ -11,6 +11,8 @@ namespace smk {
 // One warp per row; the row lives in registers (D <= 1024, D % 128 == 0); optional residual input and
 // optional second (fp32) output so that bf16-mode callers get both copies in one pass.
 // ------------------------------------------------------------------------------------------------
+constexpr int LN_ROWS = 2;   // rows per warp, all loads issued before the first reduction (bytes in flight: the kernel is HBM-bound)
+
 template <typename TOut, int kChunks>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
@@ -18,62 +20,75 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
                  TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */, int64_t rows, int D, float eps) {
   pdl_wait();
   pdl_trigger();
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_ROWS;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-  const float4* rr = res ? reinterpret_cast<const float4*>(res + row * D) : nullptr;
-  float4 v[kChunks];
-  float s = 0.f;
+  float4 v[LN_ROWS][kChunks];
 #pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    v[c] = xr[lane + 32 * c];
-    if (rr) {
-      float4 r = rr[lane + 32 * c];
-      v[c].x += r.x; v[c].y += r.y; v[c].z += r.z; v[c].w += r.w;
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const int64_t row = row0 + r;
+    if (row < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) v[r][c] = xr[lane + 32 * c];
+      if (res) {
+        const float4* rr = reinterpret_cast<const float4*>(res + row * D);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const float4 q = rr[lane + 32 * c];
+          v[r][c].x += q.x; v[r][c].y += q.y; v[r][c].z += q.z; v[r][c].w += q.w;
+        }
+      }
     }
-    s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
   }
-  if (sum_out) {   // the pre-norm residual stream (x + res), needed by post-norm callers
-    float4* so = reinterpret_cast<float4*>(sum_out + row * D);
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) so[lane + 32 * c] = v[c];
-  }
-  const float mean = warp_sum(s) / (float)D;
-  float ss = 0.f;
-#pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
-    ss += (a * a + b * b) + (cc * cc + d * d);
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)D + eps);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    const int i = lane + 32 * c;
-    float4 g = g4[i], b = b4[i], o;
-    o.x = (v[c].x - mean) * rstd * g.x + b.x;
-    o.y = (v[c].y - mean) * rstd * g.y + b.y;
-    o.z = (v[c].z - mean) * rstd * g.z + b.z;
-    o.w = (v[c].w - mean) * rstd * g.w + b.w;
-    if (y32) reinterpret_cast<float4*>(y32 + row * D)[i] = o;
-    if (y) {
-      if constexpr (sizeof(TOut) == 4) {
-        reinterpret_cast<float4*>(y + row * D)[i] = o;
-      } else {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(y + row * D)[i] = pk;
-        if (y_lo) {
-          const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
-          __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), r1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
-          uint2 pr;
-          pr.x = *reinterpret_cast<uint32_t*>(&r0);
-          pr.y = *reinterpret_cast<uint32_t*>(&r1);
-          reinterpret_cast<uint2*>(y_lo + row * D)[i] = pr;
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= rows) break;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) s += (v[r][c].x + v[r][c].y) + (v[r][c].z + v[r][c].w);
+    if (sum_out) {   // the pre-norm residual stream (x + res), needed by post-norm callers
+      float4* so = reinterpret_cast<float4*>(sum_out + row * D);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) so[lane + 32 * c] = v[r][c];
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      float a = v[r][c].x - mean, b = v[r][c].y - mean, cc = v[r][c].z - mean, d = v[r][c].w - mean;
+      ss += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)D + eps);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int i = lane + 32 * c;
+      float4 g = g4[i], b = b4[i], o;
+      o.x = (v[r][c].x - mean) * rstd * g.x + b.x;
+      o.y = (v[r][c].y - mean) * rstd * g.y + b.y;
+      o.z = (v[r][c].z - mean) * rstd * g.z + b.z;
+      o.w = (v[r][c].w - mean) * rstd * g.w + b.w;
+      if (y32) reinterpret_cast<float4*>(y32 + row * D)[i] = o;
+      if (y) {
+        if constexpr (sizeof(TOut) == 4) {
+          reinterpret_cast<float4*>(y + row * D)[i] = o;
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(y + row * D)[i] = pk;
+          if (y_lo) {
+            const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+            __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), r1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+            uint2 pr;
+            pr.x = *reinterpret_cast<uint32_t*>(&r0);
+            pr.y = *reinterpret_cast<uint32_t*>(&r1);
+            reinterpret_cast<uint2*>(y_lo + row * D)[i] = pr;
+          }
         }
       }
     }
@@ -85,7 +100,7 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
                             float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s) {
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const unsigned grid = (unsigned)((rows + 8 * LN_ROWS - 1) / (8 * LN_ROWS));
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
