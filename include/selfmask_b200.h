@@ -198,6 +198,12 @@ int smk_attention_fa(const void* q, const void* q_lo, int64_t ldq, const void* k
                      const void* v_lo, int64_t ldv, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode,
                      int B, int Lq, int Lk, int heads, float scale, void* stream);
 
+/* Residual GEMM with the following LayerNorm fused into the epilogue (tcgen05, N must be 384):
+ * X[M,N] (fp32, in place) += A[M,K] (bf16, lda) · W[N,K]^T (bf16) + bias;  Xn[M,N] (bf16) = LayerNorm(X; gamma, beta, eps).
+ * Serves attn.proj + norm2 and mlp.fc2 + the next block's norm1 (vision_transformer.py:131,165-170). */
+int smk_gemm_ln(const void* A, int64_t lda, const void* W, const float* bias, float* X, const float* gamma, const float* beta,
+                void* Xn, int M, int N, int K, float eps, void* stream);
+
 /* 3-term bf16 split along K (bf16x3): x fp32 [rows,K] → out bf16 [rows,3K]; activations [hi|hi|lo], weights [hi|lo|hi];
  * gemm_bf16(split_act(A), split_weight(W)) with K' = 3K ≈ fp32 GEMM */
 int smk_split3(const float* x, int64_t rows, int K, void* out, int is_weight, void* stream);

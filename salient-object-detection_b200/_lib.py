@@ -58,6 +58,7 @@ SIGNATURES = {
     "smk_attention_fa": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_debug_attn_trace": (_I, [_P]),
     "smk_debug_gemm_trace": (_I, [_P]),
+    "smk_gemm_ln": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "smk_split3": (_I, [_P, _L, _I, _P, _I, _P]),
     "smk_cast_bf16": (_I, [_P, _P, _L, _P]),
 }

@@ -18,6 +18,9 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
 template <typename T, typename TK>
 int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, int dh, int Lq, int Lk, int64_t q_bs, int64_t ldq,
               int64_t k_bs, int64_t ldk, int64_t v_bs, int64_t ldv, int64_t o_bs, int64_t ldo, float scale, cudaStream_t s);
+// residual GEMM + the following LayerNorm in one kernel (smk_gemm_ln.cu): X += A·W^T + bias (fp32), Xn = LN(X) (bf16); N == 384
+int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, const float* bias, float* X, const float* gamma,
+               const float* beta, __nv_bfloat16* Xn, int M, int N, int K, float eps, cudaStream_t s);
 int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, float scale, cudaStream_t s);
 // general form: q [B*Lq, ldq] / k / v [.., ld] bf16 matrices (head h at columns [h*64, h*64+64) from the given base pointer);
 // image b's queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0.  Lq <= 128, Lk <= 256.

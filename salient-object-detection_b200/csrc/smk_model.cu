@@ -481,9 +481,15 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     else SMK_PROPAGATE((im2col<float, __nv_bfloat16>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s)));
     SMK_PROPAGATE(gemm_bf16_tc(Hm, Kpe, wb + m->o_pew, Kpe, w + m->o_peb, m->X, D, B * hw, D, Kpe, SMK_EPI_NONE, 1, hw, m->pos, s));
     SMK_PROPAGATE(assemble_tokens(nullptr, w + m->o_cls, m->pos, m->X, B, hw, D, true, s));
+    // SMK_FUSE_LN=1: LayerNorms ride in the epilogue of the residual GEMM in front of them (smk_gemm_ln.cu).  Off by default:
+    // measured on B200 the fused kernel is bound by the HBM burst of its epilogue (fp32 residual tile in + out + bf16 out,
+    // 4.5 TB/s with every CTA in the same phase) and ties (proj + norm2: 57 vs 57 us) or loses (fc2 + norm1: 112 vs 94 us)
+    // against the two-kernel form; profiles/r01_gemm_ln_fusion.md.
+    static const bool fuse_env = getenv("SMK_FUSE_LN") && atoi(getenv("SMK_FUSE_LN")) != 0;
+    const bool fuse_ln = fuse_env && D == 384;
     for (int i = 0; i < c.depth; ++i) {
       const BlockW& b = m->blk[i];
-      SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
+      if (i == 0 || !fuse_ln) SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.qkvw, D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));
       if (N <= 256) {
         SMK_PROPAGATE(attention_tc(QKV, AO, B, N, c.heads, scale, s));
@@ -491,10 +497,19 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         SMK_PROPAGATE(attention_fa(QKV, nullptr, 3 * D, QKV + D, nullptr, 3 * D, QKV + 2 * D, nullptr, 3 * D, N, N, 0, AO, D, 0, B, N, N, c.heads,
                                    scale, s));
       }
-      SMK_PROPAGATE(gemm_bf16_tc(AO, D, wb + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
-      SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
+      if (fuse_ln) {
+        SMK_PROPAGATE(gemm_ln_tc(AO, D, wb + b.pw, w + b.pb, m->X, w + b.n2w, w + b.n2b, Xn, M, D, D, 1e-6f, s));
+      } else {
+        SMK_PROPAGATE(gemm_bf16_tc(AO, D, wb + b.pw, D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+        SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, nullptr, M, D, 1e-6f, s));
+      }
       SMK_PROPAGATE(gemm_bf16_tc(Xn, D, wb + b.f1w, D, w + b.f1b, Hm, F, M, F, D, SMK_EPI_GELU, 0, 0, nullptr, s));
-      SMK_PROPAGATE(gemm_bf16_tc(Hm, F, wb + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+      if (fuse_ln && i + 1 < c.depth) {      // ... + the next block's norm1
+        const BlockW& nb = m->blk[i + 1];
+        SMK_PROPAGATE(gemm_ln_tc(Hm, F, wb + b.f2w, w + b.f2b, m->X, w + nb.n1w, w + nb.n1b, Xn, M, D, F, 1e-6f, s));
+      } else {
+        SMK_PROPAGATE(gemm_bf16_tc(Hm, F, wb + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
+      }
     }
     SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tokb, m->tok32, nullptr, M, D, 1e-6f, s, m->tokl));
     SMK_PROPAGATE(gemm_bf16_tc(m->tokb, D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s));

@@ -425,3 +425,22 @@ def test_attention_fa_matches_torch(Lq, Lk, split, out_mode):
         assert err <= (3e-4 if out_mode == 2 else 5e-5), err      # 3-term products: fp32-like; the split output keeps ~16 bits
     else:
         assert err <= (0.03 if out_mode == 1 else 0.05), err
+
+
+@pytest.mark.parametrize("M_,K", [(300, 384), (50432, 384), (19000, 1536), (128, 64)])
+def test_gemm_layernorm_fused_matches_torch(M_, K):
+    """smk_gemm_ln: X += A·W^T + bias (fp32 residual stream, in place) and Xn = LayerNorm(X) in bf16 from the same tile."""
+    torch.manual_seed(31)
+    N = 384
+    A = torch.randn(M_, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    bias, gamma, beta = torch.randn(N, device=DEV), 1 + 0.1 * torch.randn(N, device=DEV), 0.1 * torch.randn(N, device=DEV)
+    X0 = torch.randn(M_, N, device=DEV) * 2 + 0.5
+    X = X0.clone()
+    Xn = torch.full((M_, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    check(lib().smk_gemm_ln(ptr(A), K, ptr(W), ptr(bias), ptr(X), ptr(gamma), ptr(beta), ptr(Xn), M_, N, K, 1e-6, stream_ptr()), "gemm_ln")
+    torch.cuda.synchronize()
+    ref_x = X0 + A.float() @ W.float().t() + bias
+    assert (X - ref_x).abs().max().item() <= 2e-3
+    ref_n = torch.nn.functional.layer_norm(X, (N,), gamma, beta, 1e-6)       # LayerNorm of the kernel's own fp32 output
+    assert (Xn.float() - ref_n).abs().max().item() <= 0.02 * max(1.0, ref_n.abs().max().item())
