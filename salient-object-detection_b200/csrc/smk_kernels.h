@@ -6,6 +6,7 @@ namespace smk {
 
 int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out, int64_t rows,
                   int D, float eps, cudaStream_t s);
+int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int64_t rows, int D, float eps, cudaStream_t s);
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
                    float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr);
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,

@@ -150,6 +150,7 @@ struct smk_model {
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
   std::vector<Dec3> dec3;         // bf16 mode only
   __nv_bfloat16 *f0w3, *f1w3, *a3a, *a3b, *a3c, *a3f, *a3q, *dqk_b, *dv_b, *cq_b;
+  __nv_bfloat16* x3qkv;
   float* debug_logits;
   int last_B;
   // decoder state after layer 0's self-attention block (image-independent: tgt = 0), filled by the first forward pass
@@ -196,7 +197,7 @@ static void plan(smk_model& m, Plan& pl) {
   m.AO = pl.take<uint8_t>(x3_mode(m) ? M * 3 * D * 2 : M * D * esz);            // bf16x3: split attention output [M, 3D] bf16
   // doubles as the im2col buffer (3*P*P <= 2*mlp_dim); bf16x3: the split GELU(fc1) output [M, 3F] bf16
   m.Hm = pl.take<uint8_t>(x3_mode(m) ? M * 3 * (int64_t)c.mlp_dim * 2 : M * (int64_t)c.mlp_dim * esz);
-  m.KV = pl.take<uint8_t>(M * L * 2 * D * esz);
+  m.KV = pl.take<uint8_t>(M * L * 2 * D * (x3 ? 6 : esz));     // bf16x3: split [hi | hi | lo] rows of 3·L·2D bf16
   m.tok32 = pl.take<float>(M * D);
   m.tokb = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
   m.tokl = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
@@ -207,6 +208,7 @@ static void plan(smk_model& m, Plan& pl) {
   m.dqk = pl.take<float>(R * 2 * D);
   m.dv = pl.take<float>(R * D);
   m.dao = pl.take<float>(R * D);
+  m.x3qkv = x3 ? pl.take<__nv_bfloat16>(R * 9 * D) : nullptr;     // bf16x3 decoder: split q|k [R, 3·2D] and split v / cross q [R, 3D]
   m.t2 = pl.take<float>(R * D);
   m.ffh = pl.take<float>(R * c.dec_ffn);
   m.queries = pl.take<float>(L * R * D);
@@ -474,6 +476,13 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     return gemm_bf16_tc(m->A3, 3 * (int64_t)K_, w3, 3 * (int64_t)K_, bias, Cc, ldc, M_, N_, 3 * K_, epi, 1, 0, nullptr, s);
   };
 
+  // bf16x3 mode: fp32 A → split GEMM whose epilogue writes the bf16x3 split [hi | hi | lo] of the result (ldc >= 3·N_ bf16)
+  auto gemm_x3_split = [m, w, s](const float* A, int64_t lda, const float* Wp, const float* bias, __nv_bfloat16* C3, int64_t ldc, int M_, int N_,
+                                 int K_) -> int {
+    SMK_PROPAGATE(split3_act(A, lda, nullptr, 0, m->A3, nullptr, M_, K_, s));
+    return gemm_bf16_tc(m->A3, 3 * (int64_t)K_, m->w3 + 3 * (Wp - w), 3 * (int64_t)K_, bias, C3, ldc, M_, N_, 3 * K_, SMK_EPI_NONE, 2, 0, nullptr, s);
+  };
+
   // ---- encoder ------------------------------------------------------------------------------------
   if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
@@ -525,14 +534,12 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       __nv_bfloat16 *Q3 = (__nv_bfloat16*)m->QKV, *AO3 = (__nv_bfloat16*)m->AO, *H3 = (__nv_bfloat16*)m->Hm;
       const __nv_bfloat16* w3 = m->w3;
       const int64_t lo = 2 * 3 * (int64_t)D;      // column of the lo part in the split q|k|v rows
-      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n1w, w + b.n1b, Xn, nullptr, M, D, 1e-6f, s));
-      SMK_PROPAGATE(split3_act(Xn, D, nullptr, 0, m->A3, nullptr, M, D, s));
+      SMK_PROPAGATE(layernorm_split3(m->X, w + b.n1w, w + b.n1b, m->A3, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_bf16_tc(m->A3, 3 * D, w3 + 3 * b.qkvw, 3 * D, w + b.qkvb, Q3, 9 * D, M, 3 * D, 3 * D, SMK_EPI_NONE, 2, 0, nullptr, s));
       SMK_PROPAGATE(attention_fa(Q3, Q3 + lo, 9 * D, Q3 + D, Q3 + lo + D, 9 * D, Q3 + 2 * D, Q3 + lo + 2 * D, 9 * D, N, N, 0, AO3, 3 * D, 2, B, N, N,
                                  c.heads, scale, s));
       SMK_PROPAGATE(gemm_bf16_tc(AO3, 3 * D, w3 + 3 * b.pw, 3 * D, w + b.pb, m->X, D, M, D, 3 * D, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
-      SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + b.n2w, w + b.n2b, Xn, nullptr, M, D, 1e-6f, s));
-      SMK_PROPAGATE(split3_act(Xn, D, nullptr, 0, m->A3, nullptr, M, D, s));
+      SMK_PROPAGATE(layernorm_split3(m->X, w + b.n2w, w + b.n2b, m->A3, M, D, 1e-6f, s));
       SMK_PROPAGATE(gemm_bf16_tc(m->A3, 3 * D, w3 + 3 * b.f1w, 3 * D, w + b.f1b, H3, 3 * F, M, F, 3 * D, SMK_EPI_GELU, 2, 0, nullptr, s));
       SMK_PROPAGATE(gemm_bf16_tc(H3, 3 * F, w3 + 3 * b.f2w, 3 * F, w + b.f2b, m->X, D, M, D, 3 * F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
     }
@@ -548,7 +555,12 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       SMK_PROPAGATE(gemm_hp(Hm, F, w + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, s));
     }
     SMK_PROPAGATE(layernorm_f32(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tok32, nullptr, M, D, 1e-6f, s));
-    SMK_PROPAGATE(gemm_hp(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
+    if (x3) {   // memory K/V as split rows [hi | hi | lo]: the decoder's cross-attention runs on the split tensor-core kernel
+      SMK_PROPAGATE(split3_act(m->tok32, D, nullptr, 0, m->A3, nullptr, M, D, s));
+      SMK_PROPAGATE(gemm_bf16_tc(m->A3, 3 * D, m->kvw3, 3 * D, m->kvb, m->KV, (int64_t)3 * L * 2 * D, M, L * 2 * D, 3 * D, SMK_EPI_NONE, 2, 0, nullptr, s));
+    } else {
+      SMK_PROPAGATE(gemm_hp(m->tok32, D, m->kvw32, D, m->kvb, (float*)m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, s));
+    }
   }
 
   // ---- decoder (transformer_decoder.py:260-297, post-norm) ---------------------------------------------------
@@ -632,18 +644,35 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     const DecW& d = m->dec[l];
     // self-attention: q = k = tgt + query_pos, v = tgt
     SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
+    if (x3) {
+      // projections write the bf16x3 split of q|k and v; attention runs on tensor cores with 3-term products (smk_attn_fa.cu)
+      __nv_bfloat16 *qk3 = m->x3qkv, *v3 = m->x3qkv + (int64_t)R * 6 * D;
+      SMK_PROPAGATE(gemm_x3_split(m->qin, D, w + d.saw, w + d.sab, qk3, 6 * D, R, 2 * D, D));
+      SMK_PROPAGATE(gemm_x3_split(m->tgt, D, w + d.saw + (int64_t)2 * D * D, w + d.sab + 2 * D, v3, 3 * D, R, D, D));
+      SMK_PROPAGATE(attention_fa(qk3, qk3 + 4 * D, 6 * D, qk3 + D, qk3 + 5 * D, 6 * D, v3, v3 + 2 * D, 3 * D, nq, nq, 0, m->dao, D, 1, B, nq, nq,
+                                 c.heads, scale, s));
+    } else {
     SMK_PROPAGATE(gemm_hp(m->qin, D, w + d.saw, D, w + d.sab, m->dqk, 2 * D, R, 2 * D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(gemm_hp(m->tgt, D, w + d.saw + (int64_t)2 * D * D, D, w + d.sab + 2 * D, m->dv, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE((attention<float, float>(m->dqk, m->dqk + D, m->dv, m->dao, B, c.heads, 64, nq, nq, (int64_t)nq * 2 * D, 2 * D,
                                            (int64_t)nq * 2 * D, 2 * D, (int64_t)nq * D, D, (int64_t)nq * D, D, scale, s)));
+    }
     SMK_PROPAGATE(gemm_hp(m->dao, D, w + d.saow, D, w + d.saob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n1w, w + d.n1b, m->tgt, nullptr, R, D, 1e-5f, s));
     // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
     SMK_PROPAGATE(add_rows(m->tgt, qpos, m->qin, R, D, nq, s));
+    if (x3) {
+      __nv_bfloat16* cq3 = m->x3qkv + (int64_t)R * 6 * D;
+      SMK_PROPAGATE(gemm_x3_split(m->qin, D, w + d.caw, w + d.cab, cq3, 3 * D, R, D, D));
+      const __nv_bfloat16* kh = (const __nv_bfloat16*)m->KV + (int64_t)l * 2 * D;      // hi part of layer l's keys; lo part 2·ldkv columns further
+      SMK_PROPAGATE(attention_fa(cq3, cq3 + 2 * D, 3 * D, kh, kh + 2 * ldkv, 3 * ldkv, kh + D, kh + 2 * ldkv + D, 3 * ldkv, nq, N, 1, m->dao, D, 1, B,
+                                 nq, hw, c.heads, scale, s));
+    } else {
     SMK_PROPAGATE(gemm_hp(m->qin, D, w + d.caw, D, w + d.cab, m->dqk, D, R, D, D, SMK_EPI_NONE, s));
     const float* kv = (const float*)m->KV + ldkv + (int64_t)l * 2 * D;
     SMK_PROPAGATE((attention<float, float>(m->dqk, kv, kv + D, m->dao, B, c.heads, 64, nq, hw, (int64_t)nq * D, D, (int64_t)N * ldkv, ldkv,
                                            (int64_t)N * ldkv, ldkv, (int64_t)nq * D, D, scale, s)));
+    }
     SMK_PROPAGATE(gemm_hp(m->dao, D, w + d.caow, D, w + d.caob, m->t2, D, R, D, D, SMK_EPI_NONE, s));
     SMK_PROPAGATE(layernorm_f32(m->tgt, m->t2, w + d.n2w, w + d.n2b, m->tgt, nullptr, R, D, 1e-5f, s));
     // FFN

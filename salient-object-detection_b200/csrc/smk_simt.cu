@@ -17,7 +17,10 @@ template <typename TOut, int kChunks>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
                  const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
-                 TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */, int64_t rows, int D, float eps) {
+                 TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */,
+                 TOut* __restrict__ y_dup /* bf16 only: second copy of y; (y, y_dup, y_lo) at columns 0, D, 2D of rows of ldy = 3D
+                                             elements form the bf16x3 split [hi | hi | lo] a split GEMM consumes */,
+                 int64_t ldy, int64_t rows, int D, float eps) {
   pdl_wait();
   pdl_trigger();
   const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_ROWS;
@@ -74,20 +77,21 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
       if (y32) reinterpret_cast<float4*>(y32 + row * D)[i] = o;
       if (y) {
         if constexpr (sizeof(TOut) == 4) {
-          reinterpret_cast<float4*>(y + row * D)[i] = o;
+          reinterpret_cast<float4*>(y + row * ldy)[i] = o;
         } else {
           __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&lo);
           pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          reinterpret_cast<uint2*>(y + row * D)[i] = pk;
+          reinterpret_cast<uint2*>(y + row * ldy)[i] = pk;
+          if (y_dup) reinterpret_cast<uint2*>(y_dup + row * ldy)[i] = pk;
           if (y_lo) {
             const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
             __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), r1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
             uint2 pr;
             pr.x = *reinterpret_cast<uint32_t*>(&r0);
             pr.y = *reinterpret_cast<uint32_t*>(&r1);
-            reinterpret_cast<uint2*>(y_lo + row * D)[i] = pr;
+            reinterpret_cast<uint2*>(y_lo + row * ldy)[i] = pr;
           }
         }
       }
@@ -97,14 +101,15 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
 
 template <typename TOut>
 static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
-                            float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s) {
+                            float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s, TOut* y_dup = nullptr, int64_t ldy = 0) {
+  if (ldy == 0) ldy = D;
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 8 * LN_ROWS - 1) / (8 * LN_ROWS));
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, ldy, rows, D, eps)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -119,6 +124,12 @@ int layernorm_f32(const float* x, const float* res, const float* gamma, const fl
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
                    float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo) {
   return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps, s);
+}
+
+// LayerNorm whose output is the bf16x3 split [hi | hi | lo] (rows of 3D bf16) of the normalised row: the A operand of a split
+// GEMM, without the fp32 round trip through a separate split kernel (bf16x3 mode encoder).
+int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int64_t rows, int D, float eps, cudaStream_t s) {
+  return launch_layernorm<__nv_bfloat16>(x, nullptr, gamma, beta, out3, nullptr, nullptr, out3 + 2 * D, rows, D, eps, s, out3 + D, 3 * (int64_t)D);
 }
 
 // ------------------------------------------------------------------------------------------------
