@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--nq", type=int, default=20)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the extra bf16x3-mode figure")
     ap.add_argument("--cpu-sample", type=int, default=48, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run exactly ONE step between cudaProfilerStart/Stop and exit "
@@ -287,6 +288,33 @@ def main():
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "sanity": {"iou": res["iou"], "f_max": res["f_max"], "e2e_iou": e2e_res["iou"]}}
+        if world == 1 and args.mode == "bf16" and not args.no_parity_mode:
+            # the same step in the bf16x3 numeric mode (every GEMM as a 3-term bf16 split on tcgen05, split attention): the mode
+            # that meets north_star's bf16 tolerance on random-init weights (logits max-abs 2e-3); reported next to the headline
+            try:
+                del ev
+                m3 = S.SelfMaskB200(n_queries=args.nq, mode="bf16x3", max_batch=B, return_intermediate=True).to(dev)
+                m3.load_state_dict(Y.synth_state_dict(m3.table(), seed=0))
+
+                def step3():
+                    o3 = m3(x)
+                    S.eval_batch(o3["mask_pred"], o3["objectness"], g, up=4, out=rec)
+                for _ in range(3):
+                    step3()
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(5):
+                    step3()
+                p1.record()
+                torch.cuda.synchronize()
+                ms3 = p0.elapsed_time(p1) / 5
+                line["parity_mode"] = {"numeric_mode": "bf16x3", "value": B / (ms3 / 1e3), "unit": "images/s", "ms_per_step": ms3, "steps": 5,
+                                       "note": "same workload, device-resident inputs; meets the 2e-2 logit / 99.9 % IoU-agreement criteria "
+                                               "(tests/test_gpu_model.py::test_bf16x3_mode_meets_the_north_star_tolerance)"}
+                del m3
+            except Exception as e:      # never lose the headline line over the extra figure
+                line["parity_mode"] = {"numeric_mode": "bf16x3", "error": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             ips, cores, sec = cpu_reference_images_per_s(args.cpu_sample, args.size, args.nq, batch=8)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",

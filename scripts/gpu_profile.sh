@@ -1,9 +1,10 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list of exactly one bench step + full-set captures of one launch of every
 # distinct kernel / shape of the step.  `bench.py --ncu-step` brackets ONE step with cudaProfilerStart/Stop, so with
-# --profile-from-start off the launch indices are the step's own (bf16 mode, 224x224, nq 20):
+# --profile-from-start off the launch indices are the step's own (bf16 mode, 224x224, nq 20, 166 launches):
 #   0 im2col, 1 patch-embed GEMM, 2 cls/pos rows, 3+7i.. encoder layer i = LN qkv attn proj LN fc1 fc2,
-#   87 final LN, 88 memory K/V GEMM, 89 split, 90+12l.. decoder layer l, 162 mask head, 163-167 objectness/features, 168-169 eval
+#   87 final LN, 88 memory K/V GEMM, 89 layer-0 state tile, 90-96 decoder layer 0 (cross-attention block + FFN),
+#   97+12(l-1).. decoder layer l >= 1, 157 mask logits, 158 mask upsample, 159-163 objectness / features, 164-165 eval
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -19,6 +20,6 @@ cap() { name=$1; skip=$2; count=$3
   echo "$name rc=$?"; }
 cap enc 10 7
 cap kv 87 2
-cap dec 102 12
-cap tail 162 8
+cap dec 97 12
+cap tail 157 9
 ls -la gpurun_out/*.ncu-rep

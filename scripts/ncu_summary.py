@@ -76,7 +76,8 @@ def traffic(paths):
     import json
     weight = {"enc": 12, "kv": 1, "dec": 6, "tail": 1}
     stage_of = [("gemm_bf16_tc", "gemm_tcgen05"), ("attn_tc", "attention_tcgen05"), ("layernorm", "layernorm"),
-                ("query_iou", "eval_metrics"), ("mask_metrics", "eval_metrics"), ("mask_head", "mask_head")]
+                ("query_iou", "eval_metrics"), ("mask_metrics", "eval_metrics"), ("mask_head", "mask_head"), ("mask_logits", "mask_head"),
+                ("mask_upsample", "mask_head"), ("attn_small", "attention_tcgen05"), ("attn_fa", "attention_tcgen05")]
     acc = collections.OrderedDict()
     for path in paths:
         tag = next((k for k in weight if f"_{k}." in path), None)
