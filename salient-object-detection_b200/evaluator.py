@@ -88,8 +88,23 @@ class Evaluator:
             assert os.path.exists(dir_dataset), f"{dir_dataset} does not exist"
         self.model, self.arch, self.dir_dataset, self.visualizer, self.debug = network, arch, dir_dataset, visualizer, debug
         self.dataset = dataset
-        self.records = None
+        self._recs = None            # per-batch device records of the last sweep
+        self._records_host = None
         self._copy_stream = None
+        self._pinned = None          # page-locked landing buffer for the finalised values (the only per-sweep read-back)
+
+    def device_records(self) -> Dict[str, torch.Tensor]:
+        """Integer / float64 records of the last sweep, in dataset order, as device tensors (what a multi-GPU caller all-reduces)."""
+        if not self._recs:
+            raise _lib.SmkError("no sweep has been evaluated yet")
+        return {k: torch.cat([getattr(r, k) for r in self._recs]) for k in ("m_counts", "m_sums", "idx", "q_counts")}
+
+    @property
+    def records(self) -> Optional[Dict[str, np.ndarray]]:
+        """The same records on the host (numpy), fetched on first access: the sweep itself only reads back the finalised values."""
+        if self._records_host is None and self._recs:
+            self._records_host = {k: v.cpu().numpy() for k, v in self.device_records().items()}
+        return self._records_host
 
     def _batches(self, dataset_name: str, batch_size: int) -> Iterable[dict]:
         if self.dataset is None:
@@ -141,9 +156,15 @@ class Evaluator:
                 vals.append(finalize_device(rec.m_counts, rec.m_sums))
             if not recs:
                 raise _lib.SmkError("empty dataset")
-            # one synchronising read-back for the whole sweep
-            self.records = {k: torch.cat([getattr(r, k) for r in recs]).cpu().numpy() for k in ("m_counts", "m_sums", "idx", "q_counts")}
-            v = values_from_device(torch.cat(vals).cpu().numpy())
+            # one synchronising read-back for the whole sweep: 8 doubles per evaluated mask, into page-locked memory
+            self._recs, self._records_host = recs, None
+            dv = torch.cat(vals)
+            if self._pinned is None or self._pinned.numel() < dv.numel():
+                self._pinned = torch.empty(dv.numel(), dtype=dv.dtype).pin_memory()
+            hv = self._pinned[:dv.numel()].view(dv.shape)
+            hv.copy_(dv, non_blocking=True)
+            compute.synchronize()
+            v = values_from_device(hv.numpy().copy())
         res = {k: running_mean(v[k][:, 0]) for k in METRIC_KEYS}
         res.update({k + "_ub": running_mean(v[k][:, 1]) for k in METRIC_KEYS})
         if dir_ckpt is not None:
