@@ -8,3 +8,4 @@ from .metrics import (AverageMeter, FMeasure, SMeasure, compute_iou, compute_mae
 from .model import SelfMaskB200, get_model, weight_table  # noqa: F401
 from .parallel import allreduce_records, shard_range  # noqa: F401
 from . import synthetic  # noqa: F401
+from .datasets import SaliencyFolder, get_dataset  # noqa: F401

@@ -263,3 +263,28 @@ def test_vit_small_patch8_shipped_config(mode):
         assert stats["iou_agreement_min"] >= 0.999, stats
     else:
         assert stats["iou_agreement_mean"] >= 0.98, stats
+
+
+def test_evaluator_over_directory_reader(tmp_path):
+    """SaliencyFolder (DUTS-TE layout, uint8 batches) → Evaluator: same 14 averages as evaluating the same batches directly, and the
+    reference's metrics_<dataset>.txt is written."""
+    from PIL import Image
+    d_img, d_gt = tmp_path / "DUTS-TE-Image", tmp_path / "DUTS-TE-Mask"
+    d_img.mkdir()
+    d_gt.mkdir()
+    rng = np.random.default_rng(9)
+    for i in range(5):
+        Image.fromarray(rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)).save(d_img / f"{i}.jpg")
+        gt = np.zeros((96, 128), np.uint8)
+        gt[20 + i: 70, 30: 90 + i] = 255
+        Image.fromarray(gt).save(d_gt / f"{i}.png")
+    model, sd, cfg = make_model(nq=20, mode="bf16", max_batch=2)
+    ds = S.get_dataset(str(tmp_path), "duts", img_size=224, batch_size=2)
+    ev = S.Evaluator(network=model, dir_dataset=str(tmp_path), dataset=ds)
+    res = ev(dataset_name="duts", dir_ckpt=str(tmp_path / "out"), batch_size=2, device=DEV)
+    assert os.path.exists(tmp_path / "out" / "metrics_duts.txt") and len(res) == 14
+    ev2 = S.Evaluator(network=model, dataset=list(ds))
+    res2 = ev2(dataset_name="duts", dir_ckpt=None, batch_size=2, device=DEV)
+    for k, v in res.items():
+        assert (np.isnan(v) and np.isnan(res2[k])) or v == res2[k], k
+    assert ev.records["m_counts"].shape[0] == 5

@@ -208,3 +208,33 @@ def test_x4_bilinear_cell_shortcut_premise():
             assert blend(above, lx1, ly1) > half
             for c in rng.random(64).astype(np.float32):          # constant fields never cross 0.5 from their own side
                 assert (blend(c, lx1, ly1) > half) == (c > half)
+
+
+def test_saliency_folder_reader_pairs_resizes_and_shards(tmp_path):
+    """Directory reader for the batched evaluator: the reference's DUTS-TE layout, uint8 batches, {0,1} masks, contiguous shards."""
+    from PIL import Image
+    import selfmask_b200 as S
+    d_img, d_gt = tmp_path / "DUTS-TE-Image", tmp_path / "DUTS-TE-Mask"
+    d_img.mkdir()
+    d_gt.mkdir()
+    rng = np.random.default_rng(5)
+    n = 7
+    for i in range(n):
+        h, w = int(rng.integers(40, 90)), int(rng.integers(40, 90))
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(d_img / f"im_{i:03d}.jpg")
+        gt = np.zeros((h, w), np.uint8)
+        gt[h // 4: h // 2 + i, w // 4: w // 2] = 255
+        Image.fromarray(gt).save(d_gt / f"im_{i:03d}.png")
+    ds = S.SaliencyFolder(str(tmp_path), "duts", img_size=32, batch_size=3, pin_memory=False)
+    batches = list(ds)
+    assert ds.n_images == n and len(ds) == 3 and [b["x"].shape[0] for b in batches] == [3, 3, 1]
+    for b in batches:
+        assert b["x"].dtype == torch.uint8 and b["x"].shape[1:] == (3, 32, 32)
+        assert b["m"].dtype == torch.uint8 and b["m"].shape[1:] == (1, 32, 32) and set(np.unique(b["m"].numpy())) <= {0, 1}
+        assert b["m"].sum() > 0
+    assert [f for b in batches for f in b["filename"]] == [f"im_{i:03d}.jpg" for i in range(n)]
+    # two ranks read disjoint contiguous shards that cover the set
+    names = [[f for b in S.SaliencyFolder(str(tmp_path), "duts", 32, 2, rank=r, world_size=2, pin_memory=False) for f in b["filename"]] for r in range(2)]
+    assert names[0] + names[1] == [f"im_{i:03d}.jpg" for i in range(n)] and len(names[0]) == 4
+    with pytest.raises(S.SmkError):
+        S.SaliencyFolder(str(tmp_path), "coco")
