@@ -9,7 +9,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libselfmask_b200.so")
+LIB_PATH = os.environ.get("SMK_LIB_PATH") or os.path.join(HERE, "libselfmask_b200.so")   # override: A/B runs of two builds (tuning)
 
 SMK_MODE_FP32, SMK_MODE_BF16, SMK_MODE_BF16X3 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RELU, EPI_RESIDUAL = 0, 1, 2, 4

@@ -10,20 +10,31 @@
 //               from TMEM (TS form: no shared-memory round trip for P) and V consumed as an MN-major operand from its
 //               TMA tile.  Issue order ping-pongs the two slots (PV0, next S0, PV1, next S1) so that one tile's MMAs and
 //               epilogue run under the other tile's softmax.
-//   warps 2-9   two softmax groups (one per query tile, 4 warps = the 4 TMEM lane quarters): one thread per query row,
-//               row max then exp2 in registers from tcgen05.ld, P (bf16 pairs) written back over S with tcgen05.st;
+//   warps 4-11  two softmax groups (one per query tile, 4 warps = the 4 TMEM lane quarters): one thread per query row.
+//               The TMEM read port (64 B/clk/SM) bounds this kernel, so S is read from TMEM exactly ONCE: an online
+//               softmax over 16-key units keeps every unit's P in registers as packed bf16 pairs (8 registers per unit),
+//               exponentiated against the running row maximum rounded UP to an integer (in the log2 domain), so that the
+//               final correction of an earlier unit is a multiplication by an exact power of two (HMUL2.BF16, no second
+//               rounding); the row sum is rescaled the same way.  P is then written back over S with tcgen05.st;
 //               after O_t lands: O / rowsum → shared-memory staging → TMA tile store through a 3-D {column,
 //               row-in-image, image} tensor map, which clips the rows beyond the image's last query.
-// TMEM slot t (256 columns): S in [0, nk), P packed in [0, nk/2) (P chunk c overwrites S columns that are already in
-// registers), O in [128, 192) (S columns consumed before the first P·V MMA is issued).
-// The MUFU exp2 (16/clk/SM) and the TMEM read port bound this kernel, not the tensor pipe.
+//               (A two-pass version — row max, then exp2 — read S twice: 480 instead of 272 columns per row and item,
+//               8.3 k cycles per item of which 7.7 k were the TMEM port; splitting the columns over warp pairs, 16 softmax
+//               warps, did not help for the same reason: profiles/r01_attention_tmem.md.)
+// TMEM slot t (256 columns): S in [0, nk), P packed in [0, nk/2) (written after the whole row is in registers), O in
+// [128, 192) (S columns consumed before the first P·V MMA is issued).
 #include "smk_tc.cuh"
 
 namespace smk {
 
 using namespace tc;
 
-constexpr int AT_BM = 128, AT_DH = 64, AT_THREADS = 320, AT_TMEM_COLS = 512, AT_MAXK = 256;
+constexpr int AT_BM = 128, AT_DH = 64, AT_TMEM_COLS = 512, AT_MAXK = 256;
+// three warpgroups: {TMA producer, MMA issuer, 2 idle warps} and two softmax groups.  The kernel is compiled for 168 registers
+// (three warps per scheduler); setmaxnreg then moves registers from the first warpgroup to the softmax warpgroups, whose
+// single-pass softmax keeps a whole row of P in registers.
+// (budget: 12 warps x 168 = 4 x 48 + 8 x 224 + slack; setmaxnreg.inc blocks for ever if the CTA pool cannot cover it)
+constexpr int AT_THREADS = 384, AT_REGS_CTRL = 48, AT_REGS_SOFTMAX = 224;
 constexpr int AT_Q_BYTES = 2 * AT_BM * 128;          // two query tiles
 constexpr int AT_KV_BYTES = AT_MAXK * 128;           // up to 256 keys x 64 dims bf16
 constexpr int AT_STG_BYTES = 8192;                   // per softmax warp: 32 rows x 256 B (64 fp32) output staging
@@ -53,13 +64,17 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// optional phase trace of CTA 0 (tuning scripts only): [item < 16][warp 10][event 8] clock64 stamps
+// optional phase trace of CTA 0 (tuning scripts only): [item < 16][warp 12][event 8] clock64 stamps
 __device__ long long* g_attn_trace = nullptr;
 #define AT_TRACE(ev)                                                                                                     \
   do {                                                                                                                   \
-    if (g_attn_trace && blockIdx.x == 0 && lane == 0 && it < 16) g_attn_trace[(it * 10 + warp) * 8 + (ev)] = clock64(); \
+    if (g_attn_trace && blockIdx.x == 0 && lane == 0 && it < 16) g_attn_trace[(it * 12 + warp) * 8 + (ev)] = clock64(); \
   } while (0)
 
+// kMaxUnits: upper bound of the 16-key units per row; kExact: the row has exactly kMaxUnits units (13 = 193..208 keys: the
+// encoder's 197 tokens), so the unrolled softmax has no run-time guards and is one basic block that ptxas can software-pipeline
+// across units (warps issue in order: with a branch per unit the max → exp2 → sum chains of successive units ran back to back).
+template <int kMaxUnits, bool kExact>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
@@ -95,7 +110,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   pdl_wait();      // PDL: the set-up above overlaps the previous kernel's tail
   pdl_trigger();
 
-  if (warp == 0) {
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CTRL));
+   if (warp == 0) {
     // ===== TMA producer (whole warp, one elected lane issues) =====
     const uint32_t q_bytes = (uint32_t)nt * AT_BM * 128u, kv_bytes = (uint32_t)p.nk_pad * 128u;
     for (int it = 0; it < n_my_items; ++it) {
@@ -162,19 +179,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
+   }
   } else {
-    // ===== softmax + epilogue: group t = (warp - 2) / 4 owns query tile t; TMEM lane quarter = warp % 4 =====
-    const int t = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AT_REGS_SOFTMAX));
+    // ===== softmax + epilogue: group t = (warp - 4) / 4 owns query tile t; TMEM lane quarter = warp % 4 =====
+    const int t = (warp - 4) >> 2;
     const int quarter = warp & 3;
     if (t < nt) {
       const int row0 = t * AT_BM + quarter * 32;     // first query row (within the image) of this warp
       const bool active = row0 < p.Lq;               // warps past the last query only keep the barrier protocol going
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * 256);
       const uint32_t x7s = (uint32_t)(lane & 7) << 4;   // 128-byte swizzle of the staging tile: 16-byte chunk index ^= row & 7
-      uint8_t* stg_ptr = smem + AT_OFF_STG + (warp - 2) * AT_STG_BYTES;
+      uint8_t* stg_ptr = smem + AT_OFF_STG + (warp - 4) * AT_STG_BYTES;
       const uint32_t stg = smem_u32(stg_ptr);
-      const int n_full = p.Lk >> 5;                  // 32-column chunks of valid keys
-      const int n_tail = (p.nk_pad - n_full * 32) >> 4;   // 0..2 trailing 16-column pieces holding the last valid keys + padding
+      const int nu = kExact ? kMaxUnits : (p.nk_pad >> 4);   // 16-key units of a row (<= kMaxUnits)
       const float sc = p.scale_log2e;
       for (int it = 0; it < n_my_items; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
@@ -186,77 +204,68 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         AT_TRACE(1);
         float sum = 0.f;
         if (active) {
-          uint32_t va[32], vb[32], vt[16];
-          // ---- pass 1: row maximum over the valid keys (TMEM loads one chunk ahead of the math) ----
-          float m0 = -INFINITY, m1 = -INFINITY;
-          auto max32 = [&](const uint32_t (&v)[32]) {
+          // ---- single pass over S: online softmax per 16-key unit, P kept in registers (bf16 pairs) ----
+          uint32_t pk[kMaxUnits][8];
+          float mrec[kMaxUnits];                     // the running maximum each unit was exponentiated against
+          uint32_t va[16], vb[16];
+          float M = -1.0e30f, l = 0.f;               // running integer-valued max of s*scale*log2e; running row sum
+          auto unit = [&](uint32_t (&v)[16], uint32_t (&pu)[8], float& mr, int c0, bool last) {
+            if (last) {                               // keys beyond Lk (padding of the last unit) drop out as -inf
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j >= p.Lk) v[j] = 0xff800000u;
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
               m0 = max3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
               m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
-          };
-          if (n_full > 0) tmem_ld_32x32(taddr, va);
-          for (int c = 0; c < n_full; c += 2) {
-            tmem_ld_wait32(va);
-            if (c + 1 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), vb);
-            max32(va);
-            if (c + 1 < n_full) {
-              tmem_ld_wait32(vb);
-              if (c + 2 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 2) * 32), va);
-              max32(vb);
-            }
-          }
-          for (int u = 0; u < n_tail; ++u) {
-            const int col0 = n_full * 32 + u * 16;
-            tmem_ld_32x16(taddr + (uint32_t)col0, vt);
-            tmem_ld_wait16(vt);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.Lk) m0 = fmaxf(m0, __uint_as_float(vt[j]));
-          }
-          const float mxs = fmaxf(m0, m1) * sc;
-          AT_TRACE(2);
-          // ---- pass 2: p = exp2(s*scale*log2e - max*scale*log2e); P (bf16 pairs) → TMEM columns [16c, 16c+16) ----
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          auto exp32 = [&](uint32_t (&v)[32], int c) {
-            float e[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mxs));
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) { s0 += e[j]; s1 += e[j + 1]; s2 += e[j + 2]; s3 += e[j + 3]; }
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
-            tmem_st_32x16(taddr + (uint32_t)(c * 16), pk);
-          };
-          if (n_full > 0) tmem_ld_32x32(taddr, va);
-          for (int c = 0; c < n_full; c += 2) {
-            tmem_ld_wait32(va);
-            if (c + 1 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 1) * 32), vb);
-            exp32(va, c);
-            if (c + 1 < n_full) {
-              tmem_ld_wait32(vb);
-              if (c + 2 < n_full) tmem_ld_32x32(taddr + (uint32_t)((c + 2) * 32), va);
-              exp32(vb, c + 1);
-            }
-          }
-          for (int u = 0; u < n_tail; ++u) {
-            const int col0 = n_full * 32 + u * 16;
-            tmem_ld_32x16(taddr + (uint32_t)col0, vt);
-            tmem_ld_wait16(vt);
+            const float Mn = fmaxf(M, ceilf(fmaxf(m0, m1) * sc));
+            const float corr = ex2_approx(M - Mn);   // exact power of two (0 on the first unit)
+            M = Mn;
+            mr = Mn;
             float e[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              e[j] = (col0 + j < p.Lk) ? ex2_approx(fmaf(__uint_as_float(vt[j]), sc, -mxs)) : 0.f;
-              s0 += e[j];
-            }
-            uint32_t pk[8];
+            for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -Mn));
+            const float cs = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7])) +
+                             (((e[8] + e[9]) + (e[10] + e[11])) + ((e[12] + e[13]) + (e[14] + e[15])));
+            l = fmaf(l, corr, cs);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
-            tmem_st_32x8(taddr + (uint32_t)(col0 >> 1), pk);
+            for (int j = 0; j < 8; ++j) pu[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+          };
+          tmem_ld_32x16(taddr, va);
+#pragma unroll
+          for (int u = 0; u < kMaxUnits; ++u) {
+            if (u < nu) {
+              if (u & 1) {
+                tmem_ld_wait16(vb);
+                if (u + 1 < nu) tmem_ld_32x16(taddr + (uint32_t)((u + 1) * 16), va);
+                unit(vb, pk[u], mrec[u], u * 16, u == nu - 1);
+              } else {
+                tmem_ld_wait16(va);
+                if (u + 1 < nu) tmem_ld_32x16(taddr + (uint32_t)((u + 1) * 16), vb);
+                unit(va, pk[u], mrec[u], u * 16, u == nu - 1);
+              }
+            }
           }
-          sum = (s0 + s1) + (s2 + s3);
+          AT_TRACE(2);
+          // ---- bring every unit to the final maximum (exact: power-of-two factors) and write P over S ----
+#pragma unroll
+          for (int u = 0; u < kMaxUnits; ++u) {
+            if (u < nu) {
+              const float fc = ex2_approx(mrec[u] - M);
+              const __nv_bfloat162 f2 = __float2bfloat162_rn(fc);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&pk[u][j]);
+                x = __hmul2(x, f2);
+                pk[u][j] = *reinterpret_cast<uint32_t*>(&x);
+              }
+              tmem_st_32x8(taddr + (uint32_t)(u * 8), pk[u]);
+            }
+          }
+          sum = l;
           tmem_st_wait();
         }
         tc_fence_before_sync();         // our TMEM reads of S / writes of P are ordered before the PV MMAs
@@ -376,7 +385,8 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_set = true;
   }
   const int n_items = B * heads;
@@ -384,7 +394,8 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   const int grid = n_items < at_num_sms() ? n_items : at_num_sms();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AT_DH * heads * B, s);
-    SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
+    if (nk_pad == 13 * 16) SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<13, true>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
+    else SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<16, false>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
