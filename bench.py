@@ -53,16 +53,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML in-process
+    (the library nvidia-smi itself reads; ~1 ms per sample, so even a 50 ms timed region gets dozens of samples); falls
+    back to an `nvidia-smi -lms` child process when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.nvml, self.samples = index, None, [], None, []
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -70,6 +107,13 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            reasons = sorted(k for k, bit in self.BITS.items() if any(mask & bit for _, mask in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -89,7 +133,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_reference_images_per_s(n_img, size, nq, batch, steps=1, warmup=0):
@@ -202,10 +246,10 @@ def main():
         torch.cuda.cudart().cudaProfilerStop()
         return
     sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib().smk_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.start()
     e0.record()
     for _ in range(K):
         counts, sums = step()
