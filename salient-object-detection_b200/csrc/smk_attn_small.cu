@@ -54,21 +54,28 @@ attn_small_kernel(const AttnSmallParams p) {
     const int64_t kv_row = (int64_t)b * p.kv_rows + p.kv_row0;
     const __nv_bfloat16* kg = p.k + kv_row * p.ldk + h * AS_DH;
     const __nv_bfloat16* vg = p.v + kv_row * p.ldv + h * AS_DH;
+    // two cp.async groups: {Q, K} then {V} — the scores and the softmax run while V is still in flight
     for (int i = tid; i < LkP * 8; i += AS_THREADS) {
       const int r = i >> 3, c = i & 7;
-      if (r < p.Lk) {
-        cp_async16((uint32_t)__cvta_generic_to_shared(sK + r * AS_LD + c * 8), kg + (int64_t)r * p.ldk + c * 8);
-        cp_async16((uint32_t)__cvta_generic_to_shared(sV + r * AS_LD + c * 8), vg + (int64_t)r * p.ldv + c * 8);
-      } else {
-        *reinterpret_cast<uint4*>(sK + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sV + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
-      }
+      if (r < p.Lk) cp_async16((uint32_t)__cvta_generic_to_shared(sK + r * AS_LD + c * 8), kg + (int64_t)r * p.ldk + c * 8);
+      else *reinterpret_cast<uint4*>(sK + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
     }
-    cp_async_wait_all();
+    cp_async_commit();
+    for (int i = tid; i < LkP * 8; i += AS_THREADS) {
+      const int r = i >> 3, c = i & 7;
+      if (r < p.Lk) cp_async16((uint32_t)__cvta_generic_to_shared(sV + r * AS_LD + c * 8), vg + (int64_t)r * p.ldv + c * 8);
+      else *reinterpret_cast<uint4*>(sV + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
   }
   const int r0 = warp * 16;
-  if (r0 >= p.Lq) return;                       // this warp's 16 query rows are all padding
+  if (r0 >= p.Lq) {                             // this warp's 16 query rows are all padding: only see the V group through
+    cp_async_wait<0>();
+    __syncthreads();
+    return;
+  }
   const int g = lane >> 2, t = lane & 3;
 
   // ---- S = Q·K^T (fragment layouts of mma.m16n8k16: A row g / g+8, cols 2t.. ; B k 2t.., col g; C row g / g+8, cols 2t, 2t+1) ----
@@ -123,6 +130,8 @@ attn_small_kernel(const AttnSmallParams p) {
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 
+  cp_async_wait<0>();
+  __syncthreads();                              // V (second cp.async group) has landed for every thread's copies
   // ---- O = P·V: the C fragments of score tiles 2j, 2j+1 are exactly the A fragment of k-step j ----
   float o[8][4];
 #pragma unroll

@@ -11,7 +11,6 @@ import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import selfmask_b200 as S  # noqa: E402
-from oracle import selfmask_oracle as O  # noqa: E402  (synthetic weights / images only)
 from selfmask_b200._lib import lib  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -21,11 +20,9 @@ ap.add_argument("--size", type=int, default=224)
 ap.add_argument("--nq", type=int, default=20)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-cfg = O.make_config(n_queries=args.nq)
-sd = O.synth_state_dict(cfg, seed=0)
+from selfmask_b200 import synthetic as Y  # noqa: E402  (same synthetic weights / images / ground truth as bench.py)
 model = S.SelfMaskB200(n_queries=args.nq, mode=args.mode, max_batch=args.batch).to(dev)
-model.load_state_dict(sd)
-from selfmask_b200 import synthetic as Y  # noqa: E402  (same synthetic images / ground truth as bench.py)
+model.load_state_dict(Y.synth_state_dict(model.table(), seed=0))
 uniq = min(args.batch, 32)
 rep = (args.batch + uniq - 1) // uniq
 x = torch.from_numpy(Y.synth_images_u8(uniq, args.size, args.size, seed=1234)).repeat(rep, 1, 1, 1)[:args.batch].to(dev)
