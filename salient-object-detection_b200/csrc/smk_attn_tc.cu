@@ -51,6 +51,7 @@ struct AttnTcParams {
   int heads, n_items;           // items = images x heads
   int out_f32;
   float scale_log2e;
+  int rev;                      // walk the items from the last one (smk_kernels.h g_traverse_rev)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -116,7 +117,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ===== TMA producer (whole warp, one elected lane issues) =====
     const uint32_t q_bytes = (uint32_t)nt * AT_BM * 128u, kv_bytes = (uint32_t)p.nk_pad * 128u;
     for (int it = 0; it < n_my_items; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
+      const int item_i = blockIdx.x + it * gridDim.x, item = p.rev ? p.n_items - 1 - item_i : item_i;
       const int b = item / p.heads, h = item % p.heads;
       const int kv_row = b * p.kv_rows + p.kv_row0;
       mbar_wait(qk_empty, (it & 1) ^ 1);
@@ -195,7 +196,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int nu = kExact ? kMaxUnits : (p.nk_pad >> 4);   // 16-key units of a row (<= kMaxUnits)
       const float sc = p.scale_log2e;
       for (int it = 0; it < n_my_items; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
+        const int item_i = blockIdx.x + it * gridDim.x, item = p.rev ? p.n_items - 1 - item_i : item_i;
         const uint32_t par = it & 1;
         const int b = item / p.heads, h = item % p.heads;
         AT_TRACE(0);
@@ -390,7 +391,7 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
     attr_set = true;
   }
   const int n_items = B * heads;
-  AttnTcParams p{Lq, Lk, nk_pad, nt, Lq, kv_rows, kv_row0, heads, n_items, out_f32, scale * 1.4426950408889634f};
+  AttnTcParams p{Lq, Lk, nk_pad, nt, Lq, kv_rows, kv_row0, heads, n_items, out_f32, scale * 1.4426950408889634f, traverse_dir()};
   const int grid = n_items < at_num_sms() ? n_items : at_num_sms();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AT_DH * heads * B, s);

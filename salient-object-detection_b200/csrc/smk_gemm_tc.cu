@@ -115,6 +115,7 @@ struct TcGemmParams {
   int tok_hw;
   const float* tok_pos;
   int dbg;
+  int rev;        // strided schedule only: walk the tile sequence from its end (smk_kernels.h g_traverse_rev)
 };
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
@@ -187,7 +188,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       WaitClock w_slot(trace != nullptr), w_all(trace != nullptr);
       w_all.begin();
       int n_loads = 0;
-      for (int tile = tile0; tile < tile_end; tile += tile_step) {
+      for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
+        const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         const bool new_m = kARes && m_blk != cur_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -300,7 +302,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     WaitClock w_tm(tr_w), w_stg(tr_w), w_all(tr_w), w_ld(tr_w), w_st(tr_w);
     long long n_tiles_done = 0;
     w_all.begin();
-    for (int tile = tile0; tile < tile_end; tile += tile_step) {
+    for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
+      const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
       const int m_blk = (tile / n_blocks) * kCtas + (int)rank, n_blk = tile % n_blocks;
       ++n_tiles_done;
       w_tm.begin();
@@ -664,7 +667,7 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
     const char* e = getenv("SMK_GEMM_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg};
+  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg, traverse_dir()};
   if (tok_hw > 0) {
     tcm = ta;   // unused by the direct-store epilogue
     return launch_bn<true, 1, false>(BN, ta, tb, tcm, p, s);

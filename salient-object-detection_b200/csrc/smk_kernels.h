@@ -4,6 +4,19 @@
 
 namespace smk {
 
+// Traversal direction of the next row-streaming launch (LayerNorm rows, GEMM tiles, attention items): 0 = ascending,
+// 1 = descending.  The encoder flips it after every launch, so each kernel starts on the rows its producer wrote LAST — the
+// ones still in the 126 MB L2 — instead of the rows that were evicted first (an LRU stream larger than the cache never hits
+// when producer and consumer walk in the same direction).  Host-side, read at launch time.
+extern thread_local int g_traverse_rev;
+extern thread_local int g_traverse_alt;   // 1: every honouring launch flips g_traverse_rev after reading it
+inline int traverse_dir() {
+  const int r = g_traverse_rev;
+  if (g_traverse_alt) g_traverse_rev ^= 1;
+  return r;
+}
+
+
 int layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y, float* sum_out, int64_t rows,
                   int D, float eps, cudaStream_t s);
 int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int64_t rows, int D, float eps, cudaStream_t s);

@@ -432,6 +432,8 @@ extern "C" int smk_model_destroy(smk_model* m) {
   return SMK_OK;
 }
 
+namespace smk { thread_local int g_traverse_rev = 0; thread_local int g_traverse_alt = 0; }
+
 static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8, const float* mean_std, int B, int H, int W, int all_layers,
                               float* mask_pred, float* objectness, float* features, void* stream);
 
@@ -534,6 +536,11 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
 
   // ---- encoder ------------------------------------------------------------------------------------
   if (bf) l2_persist_window(s, m->X, (size_t)M * D * sizeof(float));
+  // alternate the traversal direction of successive encoder launches (smk_kernels.h): every consumer starts on the rows its
+  // producer wrote last, which are still in L2.  SMK_TRAVERSE_ALT=0 switches it off.
+  static const bool alt_env = !(getenv("SMK_TRAVERSE_ALT") && atoi(getenv("SMK_TRAVERSE_ALT")) == 0);
+  struct AltGuard { ~AltGuard() { smk::g_traverse_alt = 0; smk::g_traverse_rev = 0; } } alt_guard;
+  if (bf && alt_env) smk::g_traverse_alt = 1;
   if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
     if (x_u8) SMK_PROPAGATE((im2col<uint8_t, __nv_bfloat16>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s)));
@@ -614,6 +621,8 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   }
 
   if (bf) l2_persist_window(s, nullptr, 0);
+  smk::g_traverse_alt = 0;
+  smk::g_traverse_rev = 0;
   // ---- decoder (transformer_decoder.py:260-297, post-norm) ---------------------------------------------------
   const float* qpos = w + m->o_query;
   const int64_t ldkv = (int64_t)L * 2 * D;

@@ -3,6 +3,7 @@
 // resolution → bilinear → sigmoid), objectness tail, casts.  Memory-bound ones are vectorised, one warp
 // per row with shuffle reductions.
 #include "smk_common.cuh"
+#include "smk_kernels.h"
 
 namespace smk {
 
@@ -20,10 +21,11 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
                  TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */,
                  TOut* __restrict__ y_dup /* bf16 only: second copy of y; (y, y_dup, y_lo) at columns 0, D, 2D of rows of ldy = 3D
                                              elements form the bf16x3 split [hi | hi | lo] a split GEMM consumes */,
-                 int64_t ldy, int64_t rows, int D, float eps) {
+                 int64_t ldy, int64_t rows, int D, float eps, int rev) {
   pdl_wait();
   pdl_trigger();
-  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_ROWS;
+  const int64_t blk = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;     // descending: start on the rows written last
+  const int64_t row0 = (blk * 8 + (threadIdx.x >> 5)) * LN_ROWS;
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   float4 v[LN_ROWS][kChunks];
@@ -106,10 +108,11 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 8 * LN_ROWS - 1) / (8 * LN_ROWS));
+  const int rev = traverse_dir();
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, ldy, rows, D, eps)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, ldy, rows, D, eps, rev)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include "smk_common.cuh"
+#include "smk_kernels.h"
 
 namespace smk {
 namespace tc {

@@ -23,3 +23,10 @@ cap kv 87 2
 cap dec 97 12
 cap tail 157 9
 ls -la gpurun_out/*.ncu-rep
+# summaries are produced ON the box (gpurun pulls at most 64 MiB back): tables + traffic JSON, then only the encoder-layer
+# report (source-level view of the GEMM / attention / LayerNorm kernels) travels home
+python scripts/ncu_summary.py launches gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launch_table.md
+python scripts/ncu_summary.py full gpurun_out/${TAG}_enc.ncu-rep gpurun_out/${TAG}_kv.ncu-rep gpurun_out/${TAG}_dec.ncu-rep gpurun_out/${TAG}_tail.ncu-rep > gpurun_out/${TAG}_full_tables.md
+python scripts/ncu_summary.py traffic gpurun_out/${TAG}_enc.ncu-rep gpurun_out/${TAG}_kv.ncu-rep gpurun_out/${TAG}_dec.ncu-rep gpurun_out/${TAG}_tail.ncu-rep > gpurun_out/${TAG}_traffic.json
+rm -f gpurun_out/${TAG}_kv.ncu-rep gpurun_out/${TAG}_dec.ncu-rep gpurun_out/${TAG}_tail.ncu-rep
+ls -la gpurun_out/ | tail -12
