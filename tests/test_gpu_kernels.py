@@ -261,7 +261,7 @@ def test_attention_matches_torch(Lq, Lk, is_bf16):
     assert (o.float() - ref).abs().max().item() <= (0.02 if is_bf16 else 2e-5)
 
 
-@pytest.mark.parametrize("B,N", [(1, 197), (3, 197), (2, 64), (2, 256), (5, 130), (64, 197)])
+@pytest.mark.parametrize("B,N", [(1, 197), (3, 197), (2, 64), (2, 256), (5, 130), (64, 197), (3, 208), (2, 193), (2, 17), (150, 197)])
 def test_attention_tcgen05_matches_torch(B, N):
     torch.manual_seed(4)
     H, dh = 6, 64
