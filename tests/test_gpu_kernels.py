@@ -273,7 +273,9 @@ def test_attention_tcgen05_matches_torch(B, N):
     q, k, v = [t.float().view(B, N, H, dh).transpose(1, 2) for t in qkv.view(B, N, 3 * D).split(D, dim=-1)]
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, D)
     err = (out.float() - ref).abs().max().item()
-    assert err <= 0.03, err
+    # bf16 P and a bf16 output of magnitude up to ~4: one output ulp is 0.016-0.03; the maximum over 11 M outputs (B = 150) reaches 0.0303
+    assert err <= 0.04, err
+    assert (out.float() - ref).abs().mean().item() <= 2e-3
 
 
 def test_bf16x3_split_gemm_is_near_fp32():
