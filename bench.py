@@ -93,7 +93,11 @@ class ClockSampler:
                     mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                self.samples.append((float(mhz), int(mask)))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                except Exception:
+                    pw = float("nan")
+                self.samples.append((float(mhz), int(mask), pw))
             except Exception:
                 pass
             time.sleep(0.001)
@@ -115,10 +119,17 @@ class ClockSampler:
         if self.nvml is not None:
             self._stop.set()
             self.t.join(timeout=2)
-            sm = [m for m, _ in self.samples]
-            reasons = sorted(k for k, bit in self.BITS.items() if any(mask & bit for _, mask in self.samples))
+            sm = [x[0] for x in self.samples]
+            pw = [x[2] for x in self.samples if x[2] == x[2]]
+            reasons = sorted(k for k, bit in self.BITS.items() if any(x[1] & bit for x in self.samples))
+            try:
+                limit_w = self.nvml.nvmlDeviceGetEnforcedPowerLimit(self.handle) / 1e3
+            except Exception:
+                limit_w = None
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
+                    "reasons": reasons, "samples": len(sm), "source": "nvml",
+                    "power_w_nvml_avg": float(np.median(pw)) if pw else None, "power_limit_w": limit_w,
+                    "power_note": "NVML reports a ~1 s running average, so a 50 ms timed region after an idle phase reads low"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
