@@ -116,6 +116,13 @@ struct TcGemmParams {
   const float* tok_pos;
   int dbg;
   int rev;        // strided schedule only: walk the tile sequence from its end (smk_kernels.h g_traverse_rev)
+  // "swap-AB" form for narrow outputs (fc2: 384 output features, K = 1536): the kernel computes C^T = W · A^T, i.e. its M axis
+  // runs over the output FEATURES (128-row tiles of W) and its N axis over the TOKENS (256-wide tiles of the activations), so
+  // every MMA is 128 x 256 x 16 instead of 128 x 192 x 16 — an SS-mode MMA costs ~150-170 cycles whatever its N (profiles/
+  // r01_gemm_experiments.md), so the wide form runs the tensor pipe at 1.7 instead of 0.9-1.3 PFLOP/s.  The epilogue then holds
+  // one feature per lane and 32 tokens per chunk: bias is a per-lane scalar, the staging tile is written transposed
+  // (token-major rows of 32 features) and the TMA store / reduce-add addresses C[token, feature] as usual.  fp32 output only.
+  int trans;
 };
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
@@ -140,7 +147,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + TC_ARES_KB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blocks = p.N / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);
+  const int n_blocks = (p.N + BN - 1) / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);   // N % BN == 0 unless trans
   const int num_tiles = n_blocks * m_blocks, k_blocks = p.K / TC_BK;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
   // tiles are owned by clusters.  Strided order (neighbouring CTAs work on neighbouring tiles) or, A-resident, a contiguous
@@ -190,7 +197,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int n_loads = 0;
       for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
         const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
-        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        // trans: the feature blocks of one token block are neighbours in the sequence (they share the activation tile in L2)
+        const int m_blk = p.trans ? tile % m_blocks : tile / n_blocks, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
         const bool new_m = kARes && m_blk != cur_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
           if (new_m && !((dbg & TC_DBG_NOLOAD) && a_fills > 0)) {
@@ -304,7 +312,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     w_all.begin();
     for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
       const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
-      const int m_blk = (tile / n_blocks) * kCtas + (int)rank, n_blk = tile % n_blocks;
+      const int m_blk = (p.trans ? tile % m_blocks : tile / n_blocks) * kCtas + (int)rank, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
       ++n_tiles_done;
       w_tm.begin();
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -329,7 +337,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
         float4 bv[kEW == 16 ? 1 : 8];
-        if (kEW != 16 && p.bias) {               // L1 hits after the first tile; in flight under the TMEM load
+        if (kEW != 16 && p.bias && !p.trans) {   // L1 hits after the first tile; in flight under the TMEM load
 #pragma unroll
           for (int j = 0; j < (kEW == 16 ? 1 : 8); ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
         }
@@ -347,7 +355,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+        if (p.bias && p.trans) {                 // swap-AB: the lane is an output feature
+          const float bm = m < p.M ? __ldg(p.bias + m) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bm;
+        } else if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             // 16-warp variant (<= 112 registers): no prefetched copy, the (L1-resident, warp-uniform) bias is read at use
@@ -386,7 +398,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             continue;
           }
           w_st.begin();
-          if (kEW != 16 && p.out_f32 == 1) {
+          if (kEW != 16 && p.out_f32 == 1 && p.trans) {
+            // swap-AB: v[j] = C[token n0 + j, feature row0 + lane].  Staging tile: 32 token rows x 32 features (128 B), 128-byte
+            // swizzle; for a fixed token the 32 lanes fill one 128-byte row (conflict-free 4-byte stores)
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            const uint32_t lcol = (uint32_t)(lane >> 2), lsub = (uint32_t)(lane & 3) << 2;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg_u32 + (uint32_t)j * 128u + (((lcol ^ (uint32_t)(j & 7))) << 4) + lsub), "r"(r4(v[j])) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.epi & SMK_EPI_RESIDUAL) tma_reduce_add_2d(&tmC, stg, row0, n0);
+              else tma_store_2d(&tmC, stg, row0, n0);
+              bulk_commit();
+            }
+          } else if (kEW != 16 && p.out_f32 == 1) {
             // staging tile: 32 rows x 128 B, 128-byte swizzle (16-byte chunk index ^= row & 7)
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
@@ -610,6 +638,21 @@ static bool use_cta_pair(int M, int K) {
   return K >= 1024 && M >= 16384;
 }
 
+// swap-AB form (TcGemmParams::trans): narrow fp32 outputs of long-K, many-row problems (fc2).  SMK_GEMM_SWAP_AB = 0 / 1 forces it
+// off / on for every eligible call (tuning).  Measured on B200 (kernel_bench, same box): fc2 65.9 / 66.2 → 64.8 / 64.7 us, proj
+// (K = 384, forced) 36.8 → 39.2 us: fc2 moves 310 MB at 4.8 TB/s either way — the fp32 residual read-modify-write and the
+// hidden-tensor read, not the MMA width, bound it — so the wide MMAs only buy 2 %.
+static bool use_swap_ab(int M, int N, int K) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("SMK_GEMM_SWAP_AB");
+    mode = e ? atoi(e) : -1;
+  }
+  if (N % TC_BM != 0) return false;
+  if (mode >= 0) return mode != 0;
+  return N <= 512 && K >= 1024 && M >= 16384;
+}
+
 // SMK_GEMM_ARES=1 enables the A-resident schedule for K <= 384.  Default off: measured 5-10 % slower on this model's shapes
 // (the epilogue, not the operand feed, bounds those GEMMs; see profiles/r01_gemm_experiments.md)
 static int ares_mode() {
@@ -652,6 +695,15 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
+  if (tok_hw == 0 && out_f32 == 1 && use_swap_ab(M, N, K)) {
+    // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
+    CUtensorMap ta, tb, tcm;
+    SMK_PROPAGATE(make_tmap_bf16_2d(&ta, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, TC_BM));
+    SMK_PROPAGATE(make_tmap_bf16_2d(&tb, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, 256));
+    SMK_PROPAGATE(make_tmap_2d(&tcm, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, 128));
+    TcGemmParams p{N, M, K, bias, C, ldc, epi, out_f32, 0, nullptr, 0, traverse_dir(), 1};
+    return launch_tc<256, false, 1, false>(ta, tb, tcm, p, s);
+  }
   const bool pair = tok_hw == 0 && use_cta_pair(M, K);
   const bool ares = tok_hw == 0 && ares_mode() != 0 && K <= TC_ARES_KB * TC_BK;
   const int kc = pair ? 2 : 1;
@@ -667,7 +719,7 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
     const char* e = getenv("SMK_GEMM_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg, traverse_dir()};
+  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg, traverse_dir(), 0};
   if (tok_hw > 0) {
     tcm = ta;   // unused by the direct-store epilogue
     return launch_bn<true, 1, false>(BN, ta, tb, tcm, p, s);

@@ -221,7 +221,10 @@ def test_gemm_f32_matches_torch(M_, N, K, epi):
                                             (50432, 1536, 384, 1, False), (50432, 384, 1536, 4, True), (40000, 4608, 384, 0, False),
                                             (50432, 1152, 384, 0, False), (50432, 384, 384, 4, True), (5120, 768, 1152, 0, False),
                                             (64, 256, 768, 2, True), (300, 256, 192, 0, True), (1000, 384, 128, 0, False),
-                                            (20000, 768, 256, 1, False), (19000, 1152, 384, 4, True)])
+                                            (20000, 768, 256, 1, False), (19000, 1152, 384, 4, True),
+                                            # swap-AB form (narrow fp32 output, K >= 1024, >= 16384 rows): ragged token counts, plain / ReLU / residual
+                                            (16500, 384, 1024, 4, True), (17001, 256, 2048, 0, True), (16421, 128, 1024, 2, True),
+                                            (25216, 384, 1536, 4, True)])
 def test_gemm_bf16_tcgen05_matches_torch(M_, N, K, epi, f32):
     torch.manual_seed(2)
     A = torch.randn(M_, K, device=DEV).to(torch.bfloat16)
