@@ -451,6 +451,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_store_2d(&tmC, stg + 2048, 2 * p.N + n0, row0);
               bulk_commit();
             }
+          } else if (kEW != 16 && p.out_f32 == 0 && p.trans) {
+            // swap-AB, bf16 output: v[j] = C[token n0 + j, feature row0 + lane].  Staging tile: 32 token rows x 32 features (64 B),
+            // 64-byte swizzle, two buffers; for a fixed token the 32 lanes fill one 64-byte row with 2-byte stores
+            uint8_t* buf = stg + (it & 1) * 2048;
+            ++it;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint32_t sb = stg_u32 + (uint32_t)(buf - stg) + ((uint32_t)(lane & 7) << 1), lchunk = (uint32_t)(lane >> 3);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(v[j]));
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + (uint32_t)j * 64u + ((lchunk ^ (uint32_t)((j >> 1) & 3)) << 4)), "h"(hv) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, row0, n0);
+              bulk_commit();
+            }
           } else {
             // staging tile: 32 rows x 64 B, 64-byte swizzle (16-byte chunk index ^= (row >> 1) & 3), two buffers
             uint8_t* buf = kEW == 16 ? stg : stg + (it & 1) * 2048;      // 16-warp variant: one buffer per warp
@@ -653,6 +672,20 @@ static bool use_swap_ab(int M, int N, int K) {
   return N <= 512 && K >= 1024 && M >= 16384;
 }
 
+// swap-AB for bf16 outputs whose width is not a multiple of 256 (qkv: 1152 = 9 x 128 features → every MMA 128 x 256 over tokens
+// instead of 128 x 192; 1773 tiles = 11.98 waves of 148).  OFF unless SMK_GEMM_SWAP_AB=1: measured on B200 qkv 48.4 / 48.5 us in
+// the normal form vs 49.5 / 49.3 us swapped — qkv is paced by its epilogue (TMEM read + pack + stores of 116 MB), not by the MMA
+// width, and the transposed store costs one 2-byte st.shared per element.  Never for GELU epilogues (fc1).
+static bool use_swap_ab_bf16(int M, int N, int epi) {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("SMK_GEMM_SWAP_AB");
+    mode = e ? atoi(e) : -1;
+  }
+  if (N % TC_BM != 0 || (epi & SMK_EPI_GELU)) return false;
+  return mode == 1 && N % 256 != 0 && M >= 16384;
+}
+
 // SMK_GEMM_ARES=1 enables the A-resident schedule for K <= 384.  Default off: measured 5-10 % slower on this model's shapes
 // (the epilogue, not the operand feed, bounds those GEMMs; see profiles/r01_gemm_experiments.md)
 static int ares_mode() {
@@ -695,12 +728,12 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
   if (M == 0) return SMK_OK;
-  if (tok_hw == 0 && out_f32 == 1 && use_swap_ab(M, N, K)) {
+  if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, K)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
     // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
     CUtensorMap ta, tb, tcm;
     SMK_PROPAGATE(make_tmap_bf16_2d(&ta, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, TC_BM));
     SMK_PROPAGATE(make_tmap_bf16_2d(&tb, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, 256));
-    SMK_PROPAGATE(make_tmap_2d(&tcm, 4, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, 128));
+    SMK_PROPAGATE(make_tmap_2d(&tcm, out_f32 ? 4 : 2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * (out_f32 ? 4 : 2), 32, 32, out_f32 ? 128 : 64));
     TcGemmParams p{N, M, K, bias, C, ldc, epi, out_f32, 0, nullptr, 0, traverse_dir(), 1};
     return launch_tc<256, false, 1, false>(ta, tb, tcm, p, s);
   }

@@ -224,7 +224,9 @@ def test_gemm_f32_matches_torch(M_, N, K, epi):
                                             (20000, 768, 256, 1, False), (19000, 1152, 384, 4, True),
                                             # swap-AB form (narrow fp32 output, K >= 1024, >= 16384 rows): ragged token counts, plain / ReLU / residual
                                             (16500, 384, 1024, 4, True), (17001, 256, 2048, 0, True), (16421, 128, 1024, 2, True),
-                                            (25216, 384, 1536, 4, True)])
+                                            (25216, 384, 1536, 4, True),
+                                            # shapes of the opt-in bf16 swap-AB form (SMK_GEMM_SWAP_AB=1); normal form by default
+                                            (16500, 1152, 384, 0, False), (20001, 384, 256, 2, False)])
 def test_gemm_bf16_tcgen05_matches_torch(M_, N, K, epi, f32):
     torch.manual_seed(2)
     A = torch.randn(M_, K, device=DEV).to(torch.bfloat16)
