@@ -41,7 +41,11 @@ constexpr int AT_STG_BYTES = 8192;                   // per softmax warp: 32 row
 constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_STG = AT_OFF_V + AT_KV_BYTES;
 constexpr int AT_OFF_BAR = AT_OFF_STG + 8 * AT_STG_BYTES;
 constexpr int AT_SMEM = AT_OFF_BAR + 256 /*barriers*/ + 1024 /*align*/;
-constexpr int AT_O_COL = 128;                        // O accumulator columns within a slot
+constexpr int AT_O_COL = 128;
+#ifndef SMK_ATTN_POLY_MASK
+#define SMK_ATTN_POLY_MASK 0x0         // bit j: element j of every 16-key unit uses ex2_poly (experiment, off: see ex2_poly)
+#endif
+constexpr unsigned kPolyMask = SMK_ATTN_POLY_MASK;                        // O accumulator columns within a slot
 static_assert(AT_SMEM <= 227 * 1024, "attention shared memory budget");
 
 struct AttnTcParams {
@@ -63,6 +67,20 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax of 2^f
+// (max relative error 7.5e-5, far below the bf16 rounding of P), exponent added with one shift-add.  The MUFU (16 ex2 per clock
+// and SM) is the busiest unit of the softmax pass, but the pass has no issue slots to spare either: with a quarter of the
+// exponentials on this path (SMK_ATTN_POLY_MASK=0x8888) the pass takes 4.5 k instead of 3.95 k cycles (56.3 vs 53.7 us).  Off.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0551716648f, 0.2426111251f);   // minimax fit of 2^f on [-0.5, 0.5] (relative error 7.5e-5, tests/test_host_cpu.py)
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 // optional phase trace of CTA 0 (tuning scripts only): [item < 16][warp 12][event 8] clock64 stamps
@@ -228,7 +246,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mr = Mn;
             float e[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -Mn));
+            for (int j = 0; j < 16; ++j) {
+              const float xj = fmaf(__uint_as_float(v[j]), sc, -Mn);
+              e[j] = (kPolyMask >> j) & 1 ? ex2_poly(xj) : ex2_approx(xj);
+            }
             const float cs = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7])) +
                              (((e[8] + e[9]) + (e[10] + e[11])) + ((e[12] + e[13]) + (e[14] + e[15])));
             l = fmaf(l, corr, cs);
