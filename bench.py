@@ -327,7 +327,10 @@ def main():
         ach = work_c[i] / sec / (1e12 if i in tensor_cats else 1e9) if sec > 0 else 0.0
         stages[nme] = {"ms_per_step": ms_c[i] / prof_steps, "launches_per_step": n_c[i] // prof_steps, "share": ms_c[i] / total_ms if total_ms else 0,
                        "achieved": ach, "unit": "TFLOP/s" if i in tensor_cats else "GB/s",
-                       "frac_of_peak": ach / (pk["tensor"] if i in tensor_cats else pk["hbm"])}
+                       "frac_of_peak": ach / (pk["tensor"] if i in tensor_cats else pk["hbm"]),
+                       "bound": ("tensor pipe is the yardstick north_star names; the kernel itself is paced by the MUFU (ex2) and the TMEM read "
+                                 "port of the softmax (DESIGN.md §8, profiles/r01_attention_tmem.md)") if i == 7 else
+                                ("tensor" if i in tensor_cats else "hbm")}
     traffic = None          # real DRAM bytes per launch of the dominant stage's kernels, from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     dom = max(range(8), key=lambda i: ms_c[i])
