@@ -15,7 +15,10 @@
 //               softmax over 16-key units keeps every unit's P in registers as packed bf16 pairs (8 registers per unit),
 //               exponentiated against the running row maximum rounded UP to an integer (in the log2 domain), so that the
 //               final correction of an earlier unit is a multiplication by an exact power of two (HMUL2.BF16, no second
-//               rounding); the row sum is rescaled the same way.  P is then written back over S with tcgen05.st;
+//               rounding).  The row sum is not accumulated by the softmax warps at all: the P·V MMA runs with N = 80, its B operand's
+//               second MN block being a shared-memory tile of ones, so O[:, 64] = Σ_k P[:, k] of the very bf16 values the MMA
+//               multiplies (pass 3.95 k → 2.7 k cycles per tile: the 16-way add trees were the longest dependency chains of
+//               the unit).  P is then written back over S with tcgen05.st;
 //               after O_t lands: O / rowsum → shared-memory staging → TMA tile store through a 3-D {column,
 //               row-in-image, image} tensor map, which clips the rows beyond the image's last query.
 //               (A two-pass version — row max, then exp2 — read S twice: 480 instead of 272 columns per row and item,
@@ -38,7 +41,10 @@ constexpr int AT_THREADS = 384, AT_REGS_CTRL = 48, AT_REGS_SOFTMAX = 224;
 constexpr int AT_Q_BYTES = 2 * AT_BM * 128;          // two query tiles
 constexpr int AT_KV_BYTES = AT_MAXK * 128;           // up to 256 keys x 64 dims bf16
 constexpr int AT_STG_BYTES = 8192;                   // per softmax warp: 32 rows x 256 B (64 fp32) output staging
-constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_STG = AT_OFF_V + AT_KV_BYTES;
+// the "ones" tile: second 64-column MN block of the P·V B operand (only its first 16 columns are used, N = 80): column 64 of O
+// becomes the row sum of the bf16 P that the MMA actually multiplies — the softmax warps no longer add the exponentials up
+constexpr int AT_OFF_K = AT_Q_BYTES, AT_OFF_V = AT_OFF_K + AT_KV_BYTES, AT_OFF_ONES = AT_OFF_V + AT_KV_BYTES, AT_OFF_STG = AT_OFF_ONES + AT_KV_BYTES;
+constexpr int AT_PV_N = AT_DH + 16;
 constexpr int AT_OFF_BAR = AT_OFF_STG + 8 * AT_STG_BYTES;
 constexpr int AT_SMEM = AT_OFF_BAR + 256 /*barriers*/ + 1024 /*align*/;
 constexpr int AT_O_COL = 128;
@@ -46,6 +52,7 @@ constexpr int AT_O_COL = 128;
 #define SMK_ATTN_POLY_MASK 0x0         // bit j: element j of every 16-key unit uses ex2_poly (experiment, off: see ex2_poly)
 #endif
 constexpr unsigned kPolyMask = SMK_ATTN_POLY_MASK;                        // O accumulator columns within a slot
+static_assert(AT_O_COL + AT_PV_N <= 256, "O accumulator must stay inside its TMEM slot");
 static_assert(AT_SMEM <= 227 * 1024, "attention shared memory budget");
 
 struct AttnTcParams {
@@ -121,6 +128,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, AT_TMEM_COLS);
+  for (int i = threadIdx.x; i < AT_KV_BYTES / 16; i += AT_THREADS)      // bf16 1.0 everywhere (uniform, so the swizzle does not matter)
+    *reinterpret_cast<uint4*>(smem + AT_OFF_ONES + i * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();               // generic-proxy writes → visible to the tensor core's async-proxy reads
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -151,9 +161,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp stays convergent; one elected lane issues each tcgen05 instruction) =====
     const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
-    const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_DH, 0, 1);
+    const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_PV_N, 0, 1);
     const uint64_t kd = smem_desc_k_sw128(smem_u32(sK));
-    const uint64_t vd0 = smem_desc_mn_sw128(smem_u32(sV), 1024);
+    const uint64_t vd0 = smem_desc_mn_sw128(smem_u32(sV), AT_OFF_ONES - AT_OFF_V);   // MN block 1 (columns 64..79) = the ones tile
     const int n_ksteps = p.nk_pad / 16;
     auto issue_s = [&](int t) {               // S_t = Q_t · K^T
       const uint64_t qd = smem_desc_k_sw128(smem_u32(sQ + t * AT_BM * 128));
@@ -221,13 +231,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&s_full[t], par);
         tc_fence_after_sync();
         AT_TRACE(1);
-        float sum = 0.f;
         if (active) {
           // ---- single pass over S: online softmax per 16-key unit, P kept in registers (bf16 pairs) ----
           uint32_t pk[kMaxUnits][8];
           float mrec[kMaxUnits];                     // the running maximum each unit was exponentiated against
           uint32_t va[16], vb[16];
-          float M = -1.0e30f, l = 0.f;               // running integer-valued max of s*scale*log2e; running row sum
+          float M = -1.0e30f;                        // running integer-valued max of s*scale*log2e
           auto unit = [&](uint32_t (&v)[16], uint32_t (&pu)[8], float& mr, int c0, bool last) {
             if (last) {                               // keys beyond Lk (padding of the last unit) drop out as -inf
 #pragma unroll
@@ -241,7 +250,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               m1 = max3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
             const float Mn = fmaxf(M, ceilf(fmaxf(m0, m1) * sc));
-            const float corr = ex2_approx(M - Mn);   // exact power of two (0 on the first unit)
             M = Mn;
             mr = Mn;
             float e[16];
@@ -250,9 +258,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const float xj = fmaf(__uint_as_float(v[j]), sc, -Mn);
               e[j] = (kPolyMask >> j) & 1 ? ex2_poly(xj) : ex2_approx(xj);
             }
-            const float cs = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7])) +
-                             (((e[8] + e[9]) + (e[10] + e[11])) + ((e[12] + e[13]) + (e[14] + e[15])));
-            l = fmaf(l, corr, cs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) pu[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
           };
@@ -287,7 +292,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               tmem_st_32x8(taddr + (uint32_t)(u * 8), pk[u]);
             }
           }
-          sum = l;
           tmem_st_wait();
         }
         tc_fence_before_sync();         // our TMEM reads of S / writes of P are ordered before the PV MMAs
@@ -298,12 +302,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&o_full[t], par);
         tc_fence_after_sync();
         AT_TRACE(4);
-        uint32_t oa[32], ob[32];
+        uint32_t oa[32], ob[32], osum = 0x3F800000u;
         if (active) {
           tmem_ld_32x32(taddr + AT_O_COL, oa);
           tmem_ld_32x32(taddr + AT_O_COL + 32u, ob);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(osum) : "r"(taddr + AT_O_COL + 64u) : "memory");   // row sum of P
           tmem_ld_wait32(oa);
           tmem_ld_wait32(ob);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(osum)::"memory");
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -312,7 +318,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (active) {
           if (lane == 0) bulk_wait_read<0>();            // the previous item's output tile has left the staging buffer
           __syncwarp();
-          const float inv = 1.0f / sum;
+          const float inv = 1.0f / __uint_as_float(osum);
           auto f = [&](uint32_t u) { return __uint_as_float(u) * inv; };
           const uint32_t srow = stg + lane * 128;
           if (p.out_f32 == 1) {
