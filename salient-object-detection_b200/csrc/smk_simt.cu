@@ -153,15 +153,18 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* row3, int D, int e, 
   *reinterpret_cast<uint2*>(row3 + 2 * D + e) = lo;
 }
 
+// 128-thread CTAs (4 rows): 5120 rows = 1280 CTAs fit in ONE resident wave (9 CTAs per SM x 148); with 256-thread CTAs the 640
+// CTAs needed 1.08 waves of the 592 slots, i.e. a second, almost empty wave doubled the latency of this latency-bound kernel
+constexpr int DLN_THREADS = 128;
 template <int kChunks>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DLN_THREADS)
 dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      const float* __restrict__ pos, int period, __nv_bfloat16* __restrict__ a3a, __nv_bfloat16* __restrict__ a3b,
                      const float* __restrict__ gamma2, const float* __restrict__ beta2, float* __restrict__ y2,
                      __nv_bfloat16* __restrict__ y2s, int64_t rows, int D) {
   pdl_wait();
   pdl_trigger();
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t row = (int64_t)blockIdx.x * (DLN_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   float4* xr = reinterpret_cast<float4*>(x + row * D);
@@ -228,12 +231,12 @@ int dec_layernorm(float* x, const float* res, const float* gamma, const float* b
   SMK_REQUIRE(D % 128 == 0 && D <= 512, "dec_layernorm: D=%d must be a multiple of 128 and <= 512", D);
   SMK_REQUIRE(!a3b || (pos && period > 0), "dec_layernorm: a3b needs the query positions");
   if (rows == 0) return SMK_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const unsigned grid = (unsigned)((rows + DLN_THREADS / 32 - 1) / (DLN_THREADS / 32));
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (8.0 + (res ? 4.0 : 0.0) + (a3a ? 6.0 : 0.0) + (a3b ? 6.0 : 0.0) + (y2 ? 4.0 : 0.0) +
                                                      (y2s ? 6.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_DLN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(DLN_THREADS), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D)); break;
     SMK_DLN_CASE(1) SMK_DLN_CASE(2) SMK_DLN_CASE(3) SMK_DLN_CASE(4)
 #undef SMK_DLN_CASE
   }
