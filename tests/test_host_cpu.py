@@ -238,3 +238,49 @@ def test_saliency_folder_reader_pairs_resizes_and_shards(tmp_path):
     assert names[0] + names[1] == [f"im_{i:03d}.jpg" for i in range(n)] and len(names[0]) == 4
     with pytest.raises(S.SmkError):
         S.SaliencyFolder(str(tmp_path), "coco")
+
+
+def _bf16_round(x):
+    """float32 → bf16 (round to nearest even) → float32, in numpy."""
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_attention_online_softmax_scheme_matches_direct_softmax():
+    """The encoder attention kernel (smk_attn_tc.cu) reads S once: every 16-key unit is exponentiated against the running
+    row maximum rounded UP to an integer (log2 domain), kept as bf16, and corrected at the end by 2^(M_unit - M_final) — an
+    exact power of two, so the corrected bf16 P equals bf16(exp2(x - M_final)) bit for bit; the row sum is the sum of the
+    bf16 P (taken from the tensor core through a ones column).  Emulated here in numpy against the direct definition."""
+    rng = np.random.default_rng(5)
+    n_keys, scale_log2e = 197, 0.125 * 1.4426950408889634
+    s = (rng.standard_normal((64, n_keys)) * rng.uniform(1, 60, (64, 1))).astype(np.float32)      # rows with very different spreads
+    x = (s * np.float32(scale_log2e)).astype(np.float32)
+    units = [np.arange(u, min(u + 16, n_keys)) for u in range(0, n_keys, 16)]
+    M = np.full(64, -1e30, np.float32)
+    p_units, m_units = [], []
+    for cols in units:
+        M = np.maximum(M, np.ceil(x[:, cols].max(1)))
+        m_units.append(M.copy())
+        p_units.append(_bf16_round(np.exp2((x[:, cols] - M[:, None]).astype(np.float32))))
+    p = np.concatenate([_bf16_round(pu * np.exp2(mu - M)[:, None]) for pu, mu in zip(p_units, m_units)], axis=1)
+    direct = _bf16_round(np.exp2((x - M[:, None]).astype(np.float32)))
+    assert np.array_equal(p, direct)                      # the power-of-two correction adds no second rounding
+    assert (M >= x.max(1)).all() and (M < x.max(1) + 1).all()
+    probs = p / p.sum(1, keepdims=True)
+    ref = np.exp(s.astype(np.float64) * 0.125)
+    ref /= ref.sum(1, keepdims=True)
+    assert np.abs(probs - ref).max() <= 4e-3              # bf16 P: half an ulp of values <= 1
+
+
+def test_exp2_polynomial_of_the_attention_kernel():
+    """ex2_poly (smk_attn_tc.cu; compiled out by default): round-to-nearest split through the 1.5*2^23 magic constant, degree-3
+    minimax of 2^f on [-0.5, 0.5], exponent added with a shift — relative error below 1e-4 on the whole range the kernel clamps to."""
+    x = np.linspace(-125, 0, 1_000_001).astype(np.float32)
+    t = (x + np.float32(12582912.0)).astype(np.float32)
+    f = (x - (t - np.float32(12582912.0))).astype(np.float32)
+    p = np.float32(0.0551716648) * f + np.float32(0.2426111251)
+    p = (p * f + np.float32(0.6932609677)).astype(np.float32)
+    p = (p * f + np.float32(0.9999280572)).astype(np.float32)
+    r = (p.view(np.int32) + (t.view(np.int32) << 23)).view(np.float32)
+    assert np.abs(r / np.exp2(x.astype(np.float64)) - 1).max() <= 1e-4
