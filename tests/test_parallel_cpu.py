@@ -36,3 +36,57 @@ def test_allreduce_records_is_an_exact_gather(tmp_path):
     got = [np.load(tmp_path / f"ok_{r}.npy") for r in range(world)]
     assert all(g[0] == 1 for g in got)
     assert sum(int(g[1]) for g in got) == n_total
+
+
+def _sweep_worker(rank, world, port, n_total, out_dir):
+    """BASELINE.json configs[4] in miniature: every rank evaluates its contiguous shard of a dataset sweep (here: records of
+    small synthetic masks built with the numpy emulation of the GPU record layout), all-reduces the per-image rows once, and
+    must arrive at exactly the 14 averages a single process computes over the whole sweep in dataset order."""
+    from tests.helpers import numpy_record
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def record(i):                                        # image i of the sweep: 2 evaluated masks (selected, upper bound)
+        rng = np.random.default_rng(1000 + i)
+        gt = np.zeros((24, 20), bool)
+        if i % 7 != 3:                                    # every 7th ground truth is empty (reference edge case)
+            y0, x0 = rng.integers(0, 12), rng.integers(0, 10)
+            gt[y0:y0 + rng.integers(4, 12), x0:x0 + rng.integers(4, 10)] = True
+        recs = [numpy_record(rng.random((24, 20), dtype=np.float32), gt) for _ in range(2)]
+        return np.stack([r[0] for r in recs]), np.stack([r[1] for r in recs])
+
+    a, b = S.shard_range(n_total, rank, world)
+    mine = [record(i) for i in range(a, b)]
+    lc = torch.from_numpy(np.stack([m[0] for m in mine]).astype(np.int32)) if mine else torch.zeros((0, 2, 528), dtype=torch.int32)
+    ls = torch.from_numpy(np.stack([m[1] for m in mine])) if mine else torch.zeros((0, 2, 32), dtype=torch.float64)
+    full_c, full_s = S.allreduce_records(lc, ls, a, n_total)
+    res = S.summarize(full_c.numpy(), full_s.numpy())
+    if rank == 0:                                          # single-process truth over the whole sweep
+        allr = [record(i) for i in range(n_total)]
+        ref = S.summarize(np.stack([m[0] for m in allr]).astype(np.int32), np.stack([m[1] for m in allr]))
+        same = all((np.isnan(res[k]) and np.isnan(ref[k])) or res[k] == ref[k] for k in ref)
+        np.save(os.path.join(out_dir, "sweep_ok.npy"), np.array([same, len(ref)]))
+    keys = sorted(res)
+    mine_vals = torch.tensor([res[k] for k in keys], dtype=torch.float64)
+    gathered = [torch.zeros_like(mine_vals) for _ in range(world)]
+    dist.all_gather(gathered, mine_vals)
+    agree = all(torch.equal(torch.nan_to_num(g, nan=-1.0), torch.nan_to_num(gathered[0], nan=-1.0)) for g in gathered)
+    np.save(os.path.join(out_dir, f"agree_{rank}.npy"), np.array([agree]))
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_gives_the_single_process_averages(tmp_path):
+    world, n_total = 2, 37                                 # odd count: the last rank gets the shorter shard
+    mp.spawn(_sweep_worker, args=(world, _free_port(), n_total, str(tmp_path)), nprocs=world, join=True)
+    ok = np.load(tmp_path / "sweep_ok.npy")
+    assert ok[0] == 1 and ok[1] == 14
+    assert all(np.load(tmp_path / f"agree_{r}.npy")[0] == 1 for r in range(world))
+
+
+def test_shard_ranges_of_the_duts_te_sweep():
+    """5019 images over 8 ranks (configs[4]): contiguous, disjoint, complete, at most one image of imbalance per rank pair."""
+    spans = [S.shard_range(5019, r, 8) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == 5019
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) == 628 and min(sizes) >= 623
