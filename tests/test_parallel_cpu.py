@@ -84,7 +84,7 @@ def test_sharded_sweep_gives_the_single_process_averages(tmp_path):
 
 
 def test_shard_ranges_of_the_duts_te_sweep():
-    """5019 images over 8 ranks (configs[4]): contiguous, disjoint, complete, at most one image of imbalance per rank pair."""
+    """5019 images over 8 ranks (configs[4]): contiguous, disjoint, complete; ceil(n / W) = 628 per rank, the last rank takes the remaining 623."""
     spans = [S.shard_range(5019, r, 8) for r in range(8)]
     assert spans[0][0] == 0 and spans[-1][1] == 5019
     assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
