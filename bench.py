@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--nq", type=int, default=20)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["fp16s", "bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the extra bf16x3-mode figure")
     ap.add_argument("--cpu-sample", type=int, default=256, help="images in the bounded CPU-baseline sample")

@@ -42,8 +42,12 @@ typedef enum {
 /* numeric modes */
 enum { SMK_MODE_FP32 = 0,  /* validation: every contraction in fp32 on CUDA cores          */
        SMK_MODE_BF16 = 1,  /* throughput: tcgen05 bf16 operands, fp32 accumulate/residual/LN */
-       SMK_MODE_BF16X3 = 2 /* parity on tensor cores: every GEMM as a 3-term bf16 split (hi·hi + hi·lo + lo·hi, K' = 3K) on
-                              tcgen05 with fp32 accumulate; LayerNorm / softmax attention / residual in fp32 */ };
+       SMK_MODE_BF16X3 = 2,/* parity on tensor cores: every GEMM as a 3-term bf16 split (hi·hi + hi·lo + lo·hi, K' = 3K) on
+                              tcgen05 with fp32 accumulate; LayerNorm / softmax attention / residual in fp32 */
+       SMK_MODE_FP16S = 3  /* parity AND throughput (the benchmarked mode): fp16 tcgen05 operands with as many split terms per
+                              contraction as the 2e-2 logit budget needs (patch embed / proj / fc1 / fc2: 3 terms on [hi | lo] operands;
+                              qkv, memory K/V: A_hi·(W_hi + W_lo); encoder attention: single-pass fp16 on tcgen05; decoder self-attention
+                              fp32; decoder tail as in SMK_MODE_BF16), fp32 accumulate / residual / LayerNorm / softmax */ };
 
 typedef struct {
   int32_t patch;        /* 16 (or 8)                                    */
@@ -72,6 +76,11 @@ int smk_prof_read(double* ms, double* work, int64_t* launches);
 /* per-launch timeline of the recorded launches in launch order (tuning aid): duration, category and start time relative to the
  * first recorded launch; returns the number of entries written (<= cap) or a negative status */
 int smk_prof_timeline(float* ms, int* cat, float* start_ms, int cap);
+/* the same with each launch's sub-category tag (1 patch embed, 2 qkv, 3 encoder attention, 4 proj, 5 fc1, 6 fc2, 7 encoder LayerNorm,
+ * 8 memory K/V, 9 decoder GEMM, 10 decoder attention, 11 decoder LayerNorm, 12 mask logits, 13 mask upsample, 14 objectness,
+ * 15 per-query IoU, 16 mask metrics, 17 im2col, 0 other), its ALGORITHMIC work (FLOPs or bytes) and the work it issued (split
+ * GEMMs issue 2-3 tensor-core terms per algorithmic FLOP) */
+int smk_prof_timeline2(float* ms, int* cat, int* tag, double* work, double* issued, int cap);
 
 /* ---- weights: one fp32 device blob in a canonical order --------------------------------------
  * The table maps the reference's state_dict keys (SURVEY.md §8b, 267 tensors) to blob offsets. */
@@ -164,6 +173,12 @@ int smk_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias,
  * K % 64 == 0, N % 128 == 0. */
 int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, void* C, int64_t ldc,
                   int M, int N, int K, int epilogue, int out_f32, void* stream);
+/* Split-operand tcgen05 GEMM: C[M,N] = sum over t < n_terms of A[:, a_off[t] : a_off[t]+K] · W[:, w_off[t] : w_off[t]+K]^T + bias.
+ * A [M, lda], W [N, ldw]: 16-bit operands (bf16, or fp16 when f16 != 0), offsets in elements (multiples of 64).  With operands
+ * stored as [hi | lo] rows, terms (0,0),(0,K),(K,0) give the ~fp32 3-term product, (0,0),(0,K) removes the weight rounding only.
+ * out_kind: 0 16-bit (same type as the operands), 1 fp32, 2 split [hi | hi | lo] (3N columns), 3 split [hi | lo] (2N columns). */
+int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                   int epilogue, int out_kind, int f16, int n_terms, const int32_t* a_off, const int32_t* w_off, void* stream);
 /* y = LN(x) * gamma + beta over the last dim D (fp32 statistics).  out_bf16 selects the output type. */
 int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
                   int out_bf16, void* stream);
@@ -175,6 +190,9 @@ int smk_attention(const void* q, const void* k, const void* v, void* o, int batc
 /* tcgen05 fused self-attention on the fused-QKV layout: qkv [B*N, 3*heads*64] bf16 (q|k|v), out [B*N, heads*64] bf16;
  * N <= 256 tokens per image (one key tile). */
 int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream);
+/* fp16 form of smk_attention_tc (fp16s mode): qkv / out fp16; out_mode 0 → out [B*N, ldo >= heads*64],
+ * 3 → [hi | lo] split rows (ldo >= 2*heads*64): the A operand of a 3-term smk_gemm_split */
+int smk_attention_tc_f16(const void* qkv, void* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, void* stream);
 /* general form: q [B*Lq, ldq], k / v [kv_total_rows, ld] bf16 (head h at columns [h*64, h*64+64) of each pointer); image b's
  * queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0; out [B*Lq, ldo]: out_f32 0 = bf16, 1 = fp32,
  * 2 = bf16x3 split ([hi | hi | lo], 3*heads*64 columns). */
@@ -190,6 +208,15 @@ int smk_debug_gemm_trace(long long* buf);   /* tuning aid: per-CTA wait-cycle co
  * out_mode: 0 bf16 [B*Lq, heads*64], 1 fp32, 2 bf16x3 split [hi | hi | lo] (3*heads*64 columns). */
 int smk_attention_small(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_rows,
                         int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale, void* stream);
+
+/* the same with fp16 k / v; q fp16, or fp32 rows (ldq in floats) when q_f32 != 0 — rounded to fp16 as it is staged.  Outputs as above. */
+int smk_attention_small_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_rows,
+                            int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
+                            int q_f32, void* stream);
+/* Decoder self-attention in fp32 on the CUDA cores (nq <= 32 queries = keys per image): qk [B*nq, ldqk] fp32 with q in columns
+ * [0, heads*64) and k in [heads*64, 2*heads*64), v [B*nq, ldv] fp32 → out3 [B*nq, 3*heads*64] bf16 split [hi | hi | lo]. */
+int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, void* out3, int B, int nq, int heads,
+                           float scale, void* stream);
 
 /* Online-softmax attention (64 queries x 64-key blocks per step, mma.sync) for any sequence length: 384x384 images (577 tokens),
  * ViT-S/8 (785 tokens) and, with q_lo / k_lo / v_lo non-NULL, the bf16x3 split mode (3-term products, ~fp32 accuracy).

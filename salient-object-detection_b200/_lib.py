@@ -11,7 +11,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMK_LIB_PATH") or os.path.join(HERE, "libselfmask_b200.so")   # override: A/B runs of two builds (tuning)
 
-SMK_MODE_FP32, SMK_MODE_BF16, SMK_MODE_BF16X3 = 0, 1, 2
+SMK_MODE_FP32, SMK_MODE_BF16, SMK_MODE_BF16X3, SMK_MODE_FP16S = 0, 1, 2, 3
 EPI_NONE, EPI_GELU, EPI_RELU, EPI_RESIDUAL = 0, 1, 2, 4
 QCOUNT_STRIDE, MCOUNT_STRIDE, MSUM_STRIDE = 2, 528, 32
 
@@ -34,6 +34,7 @@ SIGNATURES = {
     "smk_prof_enable": (_I, [_I]),
     "smk_prof_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L)]),
     "smk_prof_timeline": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), _I]),
+    "smk_prof_timeline2": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), _I]),
     "smk_model_debug_logits": (_I, [_P, _P]),
     "smk_weight_count": (_I, [C.POINTER(SmkConfig)]),
     "smk_weight_entry": (_I, [C.POINTER(SmkConfig), _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_L)]),
@@ -50,6 +51,10 @@ SIGNATURES = {
     "smk_upsample_bilinear": (_I, [_P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_gemm_f32": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "smk_gemm_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "smk_gemm_split": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "smk_attention_tc_f16": (_I, [_P, _P, _L, _I, _I, _I, _I, _F, _P]),
+    "smk_attention_small_f16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, C.c_float, _I, _P]),
+    "smk_dec_self_attention": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _F, _P]),
     "smk_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "smk_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P]),
     "smk_attention_tc": (_I, [_P, _P, _I, _I, _I, _F, _P]),

@@ -6,6 +6,8 @@
 //     attention is ~fp32-accurate while still running on tensor cores.
 // One CTA = 64 query rows of one (image, head), 4 warps x 16 rows; K / V blocks are double-buffered in shared memory with
 // 16-byte cp.async; S, the running max / sum and O stay in registers (mma.sync m16n8k16 bf16 → fp32).
+#include <type_traits>
+
 #include "smk_mma.cuh"
 
 namespace smk {
@@ -36,9 +38,11 @@ __device__ __forceinline__ void stage_tile(__nv_bfloat16* dst, const __nv_bfloat
   }
 }
 
-template <bool kSplit>
+// kF16 (without kSplit): q / k / v / P are fp16 instead of bf16 (fp16s mode); output modes 0 / 3 then write fp16
+template <bool kSplit, bool kF16>
 __global__ void __launch_bounds__(FA_THREADS)
 attn_fa_kernel(const AttnFaParams p) {
+  using T16 = typename std::conditional<kF16, __half, __nv_bfloat16>::type;
   extern __shared__ __align__(16) uint8_t fa_smem[];
   constexpr int kParts = kSplit ? 2 : 1;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);    // [kParts][64][LD]
@@ -105,15 +109,15 @@ attn_fa_kernel(const AttnFaParams p) {
       for (int kp = 0; kp < 2; ++kp) {
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4((uint32_t)__cvta_generic_to_shared(kh + off) + kp * 64, b0, b1, b2, b3);
-        mma_bf16(s[n], qa[0][2 * kp][0], qa[0][2 * kp][1], qa[0][2 * kp][2], qa[0][2 * kp][3], b0, b1);
-        mma_bf16(s[n], qa[0][2 * kp + 1][0], qa[0][2 * kp + 1][1], qa[0][2 * kp + 1][2], qa[0][2 * kp + 1][3], b2, b3);
+        mma_16<kF16>(s[n], qa[0][2 * kp][0], qa[0][2 * kp][1], qa[0][2 * kp][2], qa[0][2 * kp][3], b0, b1);
+        mma_16<kF16>(s[n], qa[0][2 * kp + 1][0], qa[0][2 * kp + 1][1], qa[0][2 * kp + 1][2], qa[0][2 * kp + 1][3], b2, b3);
         if constexpr (kSplit) {
           // q_lo · k_hi (same B fragments), then q_hi · k_lo
-          mma_bf16(s[n], qa[1][2 * kp][0], qa[1][2 * kp][1], qa[1][2 * kp][2], qa[1][2 * kp][3], b0, b1);
-          mma_bf16(s[n], qa[1][2 * kp + 1][0], qa[1][2 * kp + 1][1], qa[1][2 * kp + 1][2], qa[1][2 * kp + 1][3], b2, b3);
+          mma_16<kF16>(s[n], qa[1][2 * kp][0], qa[1][2 * kp][1], qa[1][2 * kp][2], qa[1][2 * kp][3], b0, b1);
+          mma_16<kF16>(s[n], qa[1][2 * kp + 1][0], qa[1][2 * kp + 1][1], qa[1][2 * kp + 1][2], qa[1][2 * kp + 1][3], b2, b3);
           ldmatrix_x4((uint32_t)__cvta_generic_to_shared(kh + FA_TILE + off) + kp * 64, b0, b1, b2, b3);
-          mma_bf16(s[n], qa[0][2 * kp][0], qa[0][2 * kp][1], qa[0][2 * kp][2], qa[0][2 * kp][3], b0, b1);
-          mma_bf16(s[n], qa[0][2 * kp + 1][0], qa[0][2 * kp + 1][1], qa[0][2 * kp + 1][2], qa[0][2 * kp + 1][3], b2, b3);
+          mma_16<kF16>(s[n], qa[0][2 * kp][0], qa[0][2 * kp][1], qa[0][2 * kp][2], qa[0][2 * kp][3], b0, b1);
+          mma_16<kF16>(s[n], qa[0][2 * kp + 1][0], qa[0][2 * kp + 1][1], qa[0][2 * kp + 1][2], qa[0][2 * kp + 1][3], b2, b3);
         }
       }
     }
@@ -161,24 +165,24 @@ attn_fa_kernel(const AttnFaParams p) {
         pack2_split(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
         pack2_split(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
       } else {
-        ph[0] = pack2(s[2 * j][0], s[2 * j][1]);
-        ph[1] = pack2(s[2 * j][2], s[2 * j][3]);
-        ph[2] = pack2(s[2 * j + 1][0], s[2 * j + 1][1]);
-        ph[3] = pack2(s[2 * j + 1][2], s[2 * j + 1][3]);
+        ph[0] = Pack16<T16>::pack(s[2 * j][0], s[2 * j][1]);
+        ph[1] = Pack16<T16>::pack(s[2 * j][2], s[2 * j][3]);
+        ph[2] = Pack16<T16>::pack(s[2 * j + 1][0], s[2 * j + 1][1]);
+        ph[3] = Pack16<T16>::pack(s[2 * j + 1][2], s[2 * j + 1][3]);
       }
       const int off = (16 * j + (lane & 15)) * FA_LD + (lane >> 4) * 8;
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4_trans((uint32_t)__cvta_generic_to_shared(vh + off) + dp * 32, b0, b1, b2, b3);
-        mma_bf16(o[2 * dp], ph[0], ph[1], ph[2], ph[3], b0, b1);
-        mma_bf16(o[2 * dp + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
+        mma_16<kF16>(o[2 * dp], ph[0], ph[1], ph[2], ph[3], b0, b1);
+        mma_16<kF16>(o[2 * dp + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
         if constexpr (kSplit) {
-          mma_bf16(o[2 * dp], pl[0], pl[1], pl[2], pl[3], b0, b1);
-          mma_bf16(o[2 * dp + 1], pl[0], pl[1], pl[2], pl[3], b2, b3);
+          mma_16<kF16>(o[2 * dp], pl[0], pl[1], pl[2], pl[3], b0, b1);
+          mma_16<kF16>(o[2 * dp + 1], pl[0], pl[1], pl[2], pl[3], b2, b3);
           ldmatrix_x4_trans((uint32_t)__cvta_generic_to_shared(vh + FA_TILE + off) + dp * 32, b0, b1, b2, b3);
-          mma_bf16(o[2 * dp], ph[0], ph[1], ph[2], ph[3], b0, b1);
-          mma_bf16(o[2 * dp + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
+          mma_16<kF16>(o[2 * dp], ph[0], ph[1], ph[2], ph[3], b0, b1);
+          mma_16<kF16>(o[2 * dp + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
         }
       }
     }
@@ -204,32 +208,35 @@ attn_fa_kernel(const AttnFaParams p) {
       const int col = h * FA_DH + 8 * d + 2 * t;
       if (p.out_mode == 1) {
         *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + grow * p.ldo + col) = make_float2(x0, x1);
-      } else {
+      } else if (p.out_mode == 2) {     // bf16 split [hi | hi | lo] whatever the operand type (decoder out-projection input)
         __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldo + col;
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(x0, x1);
-        *reinterpret_cast<__nv_bfloat162*>(orow) = hi;
-        if (p.out_mode == 2) {
-          const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - __low2float(hi), x1 - __high2float(hi));
-          *reinterpret_cast<__nv_bfloat162*>(orow + D) = hi;
-          *reinterpret_cast<__nv_bfloat162*>(orow + 2 * D) = lo;
-        }
+        uint32_t hi, lo;
+        split16x2<__nv_bfloat16>(x0, x1, hi, lo);
+        *reinterpret_cast<uint32_t*>(orow) = hi;
+        *reinterpret_cast<uint32_t*>(orow + D) = hi;
+        *reinterpret_cast<uint32_t*>(orow + 2 * D) = lo;
+      } else {                          // 0: 16-bit (operand type), 3: [hi | lo] split in the operand type
+        T16* orow = reinterpret_cast<T16*>(p.out) + grow * p.ldo + col;
+        uint32_t hi, lo;
+        split16x2<T16>(x0, x1, hi, lo);
+        *reinterpret_cast<uint32_t*>(orow) = hi;
+        if (p.out_mode == 3) *reinterpret_cast<uint32_t*>(orow + D) = lo;
       }
     }
   }
 }
 
-template <bool kSplit>
+template <bool kSplit, bool kF16>
 int launch_fa(const AttnFaParams& p, int B, cudaStream_t s) {
   const size_t smem = (size_t)(kSplit ? 2 : 1) * 5 * FA_TILE * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  static DeviceOnce attr_set;
+  if (smem > 48 * 1024 && attr_set.first()) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<kSplit, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   {
     // tensor work actually issued: 3 MMAs per product in split mode; credited as the algorithmic 4·Lq·Lk·64 FLOP
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * p.Lq * p.Lk * FA_DH * p.heads * B, s);
-    SMK_CHECK_CUDA(launch_pdl(attn_fa_kernel<kSplit>, dim3((unsigned)((p.Lq + FA_BM - 1) / FA_BM), (unsigned)(B * p.heads)), dim3(FA_THREADS), smem, s, p));
+    SMK_CHECK_CUDA(launch_pdl(attn_fa_kernel<kSplit, kF16>, dim3((unsigned)((p.Lq + FA_BM - 1) / FA_BM), (unsigned)(B * p.heads)), dim3(FA_THREADS), smem, s, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -241,18 +248,21 @@ int launch_fa(const AttnFaParams& p, int B, cudaStream_t s) {
 // b*kv_rows + kv_row0 .. +Lk.  q_lo / k_lo / v_lo non-null → bf16x3 split mode (same leading dimensions as the hi parts).
 int attention_fa(const __nv_bfloat16* q, const __nv_bfloat16* q_lo, int64_t ldq, const __nv_bfloat16* k, const __nv_bfloat16* k_lo, int64_t ldk,
                  const __nv_bfloat16* v, const __nv_bfloat16* v_lo, int64_t ldv, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo,
-                 int out_mode, int B, int Lq, int Lk, int heads, float scale, cudaStream_t s) {
+                 int out_mode, int B, int Lq, int Lk, int heads, float scale, cudaStream_t s, int f16) {
   const bool split = q_lo != nullptr;
+  SMK_REQUIRE(!(split && f16), "attention_fa: the split form takes bf16 parts");
   SMK_REQUIRE(Lq >= 1 && Lk >= 1 && B >= 1 && heads >= 1 && (int64_t)B * heads <= 65535, "attention_fa: bad sizes (B*heads <= 65535)");
   SMK_REQUIRE(split == (k_lo != nullptr) && split == (v_lo != nullptr), "attention_fa: give all three lo parts or none");
-  SMK_REQUIRE(out_mode >= 0 && out_mode <= 2 && (out_mode != 2 || ldo >= 3 * (int64_t)heads * FA_DH), "attention_fa: bad output mode / ldo");
+  SMK_REQUIRE(out_mode >= 0 && out_mode <= 3 && (out_mode != 2 || ldo >= 3 * (int64_t)heads * FA_DH) && (out_mode != 3 || ldo >= 2 * (int64_t)heads * FA_DH),
+              "attention_fa: bad output mode / ldo");
   SMK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "attention_fa: leading dimensions must be multiples of 8");
   for (const void* ptr_ : {(const void*)q, (const void*)q_lo, (const void*)k, (const void*)k_lo, (const void*)v, (const void*)v_lo})
     SMK_REQUIRE(((uintptr_t)ptr_ % 16) == 0, "attention_fa: operands must be 16-byte aligned");
   SMK_REQUIRE(ldo % 2 == 0 && ((uintptr_t)out % 8) == 0, "attention_fa: output must be 8-byte aligned with an even row stride");
   AttnFaParams p{q, q_lo, k, k_lo, v, v_lo, out, ldq, ldk, ldv, ldo, Lq, Lk, q_rows, kv_rows, kv_row0, heads, out_mode,
                  scale * 1.4426950408889634f};
-  return split ? launch_fa<true>(p, B, s) : launch_fa<false>(p, B, s);
+  if (f16) return launch_fa<false, true>(p, B, s);
+  return split ? launch_fa<true, false>(p, B, s) : launch_fa<false, false>(p, B, s);
 }
 
 }  // namespace smk
@@ -263,5 +273,5 @@ extern "C" int smk_attention_fa(const void* q, const void* q_lo, int64_t ldq, co
   SMK_REQUIRE(q && k && v && out, "smk_attention_fa: null pointer");
   return smk::attention_fa((const __nv_bfloat16*)q, (const __nv_bfloat16*)q_lo, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)k_lo, ldk,
                            (const __nv_bfloat16*)v, (const __nv_bfloat16*)v_lo, ldv, q_rows, kv_rows, kv_row0, out, ldo, out_mode, B, Lq, Lk,
-                           heads, scale, (cudaStream_t)stream);
+                           heads, scale, (cudaStream_t)stream, 0);
 }

@@ -9,6 +9,8 @@
 //   softmax     in registers (quad shuffles), exp2 with the scale folded in
 //   O = P·V     P re-used straight from the S accumulator fragments (bf16), V fragments by ldmatrix.trans
 // 1536 CTAs, 3 per SM: the op becomes HBM-bound on the K/V read (77 MB per layer).
+#include <type_traits>
+
 #include "smk_mma.cuh"
 
 namespace smk {
@@ -26,12 +28,15 @@ struct AttnSmallParams {
   int64_t ldq, ldk, ldv, ldo;
   int Lq, Lk, kv_rows, kv_row0, heads, out_mode;   // out_mode: 0 bf16, 1 fp32, 2 bf16x3 split [hi | hi | lo]
   float scale_log2e;
+  int q_f32;                                       // q points to fp32 rows (ldq in floats); rounded to the operand type when staged
 };
 
 // NT = number of 8-key score tiles held in registers (keys padded to 8*NT, a multiple of 16)
-template <int NT>
+// kF16: q / k / v (and P) are fp16 instead of bf16 (fp16s mode: 11 significant bits; the outputs stay bf16 / fp32 / bf16 split)
+template <int NT, bool kF16>
 __global__ void __launch_bounds__(AS_THREADS)
 attn_small_kernel(const AttnSmallParams p) {
+  using T16 = typename std::conditional<kF16, __half, __nv_bfloat16>::type;
   extern __shared__ __align__(16) uint8_t as_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(as_smem);   // [32][AS_LD]
   __nv_bfloat16* sK = sQ + AS_MAXQ * AS_LD;                         // [8*NT][AS_LD]
@@ -44,12 +49,25 @@ attn_small_kernel(const AttnSmallParams p) {
 
   // ---- stage Q, K, V (rows beyond the valid ones are zero: they add 0 to every dot product) ----
   {
-    const __nv_bfloat16* qg = p.q + (int64_t)b * p.Lq * p.ldq + h * AS_DH;
-    for (int i = tid; i < AS_MAXQ * 8; i += AS_THREADS) {
-      const int r = i >> 3, c = i & 7;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sQ + r * AS_LD + c * 8);
-      if (r < p.Lq) cp_async16(dst, qg + (int64_t)r * p.ldq + c * 8);
-      else *reinterpret_cast<uint4*>(sQ + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
+    if (p.q_f32) {
+      const float* qg = reinterpret_cast<const float*>(p.q) + (int64_t)b * p.Lq * p.ldq + h * AS_DH;
+      for (int i = tid; i < AS_MAXQ * 8; i += AS_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (r < p.Lq) {
+          const float4 a = *reinterpret_cast<const float4*>(qg + (int64_t)r * p.ldq + c * 8), bq = *reinterpret_cast<const float4*>(qg + (int64_t)r * p.ldq + c * 8 + 4);
+          u = make_uint4(Pack16<T16>::pack(a.x, a.y), Pack16<T16>::pack(a.z, a.w), Pack16<T16>::pack(bq.x, bq.y), Pack16<T16>::pack(bq.z, bq.w));
+        }
+        *reinterpret_cast<uint4*>(sQ + r * AS_LD + c * 8) = u;
+      }
+    } else {
+      const __nv_bfloat16* qg = p.q + (int64_t)b * p.Lq * p.ldq + h * AS_DH;
+      for (int i = tid; i < AS_MAXQ * 8; i += AS_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sQ + r * AS_LD + c * 8);
+        if (r < p.Lq) cp_async16(dst, qg + (int64_t)r * p.ldq + c * 8);
+        else *reinterpret_cast<uint4*>(sQ + r * AS_LD + c * 8) = make_uint4(0, 0, 0, 0);
+      }
     }
     const int64_t kv_row = (int64_t)b * p.kv_rows + p.kv_row0;
     const __nv_bfloat16* kg = p.k + kv_row * p.ldk + h * AS_DH;
@@ -95,8 +113,8 @@ attn_small_kernel(const AttnSmallParams p) {
     for (int kp = 0; kp < 2; ++kp) {
       uint32_t b0, b1, b2, b3;
       ldmatrix_x4(base + kp * 64, b0, b1, b2, b3);
-      mma_bf16(s[n], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
-      mma_bf16(s[n], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+      mma_16<kF16>(s[n], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+      mma_16<kF16>(s[n], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
     }
   }
 
@@ -138,16 +156,16 @@ attn_small_kernel(const AttnSmallParams p) {
   for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
   for (int j = 0; j < NT / 2; ++j) {
-    const uint32_t a0 = pack2(s[2 * j][0], s[2 * j][1]), a1 = pack2(s[2 * j][2], s[2 * j][3]);
-    const uint32_t a2 = pack2(s[2 * j + 1][0], s[2 * j + 1][1]), a3 = pack2(s[2 * j + 1][2], s[2 * j + 1][3]);
+    const uint32_t a0 = Pack16<T16>::pack(s[2 * j][0], s[2 * j][1]), a1 = Pack16<T16>::pack(s[2 * j][2], s[2 * j][3]);
+    const uint32_t a2 = Pack16<T16>::pack(s[2 * j + 1][0], s[2 * j + 1][1]), a3 = Pack16<T16>::pack(s[2 * j + 1][2], s[2 * j + 1][3]);
     // ldmatrix.x4.trans: matrices (keys 16j.., dims 8d), (keys 16j+8.., dims 8d), (keys 16j.., dims 8d+8), (keys 16j+8.., dims 8d+8)
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(sV + (16 * j + (lane & 15)) * AS_LD + (lane >> 4) * 8);
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {
       uint32_t b0, b1, b2, b3;
       ldmatrix_x4_trans(base + dp * 32, b0, b1, b2, b3);
-      mma_bf16(o[2 * dp], a0, a1, a2, a3, b0, b1);
-      mma_bf16(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+      mma_16<kF16>(o[2 * dp], a0, a1, a2, a3, b0, b1);
+      mma_16<kF16>(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
     }
   }
 
@@ -181,17 +199,16 @@ attn_small_kernel(const AttnSmallParams p) {
   }
 }
 
-template <int NT>
+template <int NT, bool kF16>
 int launch_small(const AttnSmallParams& p, int B, cudaStream_t s) {
   const size_t smem = (size_t)(AS_MAXQ + 16 * NT) * AS_LD * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  static DeviceOnce attr_set;
+  if (smem > 48 * 1024 && attr_set.first()) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NT, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * p.Lq * p.Lk * AS_DH * p.heads * B, s);
-    SMK_CHECK_CUDA(launch_pdl(attn_small_kernel<NT>, dim3((unsigned)(B * p.heads)), dim3(AS_THREADS), smem, s, p));
+    SMK_CHECK_CUDA(launch_pdl(attn_small_kernel<NT, kF16>, dim3((unsigned)(B * p.heads)), dim3(AS_THREADS), smem, s, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -202,18 +219,24 @@ int launch_small(const AttnSmallParams& p, int B, cudaStream_t s) {
 // Same argument meaning as attention_tc_general (smk_attn_tc.cu); Lq <= 32, Lk <= 256.
 int attention_small(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
                     int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
-                    cudaStream_t s) {
+                    cudaStream_t s, int f16, int q_f32) {
   SMK_REQUIRE(Lq >= 1 && Lq <= AS_MAXQ && Lk >= 1 && Lk <= 256, "attention_small: Lq=%d (1..32) / Lk=%d (1..256) not supported", Lq, Lk);
   SMK_REQUIRE(B >= 1 && heads >= 1 && (int64_t)B * heads < (1 << 30), "attention_small: bad batch/heads");
   SMK_REQUIRE(out_mode >= 0 && out_mode <= 2 && (out_mode != 2 || ldo >= 3 * (int64_t)heads * AS_DH), "attention_small: bad output mode / ldo");
-  SMK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0,
+  SMK_REQUIRE(!q_f32 || ldq % 4 == 0, "attention_small: fp32 q rows must be 16-byte aligned");
+  SMK_REQUIRE((q_f32 || ldq % 8 == 0) && ldk % 8 == 0 && ldv % 8 == 0 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0,
               "attention_small: q/k/v rows must be 16-byte aligned");
   SMK_REQUIRE(ldo % 2 == 0 && ((uintptr_t)out % 8) == 0, "attention_small: output must be 8-byte aligned with an even row stride");
-  AttnSmallParams p{q, k, v, out, ldq, ldk, ldv, ldo, Lq, Lk, kv_rows, kv_row0, heads, out_mode, scale * 1.4426950408889634f};
+  AttnSmallParams p{q, k, v, out, ldq, ldk, ldv, ldo, Lq, Lk, kv_rows, kv_row0, heads, out_mode, scale * 1.4426950408889634f, q_f32};
   const int nt = (Lk + 15) / 16 * 2;
-  if (nt <= 4) return launch_small<4>(p, B, s);
-  if (nt <= 26) return launch_small<26>(p, B, s);
-  return launch_small<32>(p, B, s);
+  if (f16) {
+    if (nt <= 4) return launch_small<4, true>(p, B, s);
+    if (nt <= 26) return launch_small<26, true>(p, B, s);
+    return launch_small<32, true>(p, B, s);
+  }
+  if (nt <= 4) return launch_small<4, false>(p, B, s);
+  if (nt <= 26) return launch_small<26, false>(p, B, s);
+  return launch_small<32, false>(p, B, s);
 }
 
 }  // namespace smk
@@ -223,5 +246,14 @@ extern "C" int smk_attention_small(const void* q, int64_t ldq, const void* k, in
                                    void* stream) {
   SMK_REQUIRE(q && k && v && out, "smk_attention_small: null pointer");
   return smk::attention_small((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, kv_rows, kv_row0,
-                              out, ldo, out_mode, B, Lq, Lk, heads, scale, (cudaStream_t)stream);
+                              out, ldo, out_mode, B, Lq, Lk, heads, scale, (cudaStream_t)stream, 0, 0);
+}
+
+/* the same with fp16 q / k / v (outputs unchanged: bf16 / fp32 / bf16 split) */
+extern "C" int smk_attention_small_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int kv_rows,
+                                       int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
+                                       int q_f32, void* stream) {
+  SMK_REQUIRE(q && k && v && out, "smk_attention_small_f16: null pointer");
+  return smk::attention_small((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, kv_rows, kv_row0,
+                              out, ldo, out_mode, B, Lq, Lk, heads, scale, (cudaStream_t)stream, 1, q_f32);
 }

@@ -26,6 +26,8 @@
 //               warps, did not help for the same reason: profiles/r01_attention_tmem.md.)
 // TMEM slot t (256 columns): S in [0, nk), P packed in [0, nk/2) (written after the whole row is in registers), O in
 // [128, 192) (S columns consumed before the first P·V MMA is issued).
+#include <type_traits>
+
 #include "smk_tc.cuh"
 
 namespace smk {
@@ -100,10 +102,13 @@ __device__ long long* g_attn_trace = nullptr;
 // kMaxUnits: upper bound of the 16-key units per row; kExact: the row has exactly kMaxUnits units (13 = 193..208 keys: the
 // encoder's 197 tokens), so the unrolled softmax has no run-time guards and is one basic block that ptxas can software-pipeline
 // across units (warps issue in order: with a branch per unit the max → exp2 → sum chains of successive units ran back to back).
-template <int kMaxUnits, bool kExact>
+// kF16: fp16 operands (Q, K, V, P) instead of bf16 — 11 significant bits: the fp16s mode's encoder attention (single pass; its
+// contribution to the mask-logit error is 1.7e-3 of the 2e-2 budget, scripts/precision_emulation.py)
+template <int kMaxUnits, bool kExact, bool kF16>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
+  using T16 = typename std::conditional<kF16, __half, __nv_bfloat16>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -128,8 +133,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, AT_TMEM_COLS);
-  for (int i = threadIdx.x; i < AT_KV_BYTES / 16; i += AT_THREADS)      // bf16 1.0 everywhere (uniform, so the swizzle does not matter)
-    *reinterpret_cast<uint4*>(smem + AT_OFF_ONES + i * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  constexpr uint32_t kOnes = kF16 ? 0x3C003C00u : 0x3F803F80u;          // 1.0 everywhere (uniform, so the swizzle does not matter)
+  for (int i = threadIdx.x; i < AT_KV_BYTES / 16; i += AT_THREADS)
+    *reinterpret_cast<uint4*>(smem + AT_OFF_ONES + i * 16) = make_uint4(kOnes, kOnes, kOnes, kOnes);
   fence_proxy_async();               // generic-proxy writes → visible to the tensor core's async-proxy reads
   tc_fence_before_sync();
   __syncthreads();
@@ -160,8 +166,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp stays convergent; one elected lane issues each tcgen05 instruction) =====
-    const uint32_t idesc_s = idesc_bf16_f32(AT_BM, p.nk_pad, 0, 0);
-    const uint32_t idesc_o = idesc_bf16_f32(AT_BM, AT_PV_N, 0, 1);
+    const uint32_t idesc_s = idesc_16_f32<kF16>(AT_BM, p.nk_pad, 0, 0);
+    const uint32_t idesc_o = idesc_16_f32<kF16>(AT_BM, AT_PV_N, 0, 1);
     const uint64_t kd = smem_desc_k_sw128(smem_u32(sK));
     const uint64_t vd0 = smem_desc_mn_sw128(smem_u32(sV), AT_OFF_ONES - AT_OFF_V);   // MN block 1 (columns 64..79) = the ones tile
     const int n_ksteps = p.nk_pad / 16;
@@ -259,7 +265,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               e[j] = (kPolyMask >> j) & 1 ? ex2_poly(xj) : ex2_approx(xj);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pu[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+            for (int j = 0; j < 8; ++j) pu[j] = Pack16<T16>::pack(e[2 * j], e[2 * j + 1]);
           };
           tmem_ld_32x16(taddr, va);
 #pragma unroll
@@ -281,13 +287,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int u = 0; u < kMaxUnits; ++u) {
             if (u < nu) {
-              const float fc = ex2_approx(mrec[u] - M);
-              const __nv_bfloat162 f2 = __float2bfloat162_rn(fc);
+              const float fc = ex2_approx(mrec[u] - M);       // an exact power of two <= 1 (fp16: flushes towards 0 below 2^-24)
+              if constexpr (kF16) {
+                const __half2 f2 = __float2half2_rn(fc);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&pk[u][j]);
-                x = __hmul2(x, f2);
-                pk[u][j] = *reinterpret_cast<uint32_t*>(&x);
+                for (int j = 0; j < 8; ++j) {
+                  __half2 x = *reinterpret_cast<__half2*>(&pk[u][j]);
+                  x = __hmul2(x, f2);
+                  pk[u][j] = *reinterpret_cast<uint32_t*>(&x);
+                }
+              } else {
+                const __nv_bfloat162 f2 = __float2bfloat162_rn(fc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&pk[u][j]);
+                  x = __hmul2(x, f2);
+                  pk[u][j] = *reinterpret_cast<uint32_t*>(&x);
+                }
               }
               tmem_st_32x8(taddr + (uint32_t)(u * 8), pk[u]);
             }
@@ -330,8 +346,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               st_shared_v4(srow + 4096 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
                            __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
             }
-          } else if (p.out_f32 == 2) {
-            // bf16x3 split: hi and lo 64-column boxes (32 rows x 128 B each); hi is stored twice ([hi | hi | lo])
+          } else if (p.out_f32 >= 2) {
+            // split output: hi and lo 64-column boxes (32 rows x 128 B each); mode 2: hi is stored twice ([hi | hi | lo]), mode 3: [hi | lo]
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               uint32_t hh[4], ll[4];
@@ -339,7 +355,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               for (int e = 0; e < 4; ++e) {
                 const int c0 = 8 * j + 2 * e;
                 const float a = c0 < 32 ? f(oa[c0]) : f(ob[c0 - 32]), bb = c0 + 1 < 32 ? f(oa[c0 + 1]) : f(ob[c0 + 1 - 32]);
-                split_bf16x2(a, bb, hh[e], ll[e]);
+                split16x2<T16>(a, bb, hh[e], ll[e]);
               }
               const uint32_t off = ((uint32_t)j << 4) ^ x7s;
               st_shared_v4(srow + off, hh[0], hh[1], hh[2], hh[3]);
@@ -349,10 +365,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // one 64-column bf16 box of 32 rows x 128 B
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), pack_bf16x2(f(oa[8 * j]), f(oa[8 * j + 1])), pack_bf16x2(f(oa[8 * j + 2]), f(oa[8 * j + 3])),
-                           pack_bf16x2(f(oa[8 * j + 4]), f(oa[8 * j + 5])), pack_bf16x2(f(oa[8 * j + 6]), f(oa[8 * j + 7])));
-              st_shared_v4(srow + (((uint32_t)(j + 4) << 4) ^ x7s), pack_bf16x2(f(ob[8 * j]), f(ob[8 * j + 1])), pack_bf16x2(f(ob[8 * j + 2]), f(ob[8 * j + 3])),
-                           pack_bf16x2(f(ob[8 * j + 4]), f(ob[8 * j + 5])), pack_bf16x2(f(ob[8 * j + 6]), f(ob[8 * j + 7])));
+              st_shared_v4(srow + (((uint32_t)j << 4) ^ x7s), Pack16<T16>::pack(f(oa[8 * j]), f(oa[8 * j + 1])), Pack16<T16>::pack(f(oa[8 * j + 2]), f(oa[8 * j + 3])),
+                           Pack16<T16>::pack(f(oa[8 * j + 4]), f(oa[8 * j + 5])), Pack16<T16>::pack(f(oa[8 * j + 6]), f(oa[8 * j + 7])));
+              st_shared_v4(srow + (((uint32_t)(j + 4) << 4) ^ x7s), Pack16<T16>::pack(f(ob[8 * j]), f(ob[8 * j + 1])), Pack16<T16>::pack(f(ob[8 * j + 2]), f(ob[8 * j + 3])),
+                           Pack16<T16>::pack(f(ob[8 * j + 4]), f(ob[8 * j + 5])), Pack16<T16>::pack(f(ob[8 * j + 6]), f(ob[8 * j + 7])));
             }
           }
           fence_proxy_async();
@@ -365,6 +381,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               tma_store_3d(&tmO, stg_ptr, Dm + h * AT_DH, row0, b);
               tma_store_3d(&tmO, stg_ptr + 4096, 2 * Dm + h * AT_DH, row0, b);
             }
+            if (p.out_f32 == 3) tma_store_3d(&tmO, stg_ptr + 4096, p.heads * AT_DH + h * AT_DH, row0, b);
             bulk_commit();
           }
         }
@@ -378,24 +395,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
 }
 
-static int at_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
-                         int64_t kv_total_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk,
-                         int heads, float scale, cudaStream_t s) {
+template <bool kF16>
+static int attention_tc_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t kv_total_rows,
+                               int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk, int heads, float scale,
+                               cudaStream_t s) {
   const int D = heads * AT_DH;
   SMK_REQUIRE(Lk >= 1 && Lk <= AT_MAXK && Lq >= 1 && Lq <= 2 * AT_BM, "attention_tc: Lq=%d / Lk=%d not supported (1..256)", Lq, Lk);
   SMK_REQUIRE(B >= 1 && heads >= 1 && (int64_t)B * heads < (1 << 30), "attention_tc: bad batch/heads");
-  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2 && (out_f32 != 2 || ldo >= 3 * (int64_t)D), "attention_tc: bad output mode / ldo");
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 3 && (out_f32 != 2 || ldo >= 3 * (int64_t)D) && (out_f32 != 3 || ldo >= 2 * (int64_t)D),
+              "attention_tc: bad output mode / ldo");
   const int esz = out_f32 == 1 ? 4 : 2;
   SMK_REQUIRE((ldo * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc: output must be 16-byte aligned");
   const int nk_pad = (Lk + 15) / 16 * 16;
@@ -406,33 +414,47 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
   SMK_PROPAGATE(make_tmap_bf16_2d(&tv, v, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldv * 2, AT_DH, (uint32_t)nk_pad));
   {
     // {column, query row within the image, image}: rows >= Lq of a 32-row output box are clipped by the TMA unit
-    const uint64_t dims[3] = {(uint64_t)(out_f32 == 2 ? 3 * D : D), (uint64_t)Lq, (uint64_t)B};
+    const int parts = out_f32 == 2 ? 3 : (out_f32 == 3 ? 2 : 1);
+    const uint64_t dims[3] = {(uint64_t)(parts * D), (uint64_t)Lq, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)ldo * esz, (uint64_t)Lq * ldo * esz};
     const uint32_t box[3] = {out_f32 == 1 ? 32u : 64u, 32u, 1u};
     SMK_PROPAGATE(make_tmap_nd(&to, esz, out, 3, dims, strides, box, 128));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_set = true;
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<13, true, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<16, false, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   }
   const int n_items = B * heads;
   AttnTcParams p{Lq, Lk, nk_pad, nt, Lq, kv_rows, kv_row0, heads, n_items, out_f32, scale * 1.4426950408889634f, traverse_dir()};
-  const int grid = n_items < at_num_sms() ? n_items : at_num_sms();
+  const int grid = n_items < device_sm_count() ? n_items : device_sm_count();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AT_DH * heads * B, s);
-    if (nk_pad == 13 * 16) SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<13, true>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
-    else SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<16, false>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
+    if (nk_pad == 13 * 16) SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<13, true, kF16>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
+    else SMK_CHECK_CUDA(launch_pdl(attn_tc_kernel<16, false, kF16>, dim3(grid), dim3(AT_THREADS), (size_t)AT_SMEM, s, tq, tk, tv, to, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
+}
+
+int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
+                         int64_t kv_total_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_f32, int B, int Lq, int Lk,
+                         int heads, float scale, cudaStream_t s) {
+  SMK_REQUIRE(out_f32 != 3, "attention_tc: the [hi | lo] output is the fp16 form's");
+  return attention_tc_launch<false>(q, ldq, k, ldk, v, ldv, kv_total_rows, kv_rows, kv_row0, out, ldo, out_f32, B, Lq, Lk, heads, scale, s);
 }
 
 // encoder form — qkv: [B*N, 3*D] bf16 (q | k | v, head h in columns [h*64, h*64+64) of each third); out: [B*N, D] bf16
 int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, float scale, cudaStream_t s) {
   const int D = heads * AT_DH;
   return attention_tc_general(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, (int64_t)B * N, N, 0, out, D, 0, B, N, N, heads, scale, s);
+}
+
+// fp16 encoder form — qkv: [B*N, 3*D] fp16; out: [B*N, ldo] fp16, out_mode 0 plain (ldo >= D) or 3 = [hi | lo] split (ldo >= 2D)
+int attention_tc_f16(const __half* qkv, __half* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, cudaStream_t s) {
+  const int D = heads * AT_DH;
+  SMK_REQUIRE(out_mode == 0 || out_mode == 3, "attention_tc_f16: output mode 0 (fp16) or 3 ([hi | lo] fp16)");
+  return attention_tc_launch<true>(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, (int64_t)B * N, N, 0, out, ldo, out_mode, B, N, N, heads, scale, s);
 }
 
 }  // namespace smk
@@ -445,6 +467,11 @@ extern "C" int smk_debug_attn_trace(long long* buf) {   // tuning aid: nullptr s
 extern "C" int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float scale, void* stream) {
   SMK_REQUIRE(qkv && out, "smk_attention_tc: null pointer");
   return smk::attention_tc((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, B, N, heads, scale, (cudaStream_t)stream);
+}
+
+extern "C" int smk_attention_tc_f16(const void* qkv, void* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, void* stream) {
+  SMK_REQUIRE(qkv && out, "smk_attention_tc_f16: null pointer");
+  return smk::attention_tc_f16((const __half*)qkv, (__half*)out, ldo, out_mode, B, N, heads, scale, (cudaStream_t)stream);
 }
 
 extern "C" int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

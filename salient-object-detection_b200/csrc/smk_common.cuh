@@ -1,6 +1,7 @@
 // Shared helpers for the selfmask_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -18,9 +19,40 @@ enum ProfCat { PROF_GEMM_TC = 0, PROF_ATTENTION = 1, PROF_GEMM_F32 = 2, PROF_LAY
 struct ProfScope {
   int slot;
   cudaStream_t stream;
-  ProfScope(int cat, double work, cudaStream_t s);   // work = algorithmic FLOPs (tensor categories) or bytes (memory ones)
+  // work = ALGORITHMIC FLOPs (tensor categories) or bytes (memory ones); issued = what the kernel really executes when that differs
+  // (split-operand GEMMs issue 2-3 tensor-core terms per algorithmic FLOP), 0 = same as work
+  ProfScope(int cat, double work, cudaStream_t s, double issued = 0.0);
   ~ProfScope();
 };
+// Sub-category of the next launches for the per-kernel roofline rows of bench.py (host side, set by the model orchestration)
+enum ProfTag { TAG_NONE = 0, TAG_PATCH_EMBED, TAG_QKV, TAG_ATTN, TAG_PROJ, TAG_FC1, TAG_FC2, TAG_LN, TAG_KV, TAG_DEC_GEMM, TAG_DEC_ATTN,
+               TAG_DEC_LN, TAG_MASK_LOGITS, TAG_MASK_UPSAMPLE, TAG_OBJECTNESS, TAG_EVAL_IOU, TAG_EVAL_METRICS, TAG_IM2COL, TAG_NUM };
+extern thread_local int g_prof_tag;
+struct TagScope {
+  int prev;
+  explicit TagScope(int t) : prev(g_prof_tag) { g_prof_tag = t; }
+  ~TagScope() { g_prof_tag = prev; }
+};
+
+// Per-device one-time state.  The library is used by one host thread per GPU, but a process may touch several devices in turn
+// (tests, the reference-style single-process callers): anything a kernel needs set once (cudaFuncSetAttribute, SM count) is keyed
+// by the current device ordinal instead of a process-wide flag.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < kMaxDevices ? d : 0;
+}
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {                       // true exactly once per device
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+int device_sm_count();                 // multiprocessors of the current device (cached per device)
 
 #define SMK_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
@@ -93,6 +125,33 @@ __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162f
 template <typename T> __device__ __forceinline__ T from_float(float v);
 template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+
+// 16-bit operand types of the tensor-core paths: pack two floats (round to nearest even) / unpack, and the 2-term split
+// x ≈ hi + lo with hi = T(x), lo = T(x − hi)  (bf16: ~16 significant bits, fp16: ~22)
+template <typename T> struct Pack16;
+template <> struct Pack16<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
+};
+template <> struct Pack16<__half> {
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+};
+template <typename T>
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = Pack16<T>::pack(a, b);
+  const float2 hf = Pack16<T>::unpack(hi);
+  lo = Pack16<T>::pack(a - hf.x, b - hf.y);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

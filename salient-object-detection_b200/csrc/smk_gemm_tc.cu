@@ -15,7 +15,9 @@
 // decoder's memory K/V projection (transformer_decoder.py:283-291 via nn.MultiheadAttention in_proj).
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include "smk_tc.cuh"
 
@@ -45,20 +47,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-u, t, fmaxf(x, 0.f));
 }
 
-constexpr int TC_ARES_KB = 6;                 // A-resident mode: up to 6 k-blocks (K <= 384) of the 128-row A block stay in shared memory
 constexpr int TC_BAR_BYTES = 512;
 
-// kARes: "A-resident" schedule for K <= 384 (qkv, proj, fc1, memory K/V), optional (SMK_GEMM_ARES=1).  A CTA (or CTA pair)
-// walks a contiguous, balanced range of the m-major tile sequence, keeps the 128 x K block of A in shared memory for all
-// n-blocks of that m-block and streams only the weight tiles through the ring: operand bytes pulled from L2 drop from
-// (128 + BN)·K·2 per tile to BN·K·2 (qkv: 695 MB → 387 MB per launch).  Measured on B200 it is 5-10 % slower than the
-// strided order on this model's shapes: those GEMMs are bound by the epilogue (GELU / TMA stores) and by the ~150-cycle
-// floor of an SS-mode M = 128 MMA, not by the L2→SM operand feed (profiles/r01_gemm_experiments.md).
+// (An "A-resident" schedule — the 128 x K block of A kept in shared memory for all n-blocks of an m-block — was measured 5-10 %
+// slower than the strided order on this model's shapes and has been removed: profiles/r01_gemm_experiments.md.)
 // kEW = 16: bf16-output tiles of 256 columns with four epilogue warps per scheduler instead of two.  The GELU / bias / pack
 // epilogue is a ~300-instruction dependent-latency stream per 32-column chunk; two warps per scheduler issue only ~50 % of the
 // cycles (ncu: long-scoreboard + fixed-latency waits), which made fc1 epilogue-bound (73 us vs 40 us of MMAs).  Each warp then
 // owns 64 columns (2 chunks) and a single 2 KB staging buffer, so the operand ring keeps its depth.
-template <int BN, int kCtas, bool kARes, int kEW = 8>
+template <int BN, int kCtas, int kEW = 8>
 struct TcCfg {
   static_assert(kEW == 8 || (kEW == 16 && BN % 128 == 0), "16 epilogue warps need whole 32-column chunks per warp");
   static constexpr int kThreads = 64 + 32 * kEW;
@@ -66,15 +63,14 @@ struct TcCfg {
   static constexpr int kBNL = BN / kCtas;                          // B-tile rows loaded by one CTA
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = kBNL * TC_BK * 2;
-  static constexpr int kAResBytes = kARes ? TC_ARES_KB * kABytes : 0;
-  static constexpr int kStageBytes = kARes ? kBBytes : kABytes + kBBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kEW * kStagingPerWarp;
-  static constexpr int kRingBudget = 227 * 1024 - kStagingBytes - 1024 - TC_BAR_BYTES - kAResBytes;
+  static constexpr int kRingBudget = 227 * 1024 - kStagingBytes - 1024 - TC_BAR_BYTES;
   static constexpr int kStages = kRingBudget / kStageBytes > 8 ? 8 : kRingBudget / kStageBytes;
   static constexpr int kTmemCols = (BN == 128) ? 256 : 512;      // two accumulator buffers of BN columns, power-of-two allocation
-  static constexpr int kSmemBytes = kAResBytes + kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + TC_BAR_BYTES;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*alignment slack*/ + TC_BAR_BYTES;
   static_assert(kSmemBytes <= 227 * 1024 && kStages >= 3, "shared memory budget");
-  static_assert((2 * kStages + 4 + 2 * TC_ARES_KB) * 8 + 8 <= TC_BAR_BYTES, "barrier area");
+  static_assert((2 * kStages + 4) * 8 + 8 <= TC_BAR_BYTES, "barrier area");
 };
 
 // Tuning instrumentation (wait-cycle trace, stage-isolation switches) is compiled in only with -DSMK_GEMM_TUNE=1
@@ -104,13 +100,19 @@ constexpr int TC_DBG_NOSTORE = 8;  // epilogue reads TMEM and does the math but 
 constexpr int TC_DBG_NOTMA = 16;   // epilogue stages to shared memory but does not issue the TMA store
 constexpr int TC_DBG_NOCOMMIT = 4; // (with NOLOAD) no per-k-block tcgen05.commit on the ring's empty barriers   // operands are loaded for the first ring pass only; the MMAs re-read the same shared memory
 
+constexpr int TC_MAX_TERMS = 3;
 struct TcGemmParams {
-  int M, N, K;
+  int M, N, K;    // K = reduction length of ONE term
+  // Split-operand products: C = Σ_t A[:, ta[t] : ta[t]+K] · W[:, tw[t] : tw[t]+K]^T.  Operands stored as [hi | lo] rows (hi = T(x),
+  // lo = T(x − hi)) give  A·W^T ≈ hi·hi + hi·lo + lo·hi  (terms (0,0), (0,K), (K,0): ~fp32 accuracy)  or  A_hi·(W_hi + W_lo)^T
+  // (terms (0,0), (0,K): the weight rounding removed) without a second copy of hi.  One term (0,0) = the plain GEMM.
+  int n_terms, ta[TC_MAX_TERMS], tw[TC_MAX_TERMS];
   const float* bias;
   void* C;
   int64_t ldc;
   int epi;        // SMK_EPI_* flags
-  int out_f32;    // 0 → bf16 output, 1 → fp32 output, 2 → bf16x3 split output [hi | hi | lo] (3N columns)
+  int out_f32;    // 0 → 16-bit output (bf16 / fp16 per kF16), 1 → fp32 output, 2 → 3-part split output [hi | hi | lo] (3N columns),
+                  // 3 → 2-part split output [hi | lo] (2N columns)
   // token assembly for patch-embed (kDirect): output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
   int tok_hw;
   const float* tok_pos;
@@ -123,39 +125,36 @@ struct TcGemmParams {
   // one feature per lane and 32 tokens per chunk: bias is a per-lane scalar, the staging tile is written transposed
   // (token-major rows of 32 features) and the TMA store / reduce-add addresses C[token, feature] as usual.  fp32 output only.
   int trans;
+  int credit_k;   // host-side bookkeeping only (profiler credit)
 };
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
 // M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
 // the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
-template <int BN, bool kDirect, int kCtas, bool kARes, int kEW = 8>
+template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const TcGemmParams p) {
-  using Cfg = TcCfg<BN, kCtas, kARes, kEW>;
+  using Cfg = TcCfg<BN, kCtas, kEW>;
+  using T16 = typename std::conditional<kF16, __half, __nv_bfloat16>::type;     // operand / 16-bit output type
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem = smem_base + Cfg::kAResBytes;   // operand ring (the resident A block, if any, sits in front of it)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // operand ring
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* a_full = tmem_empty + 2;
-  uint64_t* a_empty = a_full + TC_ARES_KB;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + TC_ARES_KB);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = (p.N + BN - 1) / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);   // N % BN == 0 unless trans
-  const int num_tiles = n_blocks * m_blocks, k_blocks = p.K / TC_BK;
+  const int kpt = p.K / TC_BK;                                  // k-blocks per term
+  const int num_tiles = n_blocks * m_blocks, k_blocks = kpt * p.n_terms;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
-  // tiles are owned by clusters.  Strided order (neighbouring CTAs work on neighbouring tiles) or, A-resident, a contiguous
-  // balanced range of the m-major sequence (tile = m_blk * n_blocks + n_blk)
+  // tiles are owned by clusters, strided order (neighbouring CTAs work on neighbouring tiles)
   const int n_cl = gridDim.x / kCtas, cl = blockIdx.x / kCtas;
-  const int tile0 = kARes ? (int)((int64_t)cl * num_tiles / n_cl) : cl;
-  const int tile_end = kARes ? (int)((int64_t)(cl + 1) * num_tiles / n_cl) : num_tiles;
-  const int tile_step = kARes ? 1 : n_cl;
+  const int tile0 = cl, tile_end = num_tiles, tile_step = n_cl;
   long long* trace = (SMK_GEMM_TUNE && g_gemm_trace) ? g_gemm_trace + 16 * blockIdx.x : nullptr;
   const int dbg = SMK_GEMM_TUNE ? p.dbg : 0;
 
@@ -165,7 +164,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (!kDirect) tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEW * kCtas); }
-    for (int i = 0; i < TC_ARES_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -190,49 +188,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int cur_m = -1;
-      uint32_t a_fills = 0;                      // A-resident: m-blocks loaded so far (slot parity)
       WaitClock w_slot(trace != nullptr), w_all(trace != nullptr);
       w_all.begin();
       int n_loads = 0;
       for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
-        const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
+        const int tile = p.rev ? num_tiles - 1 - tile_i : tile_i;
         // trans: the feature blocks of one token block are neighbours in the sequence (they share the activation tile in L2)
         const int m_blk = p.trans ? tile % m_blocks : tile / n_blocks, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
-        const bool new_m = kARes && m_blk != cur_m;
+        int term = 0, kk = 0;                      // k-block kb = term * kpt + kk
         for (int kb = 0; kb < k_blocks; ++kb) {
-          if (new_m && !((dbg & TC_DBG_NOLOAD) && a_fills > 0)) {
-            // slot kb is released when the last n-block of the previous m-block has consumed it
-            mbar_wait(&a_empty[kb], (a_fills & 1) ^ 1);
-            uint8_t* sa = smem_base + kb * Cfg::kABytes;
-            if constexpr (kCtas == 2) {
-              if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * Cfg::kABytes);
-              tma_load_2d_cg2(sa, &tmA, mapa_shared(smem_u32(&a_full[kb]), 0), kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
-            } else {
-              mbar_arrive_expect_tx(&a_full[kb], Cfg::kABytes);
-              tma_load_2d(sa, &tmA, &a_full[kb], kb * TC_BK, m_blk * TC_BM);
-            }
-          }
+          const int ka = p.ta[term] + kk * TC_BK, kw = p.tw[term] + kk * TC_BK;
+          if (++kk == kpt) { kk = 0; ++term; }
           if ((dbg & TC_DBG_NOLOAD) && n_loads++ >= Cfg::kStages) continue;
           w_slot.begin();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           w_slot.end();
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = kARes ? sa : sa + Cfg::kABytes;
+          uint8_t* sb = sa + Cfg::kABytes;
           if constexpr (kCtas == 2) {
             // both CTAs' bytes complete on the even CTA's barrier (its MMA thread is the only consumer)
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if constexpr (!kARes) tma_load_2d_cg2(sa, &tmA, bar, kb * TC_BK, (m_blk * 2 + (int)rank) * TC_BM);
-            tma_load_2d_cg2(sb, &tmB, bar, kb * TC_BK, n_blk * BN + (int)rank * Cfg::kBNL);
+            tma_load_2d_cg2(sa, &tmA, bar, ka, (m_blk * 2 + (int)rank) * TC_BM);
+            tma_load_2d_cg2(sb, &tmB, bar, kw, n_blk * BN + (int)rank * Cfg::kBNL);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if constexpr (!kARes) tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+            tma_load_2d(sa, &tmA, &full_bar[stage], ka, m_blk * TC_BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kw, n_blk * BN);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (new_m) { cur_m = m_blk; ++a_fills; }
       }
       w_all.end();
       if (trace) { trace[0] = w_slot.acc; trace[1] = w_all.acc; }
@@ -240,20 +225,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(TC_BM * kCtas, BN, 0, 0);
+      constexpr uint32_t idesc = idesc_16_f32<kF16>(TC_BM * kCtas, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      int cur_m = -1;
-      uint32_t a_uses = 0;                       // A-resident: m-blocks consumed so far (slot parity)
       WaitClock w_ops(trace != nullptr), w_acc(trace != nullptr), w_all(trace != nullptr);
       w_all.begin();
       int n_used = 0;
       for (int tile = tile0; tile < tile_end; tile += tile_step) {
-        const int m_blk = tile / n_blocks;
-        const bool new_m = kARes && m_blk != cur_m;
-        const bool last_of_m = kARes && (tile + 1 == tile_end || (tile + 1) / n_blocks != m_blk);
         w_acc.begin();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         w_acc.end();
@@ -262,12 +242,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           w_ops.begin();
           const bool skip_wait = (dbg & TC_DBG_NOLOAD) && n_used++ >= Cfg::kStages;
-          if (new_m && !((dbg & TC_DBG_NOLOAD) && a_uses > 0)) mbar_wait(&a_full[kb], a_uses & 1);
           if (!skip_wait) mbar_wait(&full_bar[stage], phase);
           w_ops.end();
           tc_fence_after_sync();
-          const uint32_t sa = kARes ? smem_u32(smem_base + kb * Cfg::kABytes) : smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = smem_u32(smem + stage * Cfg::kStageBytes) + (kARes ? 0u : (uint32_t)Cfg::kABytes);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + (uint32_t)Cfg::kABytes;
           const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
@@ -279,17 +258,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
             else tc_commit(&empty_bar[stage]);
           }
-          if (last_of_m) {                       // ... and the resident A k-block after its last n-block
-            if constexpr (kCtas == 2) tc_commit_cg2(&a_empty[kb], 3);
-            else tc_commit(&a_empty[kb]);
-          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete → epilogue (of both CTAs)
         if constexpr (kCtas == 2) tc_commit_cg2(&tmem_full[acc], 3);
         else tc_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (new_m) { cur_m = m_blk; ++a_uses; }
       }
       w_all.end();
       if (trace) { trace[2] = w_ops.acc; trace[3] = w_acc.acc; trace[4] = w_all.acc; }
@@ -311,7 +285,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     long long n_tiles_done = 0;
     w_all.begin();
     for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
-      const int tile = (!kARes && p.rev) ? num_tiles - 1 - tile_i : tile_i;
+      const int tile = p.rev ? num_tiles - 1 - tile_i : tile_i;
       const int m_blk = (p.trans ? tile % m_blocks : tile / n_blocks) * kCtas + (int)rank, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
       ++n_tiles_done;
       w_tm.begin();
@@ -429,8 +403,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               else tma_store_2d(&tmC, stg, n0, row0);
               bulk_commit();
             }
-          } else if (kEW != 16 && p.out_f32 == 2) {
-            // bf16x3 split output: hi tile → columns n0 and N + n0, lo tile → 2N + n0 (two 32 x 64 B staging tiles)
+          } else if (kEW != 16 && p.out_f32 >= 2) {
+            // split output (two 32 x 64 B staging tiles): 3-part [hi | hi | lo]: hi → columns n0 and N + n0, lo → 2N + n0;
+            // 2-part [hi | lo]: hi → n0, lo → N + n0
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             const uint32_t srow = stg_u32 + lane * 64;
@@ -438,7 +413,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 4; ++j) {
               uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], h[e], l[e]);
+              for (int e = 0; e < 4; ++e) split16x2<T16>(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], h[e], l[e]);
               const uint32_t off = (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
               st_shared_v4(srow + off, h[0], h[1], h[2], h[3]);
               st_shared_v4(srow + 2048 + off, l[0], l[1], l[2], l[3]);
@@ -447,8 +422,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) {
               tma_store_2d(&tmC, stg, n0, row0);
-              tma_store_2d(&tmC, stg, p.N + n0, row0);
-              tma_store_2d(&tmC, stg + 2048, 2 * p.N + n0, row0);
+              if (p.out_f32 == 2) {
+                tma_store_2d(&tmC, stg, p.N + n0, row0);
+                tma_store_2d(&tmC, stg + 2048, 2 * p.N + n0, row0);
+              } else {
+                tma_store_2d(&tmC, stg + 2048, p.N + n0, row0);
+              }
               bulk_commit();
             }
           } else if (kEW != 16 && p.out_f32 == 0 && p.trans) {
@@ -461,7 +440,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t sb = stg_u32 + (uint32_t)(buf - stg) + ((uint32_t)(lane & 7) << 1), lchunk = (uint32_t)(lane >> 3);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(v[j]));
+              const unsigned short hv = (unsigned short)(Pack16<T16>::pack(v[j], 0.f) & 0xffffu);
               asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + (uint32_t)j * 64u + ((lchunk ^ (uint32_t)((j >> 1) & 3)) << 4)), "h"(hv) : "memory");
             }
             fence_proxy_async();
@@ -482,8 +461,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t srow = stg_u32 + (uint32_t)(buf - stg) + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              st_shared_v4(srow + ((j ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              st_shared_v4(srow + ((j ^ ((lane >> 1) & 3)) << 4), Pack16<T16>::pack(v[8 * j], v[8 * j + 1]), Pack16<T16>::pack(v[8 * j + 2], v[8 * j + 3]),
+                           Pack16<T16>::pack(v[8 * j + 4], v[8 * j + 5]), Pack16<T16>::pack(v[8 * j + 6], v[8 * j + 7]));
             fence_proxy_async();
             __syncwarp();
             if (lane == 0 && !(dbg & TC_DBG_NOTMA)) {
@@ -570,25 +549,15 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return make_tmap_2d(out, 2, base, inner, outer, row_stride_bytes, box_inner, box_outer, 128);
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
-template <int BN, bool kDirect, int kCtas, bool kARes, int kEW = 8>
+template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
-  using Cfg = TcCfg<BN, kCtas, kARes, kEW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  using Cfg = TcCfg<BN, kCtas, kEW>;
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
-    attr_set = true;
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas));
   const int slots = num_sms() / kCtas;                     // CTAs (kCtas = 1) or CTA pairs (2) that can be resident
@@ -615,8 +584,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
   {
-    ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.K, s);
-    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kARes, kEW>, ta, tb, tcm, p));
+    // credited work = ALGORITHMIC FLOPs of the contraction (one term; p.credit_k is the mathematical reduction length), whatever
+    // number of split terms the tensor core is issued
+    ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * p.n_terms);
+    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -647,6 +618,7 @@ static int pick_bn(int M, int N, int bm, int slots) {
 // CTA pairs (cta_group::2, 256-row tiles, each CTA loads half of the weight tile): measured slower at K = 384 (the extra
 // cross-CTA hand-shakes per k-block are not amortised) and faster from K >= 1024 on many-row problems, where the GEMM sits at
 // the L2→SM operand-feed limit (fc2: 73.0 → 66.8 us).  SMK_GEMM_CTA_PAIR = 0 / 1 forces single CTAs / pairs (tuning).
+// K here is the TOTAL reduction length issued (all split terms).
 static bool use_cta_pair(int M, int K) {
   static int mode = -2;
   if (mode == -2) {
@@ -672,7 +644,7 @@ static bool use_swap_ab(int M, int N, int K) {
   return N <= 512 && K >= 1024 && M >= 16384;
 }
 
-// swap-AB for bf16 outputs whose width is not a multiple of 256 (qkv: 1152 = 9 x 128 features → every MMA 128 x 256 over tokens
+// swap-AB for 16-bit outputs whose width is not a multiple of 256 (qkv: 1152 = 9 x 128 features → every MMA 128 x 256 over tokens
 // instead of 128 x 192; 1773 tiles = 11.98 waves of 148).  OFF unless SMK_GEMM_SWAP_AB=1: measured on B200 qkv 48.4 / 48.5 us in
 // the normal form vs 49.5 / 49.3 us swapped — qkv is paced by its epilogue (TMEM read + pack + stores of 116 MB), not by the MMA
 // width, and the transposed store costs one 2-byte st.shared per element.  Never for GELU epilogues (fc1).
@@ -686,18 +658,7 @@ static bool use_swap_ab_bf16(int M, int N, int epi) {
   return mode == 1 && N % 256 != 0 && M >= 16384;
 }
 
-// SMK_GEMM_ARES=1 enables the A-resident schedule for K <= 384.  Default off: measured 5-10 % slower on this model's shapes
-// (the epilogue, not the operand feed, bounds those GEMMs; see profiles/r01_gemm_experiments.md)
-static int ares_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("SMK_GEMM_ARES");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode;
-}
-
-// 16 epilogue warps: bf16-output 256-column tiles of many-row problems (fc1, memory K/V); SMK_GEMM_EPI16 = 0 / 1 overrides (tuning)
+// 16 epilogue warps: 16-bit-output 256-column tiles of many-row problems (fc1, memory K/V); SMK_GEMM_EPI16 = 0 / 1 overrides (tuning)
 static bool use_epi16(const TcGemmParams& p) {
   static int mode = -2;
   if (mode == -2) {
@@ -708,61 +669,89 @@ static bool use_epi16(const TcGemmParams& p) {
   return mode >= 0 ? mode != 0 : p.M >= 16384;
 }
 
-template <bool kDirect, int kCtas, bool kARes>
+template <bool kDirect, int kCtas, bool kF16>
 static int launch_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
-  if constexpr (!kDirect && !kARes) {
-    if (BN == 256 && use_epi16(p)) return launch_tc<256, false, kCtas, false, 16>(ta, tb, tcm, p, s);
+  if constexpr (!kDirect) {
+    if (BN == 256 && use_epi16(p)) return launch_tc<256, false, kCtas, 16, kF16>(ta, tb, tcm, p, s);
   }
-  return BN == 256 ? launch_tc<256, kDirect, kCtas, kARes>(ta, tb, tcm, p, s)
-                   : (BN == 192 ? launch_tc<192, kDirect, kCtas, kARes>(ta, tb, tcm, p, s) : launch_tc<128, kDirect, kCtas, kARes>(ta, tb, tcm, p, s));
+  return BN == 256 ? launch_tc<256, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s)
+                   : (BN == 192 ? launch_tc<192, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s) : launch_tc<128, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s));
 }
 
-// A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements)
-int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
-                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s) {
-  SMK_REQUIRE(K % TC_BK == 0 && N % 128 == 0, "gemm_bf16: need K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, N);
-  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2, "gemm_bf16: out_f32 must be 0 (bf16), 1 (fp32) or 2 (bf16x3 split)");
-  SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32 == 1, "gemm_bf16: residual epilogue needs fp32 output");
-  SMK_REQUIRE(out_f32 != 2 || ldc >= 3 * (int64_t)N, "gemm_bf16: split output needs ldc >= 3N");
-  SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
-  SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_bf16: bias must be 16-byte aligned");
-  SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_bf16: token assembly needs a plain fp32 output");
-  if (M == 0) return SMK_OK;
-  if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, K)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
-    // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
-    CUtensorMap ta, tb, tcm;
-    SMK_PROPAGATE(make_tmap_bf16_2d(&ta, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, TC_BM));
-    SMK_PROPAGATE(make_tmap_bf16_2d(&tb, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, 256));
-    SMK_PROPAGATE(make_tmap_2d(&tcm, out_f32 ? 4 : 2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * (out_f32 ? 4 : 2), 32, 32, out_f32 ? 128 : 64));
-    TcGemmParams p{N, M, K, bias, C, ldc, epi, out_f32, 0, nullptr, 0, traverse_dir(), 1};
-    return launch_tc<256, false, 1, false>(ta, tb, tcm, p, s);
+// General form.  A [M, >= lda] / W [N, >= ldw] hold 16-bit operands (bf16, or fp16 when f16 != 0); every term t multiplies the K
+// columns of A starting at terms.a_off[t] with the K columns of W starting at terms.w_off[t] (element offsets, multiples of 64).
+template <bool kF16>
+static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                        int epi, int out_f32, int tok_hw, const float* tok_pos, const GemmTerms& tr, int credit_k, cudaStream_t s) {
+  SMK_REQUIRE(K % TC_BK == 0 && N % 128 == 0, "gemm_tc: need K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, N);
+  SMK_REQUIRE(tr.n >= 1 && tr.n <= TC_MAX_TERMS, "gemm_tc: 1..3 terms");
+  int64_t a_cols = 0, w_cols = 0;
+  for (int t = 0; t < tr.n; ++t) {
+    SMK_REQUIRE(tr.a_off[t] >= 0 && tr.w_off[t] >= 0 && tr.a_off[t] % TC_BK == 0 && tr.w_off[t] % TC_BK == 0, "gemm_tc: term offsets must be multiples of 64");
+    a_cols = std::max<int64_t>(a_cols, tr.a_off[t] + K);
+    w_cols = std::max<int64_t>(w_cols, tr.w_off[t] + K);
   }
-  const bool pair = tok_hw == 0 && use_cta_pair(M, K);
-  const bool ares = tok_hw == 0 && ares_mode() != 0 && K <= TC_ARES_KB * TC_BK;
-  const int kc = pair ? 2 : 1;
-  // A-resident: work is split by tile ranges, perfectly balanced for any width → the widest tile (fewest epilogue hand-overs)
-  int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
-  if (ares && !getenv("SMK_GEMM_BN")) BN = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
-  if (tok_hw > 0 && !getenv("SMK_GEMM_BN")) BN = 128;   // direct-store epilogue (patch embed): per-thread row stores favour narrow tiles (78 vs 82 us)
-  CUtensorMap ta, tb, tcm;
-  SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
-  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));
+  SMK_REQUIRE(lda >= a_cols && ldw >= w_cols, "gemm_tc: operand rows shorter than the terms reach (lda=%lld ldw=%lld)", (long long)lda, (long long)ldw);
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 3, "gemm_tc: out_f32 must be 0 (16-bit), 1 (fp32), 2 ([hi|hi|lo] split) or 3 ([hi|lo] split)");
+  SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32 == 1, "gemm_tc: residual epilogue needs fp32 output");
+  SMK_REQUIRE(out_f32 != 2 || ldc >= 3 * (int64_t)N, "gemm_tc: split output needs ldc >= 3N");
+  SMK_REQUIRE(out_f32 != 3 || ldc >= 2 * (int64_t)N, "gemm_tc: split output needs ldc >= 2N");
+  SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_tc: C must be 16-byte aligned with ldc %% 8 == 0");
+  SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
+  SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_tc: token assembly needs a plain fp32 output");
+  if (M == 0) return SMK_OK;
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("SMK_GEMM_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  TcGemmParams p{M, N, K, bias, C, ldc, epi, out_f32, tok_hw, tok_pos, dbg, traverse_dir(), 0};
+  const int Ktot = K * tr.n;
+  TcGemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.n_terms = tr.n;
+  for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.a_off[t]; p.tw[t] = tr.w_off[t]; }
+  p.bias = bias; p.C = C; p.ldc = ldc; p.epi = epi; p.out_f32 = out_f32; p.tok_hw = tok_hw; p.tok_pos = tok_pos; p.dbg = dbg;
+  p.rev = traverse_dir(); p.trans = 0; p.credit_k = credit_k > 0 ? credit_k : K;
+  if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, Ktot)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
+    // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
+    CUtensorMap ta, tb, tcm;
+    SMK_PROPAGATE(make_tmap_bf16_2d(&ta, W, (uint64_t)w_cols, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, TC_BM));
+    SMK_PROPAGATE(make_tmap_bf16_2d(&tb, A, (uint64_t)a_cols, (uint64_t)M, (uint64_t)lda * 2, TC_BK, 256));
+    SMK_PROPAGATE(make_tmap_2d(&tcm, out_f32 ? 4 : 2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * (out_f32 ? 4 : 2), 32, 32, out_f32 ? 128 : 64));
+    p.M = N; p.N = M; p.trans = 1;
+    for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.w_off[t]; p.tw[t] = tr.a_off[t]; }
+    return launch_tc<256, false, 1, 8, kF16>(ta, tb, tcm, p, s);
+  }
+  const bool pair = tok_hw == 0 && use_cta_pair(M, Ktot);
+  const int kc = pair ? 2 : 1;
+  int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
+  if (tok_hw > 0 && !getenv("SMK_GEMM_BN")) BN = 128;   // direct-store epilogue (patch embed): per-thread row stores favour narrow tiles (78 vs 82 us)
+  CUtensorMap ta, tb, tcm;
+  SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)a_cols, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
+  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)w_cols, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));
   if (tok_hw > 0) {
     tcm = ta;   // unused by the direct-store epilogue
-    return launch_bn<true, 1, false>(BN, ta, tb, tcm, p, s);
+    return launch_bn<true, 1, kF16>(BN, ta, tb, tcm, p, s);
   }
-  // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (bf16, 64-byte swizzle) per row
+  // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (16-bit, 64-byte swizzle) per row
   const int esz = out_f32 == 1 ? 4 : 2;
-  SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(out_f32 == 2 ? 3 * N : N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32,
-                             out_f32 == 1 ? 128 : 64));
-  if (pair) return ares ? launch_bn<false, 2, true>(BN, ta, tb, tcm, p, s) : launch_bn<false, 2, false>(BN, ta, tb, tcm, p, s);
-  return ares ? launch_bn<false, 1, true>(BN, ta, tb, tcm, p, s) : launch_bn<false, 1, false>(BN, ta, tb, tcm, p, s);
+  const int parts = out_f32 == 2 ? 3 : (out_f32 == 3 ? 2 : 1);
+  SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(parts * N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32, out_f32 == 1 ? 128 : 64));
+  if (pair) return launch_bn<false, 2, kF16>(BN, ta, tb, tcm, p, s);
+  return launch_bn<false, 1, kF16>(BN, ta, tb, tcm, p, s);
+}
+
+int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K, int epi,
+            int out_f32, int tok_hw, const float* tok_pos, int f16, const GemmTerms& terms, int credit_k, cudaStream_t s) {
+  return f16 ? gemm_tc_impl<true>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, out_f32, tok_hw, tok_pos, terms, credit_k, s)
+             : gemm_tc_impl<false>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, out_f32, tok_hw, tok_pos, terms, credit_k, s);
+}
+
+// plain bf16 form: A [M,K] bf16 (lda elements), W [N,K] bf16 (ldw elements).  credit_k: mathematical reduction length when K is
+// the K' = 3K of a [hi | hi | lo] x [hi | lo | hi] split pair (0 = K)
+int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s, int credit_k) {
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2, "gemm_bf16: out_f32 must be 0 (bf16), 1 (fp32) or 2 (bf16x3 split)");
+  return gemm_tc_impl<false>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, out_f32, tok_hw, tok_pos, GemmTerms{1, {0, 0, 0}, {0, 0, 0}}, credit_k, s);
 }
 
 }  // namespace smk
@@ -777,4 +766,13 @@ extern "C" int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const fl
   SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0, "smk_gemm_bf16: bad arguments");
   return smk::gemm_bf16_tc((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, K, bias, C, ldc, M, N, K, epilogue, out_f32, 0, nullptr,
                            (cudaStream_t)stream);
+}
+
+extern "C" int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,
+                              int K, int epilogue, int out_kind, int f16, int n_terms, const int32_t* a_off, const int32_t* w_off,
+                              void* stream) {
+  SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && a_off && w_off && n_terms >= 1 && n_terms <= 3, "smk_gemm_split: bad arguments");
+  smk::GemmTerms t{n_terms, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < n_terms; ++i) { t.a_off[i] = a_off[i]; t.w_off[i] = w_off[i]; }
+  return smk::gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, epilogue, out_kind, 0, nullptr, f16, t, 0, (cudaStream_t)stream);
 }

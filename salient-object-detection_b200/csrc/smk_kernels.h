@@ -22,13 +22,23 @@ int layernorm_f32(const float* x, const float* res, const float* gamma, const fl
 int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int64_t rows, int D, float eps, cudaStream_t s);
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
                    float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr);
+int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s);
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
                   int64_t rows, int D, cudaStream_t s);
 int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N, int K,
              int epi, cudaStream_t s);
 int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
-                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s);
+                 int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s, int credit_k = 0);
+// split-operand tcgen05 GEMM (smk_gemm_tc.cu): C = Σ_t A[:, a_off[t] : +K] · W[:, w_off[t] : +K]^T, 16-bit operands (fp16 when f16),
+// out_f32: 0 16-bit, 1 fp32, 2 [hi | hi | lo] split, 3 [hi | lo] split
+struct GemmTerms { int n; int a_off[3]; int w_off[3]; };
+inline GemmTerms terms_plain() { return GemmTerms{1, {0, 0, 0}, {0, 0, 0}}; }
+inline GemmTerms terms_wsplit(int K) { return GemmTerms{2, {0, 0, 0}, {0, K, 0}}; }        // A_hi·(W_hi + W_lo)
+inline GemmTerms terms_full(int K) { return GemmTerms{3, {0, 0, K}, {0, K, 0}}; }          // hi·hi + hi·lo + lo·hi
+int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K, int epi,
+            int out_f32, int tok_hw, const float* tok_pos, int f16, const GemmTerms& terms, int credit_k, cudaStream_t s);
 template <typename T, typename TK>
 int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, int dh, int Lq, int Lk, int64_t q_bs, int64_t ldq,
               int64_t k_bs, int64_t ldk, int64_t v_bs, int64_t ldv, int64_t o_bs, int64_t ldo, float scale, cudaStream_t s);
@@ -36,6 +46,7 @@ int attention(const T* q, const TK* k, const TK* v, T* o, int batch, int heads, 
 int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, const float* bias, float* X, const float* gamma,
                const float* beta, __nv_bfloat16* Xn, int M, int N, int K, float eps, cudaStream_t s);
 int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, float scale, cudaStream_t s);
+int attention_tc_f16(const __half* qkv, __half* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, cudaStream_t s);
 // general form: q [B*Lq, ldq] / k / v [.., ld] bf16 matrices (head h at columns [h*64, h*64+64) from the given base pointer);
 // image b's queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0.  Lq <= 128, Lk <= 256.
 // out: [B*Lq, ldo], fp32 when out_f32 else bf16.
@@ -45,21 +56,27 @@ int attention_tc_general(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat1
 // few-query attention (decoder): Lq <= 32, Lk <= 256; out_mode 0 bf16, 1 fp32, 2 bf16x3 split (smk_attn_small.cu)
 int attention_small(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v, int64_t ldv,
                     int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
-                    cudaStream_t s);
+                    cudaStream_t s, int f16 = 0, int q_f32 = 0);
 // online-softmax attention for long sequences / the bf16x3 split mode (smk_attn_fa.cu); *_lo == nullptr → plain bf16 operands
 int attention_fa(const __nv_bfloat16* q, const __nv_bfloat16* q_lo, int64_t ldq, const __nv_bfloat16* k, const __nv_bfloat16* k_lo, int64_t ldk,
                  const __nv_bfloat16* v, const __nv_bfloat16* v_lo, int64_t ldv, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo,
-                 int out_mode, int B, int Lq, int Lk, int heads, float scale, cudaStream_t s);
+                 int out_mode, int B, int Lq, int Lk, int heads, float scale, cudaStream_t s, int f16 = 0);
 int split3_act(const float* x, int64_t ldx, const float* pos, int period, __nv_bfloat16* out_a, __nv_bfloat16* out_b, int64_t rows,
                int K, cudaStream_t s);
 int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s);
 template <typename TIn, typename T>
 int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std /* host, 6 floats or null */,
            cudaStream_t s);
+template <typename TIn>
+int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s);
+int split2_f16(const float* w, int64_t ldw, __half* out, int64_t rows, int K, cudaStream_t s);
+int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, __nv_bfloat16* out3, int B, int nq, int heads, float scale,
+                       cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
                     cudaStream_t s);
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t s);
 int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s1, int row_bytes1, int64_t rows, int period, cudaStream_t s);
 // bf16 tensor-core mode, scale factor 4 (smk_mask_mma.cu): logits on mma.sync with the 3-term split, then upsample + sigmoid
 int mask_head_mma(const __nv_bfloat16* q3, int64_t Rall, const __nv_bfloat16* tok_hi, const __nv_bfloat16* tok_lo, float* logits_lowres,

@@ -21,6 +21,8 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
                  TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */,
                  TOut* __restrict__ y_dup /* bf16 only: second copy of y; (y, y_dup, y_lo) at columns 0, D, 2D of rows of ldy = 3D
                                              elements form the bf16x3 split [hi | hi | lo] a split GEMM consumes */,
+                 __nv_bfloat16* __restrict__ alt_hi, __nv_bfloat16* __restrict__ alt_lo /* optional bf16 hi / lo copies (rows of D) next to
+                                             a 16-bit y of another type: the final encoder norm feeds fp16 GEMMs and the bf16 mask head */,
                  int64_t ldy, int64_t rows, int D, float eps, int rev) {
   pdl_wait();
   pdl_trigger();
@@ -81,20 +83,21 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
         if constexpr (sizeof(TOut) == 4) {
           reinterpret_cast<float4*>(y + row * ldy)[i] = o;
         } else {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          uint2 pk, pr;
+          split16x2<TOut>(o.x, o.y, pk.x, pr.x);
+          split16x2<TOut>(o.z, o.w, pk.y, pr.y);
           reinterpret_cast<uint2*>(y + row * ldy)[i] = pk;
           if (y_dup) reinterpret_cast<uint2*>(y_dup + row * ldy)[i] = pk;
-          if (y_lo) {
-            const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
-            __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), r1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
-            uint2 pr;
-            pr.x = *reinterpret_cast<uint32_t*>(&r0);
-            pr.y = *reinterpret_cast<uint32_t*>(&r1);
-            reinterpret_cast<uint2*>(y_lo + row * ldy)[i] = pr;
-          }
+          if (y_lo) reinterpret_cast<uint2*>(y_lo + row * ldy)[i] = pr;
+        }
+      }
+      if constexpr (sizeof(TOut) == 2) {
+        if (alt_hi) {
+          uint2 pk, pr;
+          split16x2<__nv_bfloat16>(o.x, o.y, pk.x, pr.x);
+          split16x2<__nv_bfloat16>(o.z, o.w, pk.y, pr.y);
+          reinterpret_cast<uint2*>(alt_hi + row * D)[i] = pk;
+          if (alt_lo) reinterpret_cast<uint2*>(alt_lo + row * D)[i] = pr;
         }
       }
     }
@@ -103,16 +106,18 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
 
 template <typename TOut>
 static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
-                            float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s, TOut* y_dup = nullptr, int64_t ldy = 0) {
+                            float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s, TOut* y_dup = nullptr, int64_t ldy = 0,
+                            __nv_bfloat16* alt_hi = nullptr, __nv_bfloat16* alt_lo = nullptr) {
   if (ldy == 0) ldy = D;
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 8 * LN_ROWS - 1) / (8 * LN_ROWS));
   const int rev = traverse_dir();
-  ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0)), s);
+  ProfScope prof(PROF_LAYERNORM, (double)rows * D * (4.0 + (res ? 4.0 : 0.0) + (y ? sizeof(TOut) : 0) + (y32 ? 4.0 : 0.0) + (y_lo ? sizeof(TOut) : 0) +
+                                                     (y_dup ? sizeof(TOut) : 0) + (alt_hi ? 2.0 : 0.0) + (alt_lo ? 2.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, ldy, rows, D, eps, rev)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, alt_hi, alt_lo, ldy, rows, D, eps, rev)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -127,6 +132,13 @@ int layernorm_f32(const float* x, const float* res, const float* gamma, const fl
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
                    float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo) {
   return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps, s);
+}
+
+// fp16 output for the fp16s mode: y = fp16(LN(x)) in rows of ldy elements; y_lo (optional) = fp16 rounding residue, normally at
+// y + D so that a row is the [hi | lo] split operand of a 3-term GEMM; y32 / alt_hi / alt_lo: optional fp32 and bf16 hi / lo copies
+int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s) {
+  return launch_layernorm<__half>(x, nullptr, gamma, beta, y, y32, nullptr, y_lo, rows, D, eps, s, nullptr, ldy, alt_hi, alt_lo);
 }
 
 // LayerNorm whose output is the bf16x3 split [hi | hi | lo] (rows of 3D bf16) of the normalised row: the A operand of a split
@@ -504,6 +516,82 @@ im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int
     *reinterpret_cast<uint4*>(dst + (int64_t)px * K + j * kV) = v;
   }
 }
+// fp16s mode: cols[row] = [hi (K) | lo (K)] fp16 split of the (normalised) pixels — the A operand of the 3-term patch-embed GEMM
+// (the patch embed is the most rounding-sensitive contraction of the model: scripts/precision_emulation.py).  Same two phases with
+// an fp32 strip; phase 2 splits 4 pixels per thread into 8 B of hi and 8 B of lo.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+im2col_split_kernel(const TIn* __restrict__ x, __half* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc, bool vec_ok) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t im2col_smem[];
+  __shared__ float lut[sizeof(TIn) == 1 ? 3 * 256 : 1];
+  if constexpr (sizeof(TIn) == 1) {
+    for (int i = threadIdx.x; i < 3 * 256; i += 256) {
+      const int c = i >> 8;
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), nc.mean[c]), nc.std[c]);
+    }
+    __syncthreads();
+  }
+  float* strip = reinterpret_cast<float*>(im2col_smem);         // [3*P][ws], ws = wp*P + 4
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int Wp = wp * P, ws = Wp + 4;
+  const TIn* src = x + (int64_t)b * 3 * H * W;
+  const int Wq = Wp >> 2;
+  for (int i = threadIdx.x; i < 3 * P * Wq; i += 256) {
+    const int r = i / Wq, xx = (i - r * Wq) << 2, c = r / P, ky = r - c * P, yy = py * P + ky;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (yy < H) {
+      const TIn* row = src + ((int64_t)c * H + yy) * W;
+      if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, lut, v);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, lut);
+      }
+    }
+    store4(strip + r * ws + xx, v);
+  }
+  __syncthreads();
+  const int K = 3 * P * P, vec_per_row = P / 4, vec_per_patch = K / 4;
+  __half* dst = cols + ((int64_t)b * hp + py) * wp * 2 * K;
+  for (int i = threadIdx.x; i < wp * vec_per_patch; i += 256) {
+    const int px = i / vec_per_patch, j = i - px * vec_per_patch;     // j = (c*P + ky) * vec_per_row + kxv
+    const int r = j / vec_per_row, kxv = j - r * vec_per_row;
+    const float4 v = *reinterpret_cast<const float4*>(strip + r * ws + px * P + kxv * 4);
+    uint2 hi, lo;
+    split16x2<__half>(v.x, v.y, hi.x, lo.x);
+    split16x2<__half>(v.z, v.w, hi.y, lo.y);
+    __half* o = dst + (int64_t)px * 2 * K + j * 4;
+    *reinterpret_cast<uint2*>(o) = hi;
+    *reinterpret_cast<uint2*>(o + K) = lo;
+  }
+}
+template <typename TIn>
+int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s) {
+  if (B == 0) return SMK_OK;
+  SMK_REQUIRE(B <= 65535 && P % 4 == 0, "im2col_split: bad batch / patch size");
+  NormConst nc{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (mean_std) for (int c = 0; c < 3; ++c) { nc.mean[c] = mean_std[c]; nc.std[c] = mean_std[3 + c]; }
+  const int smem = 3 * P * (wp * P + 4) * 4;
+  SMK_REQUIRE(smem <= 227 * 1024, "im2col_split: image too wide for the shared-memory strip (%d bytes)", smem);
+  static int attr_max[kMaxDevices] = {};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr_max[dev]) {
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(im2col_split_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_max[dev] = smem;
+  }
+  {
+    ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + 4.0), s);
+    const bool vec_ok = (W & 3) == 0 && ((uintptr_t)x % (4 * sizeof(TIn))) == 0;
+    SMK_CHECK_CUDA(launch_pdl(im2col_split_kernel<TIn>, dim3(hp, B), dim3(256), (size_t)smem, s, x, cols, H, W, P, hp, wp, nc, vec_ok));
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+template int im2col_split_f16<float>(const float*, __half*, int, int, int, int, int, int, const float*, cudaStream_t);
+template int im2col_split_f16<uint8_t>(const uint8_t*, __half*, int, int, int, int, int, int, const float*, cudaStream_t);
+
 template <typename TIn, typename T>
 int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s) {
   if (B == 0) return SMK_OK;
@@ -513,10 +601,11 @@ int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, co
   if (mean_std) for (int c = 0; c < 3; ++c) { nc.mean[c] = mean_std[c]; nc.std[c] = mean_std[3 + c]; }
   const int smem = 3 * P * (wp * P + 16 / (int)sizeof(T)) * (int)sizeof(T);
   SMK_REQUIRE(smem <= 227 * 1024, "im2col: image too wide for the shared-memory strip (%d bytes)", smem);
-  static int attr_max = 0;
-  if (smem > 48 * 1024 && smem > attr_max) {
+  static int attr_max[kMaxDevices] = {};
+  const int dev = current_device();
+  if (smem > 48 * 1024 && smem > attr_max[dev]) {
     SMK_CHECK_CUDA(cudaFuncSetAttribute(im2col_kernel<TIn, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_max = smem;
+    attr_max[dev] = smem;
   }
   {
     ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + sizeof(T)), s);
@@ -624,6 +713,20 @@ int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
   return SMK_OK;
 }
 
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return SMK_OK;
+  {
+    ProfScope prof(PROF_OTHER, (double)n * 6.0, s);
+    cast_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+  }
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3-term bf16 split ("bf16x3") laid out along K so that ONE tensor-core GEMM with K' = 3K computes
 //   A·W^T ≈ A_hi·W_hi^T + A_hi·W_lo^T + A_lo·W_hi^T      (hi = bf16(x), lo = bf16(x − hi); error ~2^-16 relative)
@@ -678,6 +781,26 @@ split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ou
   __nv_bfloat16* o = out + r * 3 * K;
   o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
 }
+// fp16s mode weights: row → [hi (K) | lo (K)] fp16
+__global__ void __launch_bounds__(256)
+split2_f16_kernel(const float* __restrict__ w, int64_t ldw, __half* __restrict__ out, int64_t rows, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  const float v = w[r * ldw + k];
+  const __half hi = __float2half_rn(v);
+  __half* o = out + r * 2 * K;
+  o[k] = hi;
+  o[K + k] = __float2half_rn(v - __half2float(hi));
+}
+int split2_f16(const float* w, int64_t ldw, __half* out, int64_t rows, int K, cudaStream_t s) {
+  if (rows == 0) return SMK_OK;
+  split2_f16_kernel<<<(unsigned)((rows * K + 255) / 256), 256, 0, s>>>(w, ldw, out, rows, K);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
+}
+
 int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaStream_t s) {
   if (rows == 0) return SMK_OK;
   split3_weight_kernel<<<(unsigned)((rows * K + 255) / 256), 256, 0, s>>>(w, out, rows, K);

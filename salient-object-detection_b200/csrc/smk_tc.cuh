@@ -314,6 +314,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_maj
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with fp16 operands (A / B format 0 = F16): 11 significant bits instead of 8, same tensor-pipe rate
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool kF16>
+__host__ __device__ constexpr uint32_t idesc_16_f32(int M, int N, int a_mn_major, int b_mn_major) {
+  return kF16 ? idesc_f16_f32(M, N, a_mn_major, b_mn_major) : idesc_bf16_f32(M, N, a_mn_major, b_mn_major);
+}
 
 }  // namespace tc
 

@@ -451,3 +451,133 @@ def test_gemm_layernorm_fused_matches_torch(M_, K):
     assert (X - ref_x).abs().max().item() <= 2e-3
     ref_n = torch.nn.functional.layer_norm(X, (N,), gamma, beta, 1e-6)       # LayerNorm of the kernel's own fp32 output
     assert (Xn.float() - ref_n).abs().max().item() <= 0.02 * max(1.0, ref_n.abs().max().item())
+
+
+# ---- fp16s mode kernels --------------------------------------------------------------------------------------------------------
+def _split16(x, dt):
+    hi = x.to(dt)
+    return hi, (x - hi.float()).to(dt)
+
+
+@pytest.mark.parametrize("f16", [1, 0])
+@pytest.mark.parametrize("M_,N,K,epi,terms,out_kind", [
+    (50432, 1152, 384, 0, 2, 0),      # qkv: A_hi·(W_hi + W_lo), 16-bit output (16-warp epilogue)
+    (50432, 384, 384, 4, 3, 1),       # proj: 3 terms, fp32 residual
+    (50432, 1536, 384, 1, 3, 3),      # fc1: 3 terms, GELU, [hi | lo] output
+    (50432, 384, 1536, 4, 3, 1),      # fc2: 3 terms over K = 1536 (swap-AB form), fp32 residual
+    (20000, 4608, 384, 0, 2, 0),      # memory K/V
+    (700, 384, 768, 0, 3, 1), (130, 256, 128, 2, 1, 3), (333, 128, 64, 0, 3, 2), (5120, 768, 384, 0, 2, 1)])
+def test_gemm_split_terms_match_fp64(M_, N, K, epi, terms, out_kind, f16):
+    """smk_gemm_split: operands stored as [hi | lo] rows, 1 / 2 / 3 tensor-core terms selected by column offsets; fp16 and bf16."""
+    torch.manual_seed(40)
+    dt = torch.float16 if f16 else torch.bfloat16
+    A32 = torch.randn(M_, K, device=DEV) * 1.5
+    W32 = torch.randn(N, K, device=DEV) * 0.05
+    bias = torch.randn(N, device=DEV)
+    (ah, al), (wh, wl) = _split16(A32, dt), _split16(W32, dt)
+    A2 = torch.cat([ah, al], dim=1).contiguous()
+    W2 = torch.cat([wh, wl], dim=1).contiguous()
+    a_off, w_off = {1: ([0], [0]), 2: ([0, 0], [0, K]), 3: ([0, 0, K], [0, K, 0])}[terms]
+    C0 = torch.randn(M_, N, device=DEV) if epi & 4 else None
+    if out_kind == 1:
+        out = C0.clone() if C0 is not None else torch.empty(M_, N, device=DEV)
+    else:
+        out = torch.full((M_, N * {0: 1, 2: 3, 3: 2}[out_kind]), 7.0, dtype=dt, device=DEV)
+    ao, wo = (C.c_int32 * 3)(*a_off), (C.c_int32 * 3)(*w_off)
+    check(lib().smk_gemm_split(ptr(A2), 2 * K, ptr(W2), 2 * K, ptr(bias), ptr(out), out.shape[1], M_, N, K, epi, out_kind, f16, terms, ao, wo,
+                               stream_ptr()), "smk_gemm_split")
+    torch.cuda.synchronize()
+    # the exact value of the issued terms (fp64), and the full-precision product they approximate
+    Ah, Al, Wh, Wl = ah.double(), al.double(), wh.double(), wl.double()
+    issued = Ah @ Wh.t()
+    if terms >= 2:
+        issued = issued + Ah @ Wl.t()
+    if terms >= 3:
+        issued = issued + Al @ Wh.t()
+    issued = issued + bias.double()
+    act = (lambda t: torch.nn.functional.gelu(t)) if epi & 1 else ((lambda t: torch.relu(t)) if epi & 2 else (lambda t: t))
+    ref = act(issued) + (C0.double() if C0 is not None else 0)
+    if out_kind == 1:
+        got = out.double()
+    elif out_kind == 0:
+        got = out.double()
+    elif out_kind == 3:
+        got = out[:, :N].double() + out[:, N:].double()
+    else:
+        assert torch.equal(out[:, :N], out[:, N:2 * N])
+        got = out[:, :N].double() + out[:, 2 * N:].double()
+    scale = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    if out_kind == 0:
+        assert err <= (2.0 ** -10 if f16 else 2.0 ** -7) * scale, err          # one rounding of the 16-bit output
+    else:
+        assert err <= 2e-4 * scale, err                                        # fp32 accumulate (+ gelu_fast's 2e-5)
+    if terms == 3:      # and the 3-term product is ~fp32-accurate against the unsplit fp32 operands
+        full = act(A32.double() @ W32.double().t() + bias.double()) + (C0.double() if C0 is not None else 0)
+        assert (got - full).abs().max().item() <= (2e-4 if f16 else 6e-4) * scale
+
+
+@pytest.mark.parametrize("B,N,out_mode", [(3, 197, 0), (64, 197, 3), (2, 256, 3), (5, 130, 0), (150, 197, 3), (2, 17, 3)])
+def test_attention_tcgen05_fp16_matches_torch(B, N, out_mode):
+    """fp16 operands on the tcgen05 attention kernel (fp16s mode): plain fp16 output and the [hi | lo] fp16 split output."""
+    torch.manual_seed(41)
+    H, dh = 6, 64
+    D = H * dh
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 1.5).to(torch.float16)
+    ldo = D if out_mode == 0 else 2 * D
+    out = torch.full((B * N, ldo), 7.0, device=DEV, dtype=torch.float16)
+    check(lib().smk_attention_tc_f16(ptr(qkv), ptr(out), ldo, out_mode, B, N, H, 0.125, stream_ptr()), "smk_attention_tc_f16")
+    torch.cuda.synchronize()
+    q, k, v = [t.double().view(B, N, H, dh).transpose(1, 2) for t in qkv.view(B, N, 3 * D).split(D, dim=-1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, D)
+    got = out[:, :D].double() + (out[:, D:].double() if out_mode == 3 else 0)
+    err = (got - ref).abs().max().item()
+    # fp16 P (2^-11 relative) and ex2.approx; the plain output adds one fp16 rounding of values up to ~4
+    assert err <= (6e-3 if out_mode == 0 else 4e-3), err
+    assert (got - ref).abs().mean().item() <= 3e-4
+    if out_mode == 3:
+        assert (out[:, D:].float().abs() <= out[:, :D].float().abs() * 2.0 ** -10 + 1e-7).all()     # lo is the rounding residue of hi
+
+
+@pytest.mark.parametrize("nq,B", [(20, 37), (10, 5), (32, 3), (1, 2)])
+def test_decoder_self_attention_fp32_matches_torch(nq, B):
+    torch.manual_seed(42)
+    H, dh = 6, 64
+    D = H * dh
+    qk = torch.randn(B * nq, 2 * D, device=DEV) * 3.0            # large scores: a peaked softmax, as with query_embed ~ N(0, 1)
+    v = torch.randn(B * nq, D, device=DEV)
+    out = torch.full((B * nq, 3 * D), 7.0, device=DEV, dtype=torch.bfloat16)
+    check(lib().smk_dec_self_attention(ptr(qk), 2 * D, ptr(v), D, ptr(out), B, nq, H, 0.125, stream_ptr()), "smk_dec_self_attention")
+    torch.cuda.synchronize()
+    qh = qk[:, :D].double().view(B, nq, H, dh).transpose(1, 2)
+    kh = qk[:, D:].double().view(B, nq, H, dh).transpose(1, 2)
+    vh = v.double().view(B, nq, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * nq, D)
+    assert torch.equal(out[:, :D], out[:, D:2 * D])
+    got = out[:, :D].double() + out[:, 2 * D:].double()
+    assert (got - ref).abs().max().item() <= 1e-4           # fp32 math; the bf16 hi + lo pair keeps ~16 bits of values up to ~4
+
+
+@pytest.mark.parametrize("Lq,Lk,kv_rows,kv_row0,q_f32", [(20, 196, 197, 1, 1), (20, 196, 197, 1, 0), (10, 144, 145, 1, 1), (32, 256, 256, 0, 1)])
+def test_attention_small_fp16_matches_torch(Lq, Lk, kv_rows, kv_row0, q_f32):
+    """fp16s-mode decoder cross-attention: fp16 K / V, the query either fp16 or fp32 rows rounded while staged; bf16 split output."""
+    torch.manual_seed(43)
+    B, H, dh = 37, 6, 64
+    D = H * dh
+    q32 = torch.randn(B * Lq, D, device=DEV)
+    q16 = q32.to(torch.float16)
+    kv = torch.randn(B * kv_rows, 2 * D, device=DEV).to(torch.float16)
+    k_view, v_view = kv[:, :D], kv[:, D:]
+    out = torch.full((B * Lq, 3 * D), 7.0, device=DEV, dtype=torch.bfloat16)
+    qarg = q32 if q_f32 else q16
+    check(lib().smk_attention_small_f16(ptr(qarg), D, C.c_void_p(k_view.data_ptr()), 2 * D, C.c_void_p(v_view.data_ptr()), 2 * D, kv_rows, kv_row0,
+                                        ptr(out), 3 * D, 2, B, Lq, Lk, H, 0.125, q_f32, stream_ptr()))
+    torch.cuda.synchronize()
+    qh = q16.double().view(B, Lq, H, dh).transpose(1, 2)
+    kk = kv.double().view(B, kv_rows, 2 * D)[:, kv_row0:kv_row0 + Lk]
+    kh = kk[..., :D].reshape(B, Lk, H, dh).transpose(1, 2)
+    vh = kk[..., D:].reshape(B, Lk, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    assert torch.equal(out[:, :D], out[:, D:2 * D])
+    got = out[:, :D].double() + out[:, 2 * D:].double()
+    assert (got - ref).abs().max().item() <= 3e-3            # fp16 P: 2^-11 relative; bf16 operands give ~2e-2 here
