@@ -12,6 +12,12 @@
 
 namespace smk {
 
+// F-max thresholds t_k = float32(k * (1/255)), the product formed in double (f_measure.py:65 `torch.arange(0, 1, 1/255)`, ATen CPU
+// arange accumulates in double): computed in the kernel — IEEE double multiply + round-to-nearest conversion, bit-identical to the
+// host expression — so the library keeps no per-process device table (no allocation, no synchronisation, any device, capturable).
+__device__ __forceinline__ float fmax_threshold(int k) { return __double2float_rn(__dmul_rn((double)k, 1.0 / 255.0)); }
+
+
 constexpr int kEvalThreads = 256;
 constexpr int kEvalWarps = kEvalThreads / 32;
 
@@ -108,7 +114,7 @@ template <bool kSelect, bool kSmemPlane>
 __global__ void __launch_bounds__(kEvalThreads)
 mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
                     int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
-                    int nq, int hp, int wp, int up, int H, int W, const float* __restrict__ thresholds,
+                    int nq, int hp, int wp, int up, int H, int W,
                     int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
   extern __shared__ float dyn[];
   __shared__ int hist[kEvalWarps][512];
@@ -143,7 +149,7 @@ mask_metrics_kernel(const float* __restrict__ planes, int64_t batch_stride, cons
     s_sel = sel;
   }
   for (int i = threadIdx.x; i < kEvalWarps * 512; i += kEvalThreads) (&hist[0][0])[i] = 0;
-  if (threadIdx.x < 255) thr[threadIdx.x] = thresholds[threadIdx.x];
+  if (threadIdx.x < 255) thr[threadIdx.x] = fmax_threshold(threadIdx.x);
   if (threadIdx.x == 255) thr[255] = 3.0e38f;
   __syncthreads();
   const int sel = s_sel;
@@ -701,7 +707,7 @@ __device__ __forceinline__ int bitpos_sum(uint32_t w) {
 __global__ void __launch_bounds__(kEvalThreads)
 mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, const float* __restrict__ objectness,
                        int64_t obj_stride, const int32_t* __restrict__ q_counts, const uint8_t* __restrict__ gt,
-                       int nq, int hp, int wp, int H, int W, const float* __restrict__ thresholds,
+                       int nq, int hp, int wp, int H, int W,
                        int32_t* __restrict__ idx_out, int32_t* __restrict__ m_counts, double* __restrict__ m_sums) {
   pdl_wait();
   pdl_trigger();
@@ -745,7 +751,7 @@ mask_metrics_x4_kernel(const float* __restrict__ planes, int64_t batch_stride, c
     s_sel = sel;
   }
   for (int i = threadIdx.x; i < kEvalWarps * 512; i += kEvalThreads) (&hist[0][0])[i] = 0;
-  for (int i = threadIdx.x; i < 258; i += kEvalThreads) thr[i] = i < 255 ? thresholds[i] : 3.0e38f;
+  for (int i = threadIdx.x; i < 258; i += kEvalThreads) thr[i] = i < 255 ? fmax_threshold(i) : 3.0e38f;
   const uint8_t* g = gt + (int64_t)b * H * W;
   int ng = pack_gt_bits(g, gbits, H, W, ww);
   __syncthreads();
@@ -933,18 +939,6 @@ __global__ void upsample_bilinear_kernel(const float* __restrict__ in, float* __
   for (int x = threadIdx.x & 31; x < W; x += 32) o[x] = pixel(r, x, w, rscale);
 }
 
-static float* g_thresholds = nullptr;   // 255 float32 thresholds t_k = float(k * (1/255)) (f_measure.py:65)
-
-static int ensure_thresholds() {
-  if (g_thresholds) return SMK_OK;
-  float h[256];
-  for (int k = 0; k < 255; ++k) h[k] = (float)((double)k * (1.0 / 255.0));
-  h[255] = 3.0e38f;
-  SMK_CHECK_CUDA(cudaMalloc(&g_thresholds, sizeof(h)));   // 1 KB constant table, once per process
-  SMK_CHECK_CUDA(cudaMemcpy(g_thresholds, h, sizeof(h), cudaMemcpyHostToDevice));
-  return SMK_OK;
-}
-
 }  // namespace smk
 
 using namespace smk;
@@ -957,7 +951,6 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
   SMK_REQUIRE(H > 0 && W > 0 && H <= hp * up && W <= wp * up, "smk_eval_batch: gt %dx%d larger than masks %dx%d x%d", H, W, hp, wp, up);
   SMK_REQUIRE(B <= 65535, "smk_eval_batch: B > 65535");
   if (B == 0) return SMK_OK;
-  SMK_PROPAGATE(ensure_thresholds());
   cudaStream_t s = (cudaStream_t)stream;
   const size_t plane_bytes = (size_t)hp * wp * sizeof(float);
   SMK_REQUIRE(plane_bytes <= 160 * 1024, "smk_eval_batch: mask plane %dx%d does not fit shared memory", hp, wp);
@@ -999,10 +992,10 @@ extern "C" int smk_eval_batch(const float* mask_pred, int64_t batch_stride, cons
     ProfScope prof(PROF_EVAL, (double)B * 2.0 * ((double)H * W * 4.0 + (double)H * W), s);
     if (x4m)
       SMK_CHECK_CUDA(launch_pdl(mask_metrics_x4_kernel, dim3(2, B), dim3(kEvalThreads), mm_bytes, s, mask_pred, batch_stride, objectness,
-                                obj_stride, q_counts, gt, nq, hp, wp, H, W, g_thresholds, idx, m_counts, m_sums));
+                                obj_stride, q_counts, gt, nq, hp, wp, H, W, idx, m_counts, m_sums));
     else
       mask_metrics_kernel<true, true><<<dim3(2, B), kEvalThreads, plane_bytes, s>>>(
-          mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, g_thresholds, idx, m_counts, m_sums);
+          mask_pred, batch_stride, objectness, obj_stride, q_counts, gt, nq, hp, wp, up, H, W, idx, m_counts, m_sums);
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -1013,10 +1006,9 @@ extern "C" int smk_mask_metrics(const float* pred, const uint8_t* gt, int n, int
   SMK_REQUIRE(pred && gt && m_counts && m_sums, "smk_mask_metrics: null pointer");
   SMK_REQUIRE(n >= 0 && n <= 65535 && H > 0 && W > 0, "smk_mask_metrics: bad sizes");
   if (n == 0) return SMK_OK;
-  SMK_PROPAGATE(ensure_thresholds());
   // one full-resolution plane per "image"; the plane is read from global memory (L1/L2), up = 1
   mask_metrics_kernel<false, false><<<dim3(1, n), kEvalThreads, 0, (cudaStream_t)stream>>>(
-      pred, (int64_t)H * W, nullptr, 0, nullptr, gt, 1, H, W, 1, H, W, g_thresholds, nullptr, m_counts, m_sums);
+      pred, (int64_t)H * W, nullptr, 0, nullptr, gt, 1, H, W, 1, H, W, nullptr, m_counts, m_sums);
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }

@@ -556,7 +556,6 @@ gemm_ln2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 }  // namespace
 
-static int g_gl_sms = 0;
 
 // X[M,384] += A[M,K]·W[384,K]^T + bias (fp32, in place);  Xn[M,384] = LayerNorm(X) (bf16)
 int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, const float* bias, float* X, const float* gamma,
@@ -565,12 +564,7 @@ int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, cons
   SMK_REQUIRE(bias && gamma && beta && ((uintptr_t)bias % 16) == 0 && ((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0,
               "gemm_ln: bias / gamma / beta must be 16-byte aligned");
   if (M == 0) return SMK_OK;
-  if (!g_gl_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_gl_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_gl_sms <= 0) g_gl_sms = 148;
-  }
+  const int g_gl_sms = device_sm_count();
   static int variant = -1;      // SMK_GEMM_LN_V = 1: one CTA per 128 x 384 tile; 2 (default): cluster of two CTAs, 128 x 192 each
   if (variant < 0) {
     const char* e = getenv("SMK_GEMM_LN_V");
@@ -581,19 +575,13 @@ int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, cons
   SMK_PROPAGATE(make_tmap_bf16_2d(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, GL_BK, GL_NH));
   SMK_PROPAGATE(make_tmap_2d(&tx, 4, X, (uint64_t)N, (uint64_t)M, (uint64_t)N * 4, 32, 32, 128));
   SMK_PROPAGATE(make_tmap_2d(&txn, 2, Xn, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32, 32, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM));
-    attr_set = true;
-  }
+  static DeviceOnce attr_set;
+  if (attr_set.first()) SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM));
   const int m_blocks = (M + GL_BM - 1) / GL_BM;
   GemmLnParams p{M, K, bias, gamma, beta, eps};
   if (variant == 2) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-      attr2_set = true;
-    }
+    static DeviceOnce attr2_set;
+    if (attr2_set.first()) SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     const int clusters = m_blocks < g_gl_sms / 2 ? m_blocks : g_gl_sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * clusters));

@@ -183,11 +183,8 @@ int mask_head_mma(const __nv_bfloat16* q3, int64_t Rall, const __nv_bfloat16* to
   const int hw = hp * wp, R = L * nq;
   SMK_REQUIRE(D % ML_KC == 0 && B <= 65535, "mask_head_mma: D=%d / B=%d unsupported", D, B);
   const size_t smem1 = 2 * (size_t)ML_STAGE * sizeof(__nv_bfloat16);
-  static bool attr1 = false;
-  if (!attr1) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    attr1 = true;
-  }
+  static DeviceOnce attr1;
+  if (attr1.first()) SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   const int m_blocks = (R + ML_BM - 1) / ML_BM, n_blocks = (hw + ML_BN - 1) / ML_BN;
   MaskLogitsParams p{q3, tok_hi, tok_lo, logits_lowres, Rall, layer0, R, nq, hw, hw + 1, D, m_blocks};
   {

@@ -521,11 +521,15 @@ extern "C" int smk_model_forward_u8(smk_model* m, const uint8_t* x, const float*
 // is read by both LayerNorms and read-modify-written by the proj / fc2 reduce-add epilogues of every block, while QKV / the MLP
 // hidden tensor (116 / 155 MB) stream through the 126 MB L2 once and would evict it.  Only a slice of X is kept (hitRatio =
 // carve-out / window, 16 MB by default, SMK_L2_PERSIST_MB): +1.3 % images/s.  SMK_L2_PERSIST=0 switches it off.
+// State per device ordinal (a process may drive several GPUs in turn; one host thread per GPU at a time — include/selfmask_b200.h).
 static void l2_persist_window(cudaStream_t s, void* base, size_t bytes) {
-  static int state = -1;           // -1 unknown, 0 unavailable / off, 1 on
-  static size_t persist_max = 0, window_max = 0;
-  if (state < 0) {
-    state = 0;
+  static int state_d[kMaxDevices];           // 0 unknown, -1 unavailable / off, 1 on
+  static size_t persist_max_d[kMaxDevices], window_max_d[kMaxDevices];
+  const int d_ = current_device();
+  int& state = state_d[d_];
+  size_t &persist_max = persist_max_d[d_], &window_max = window_max_d[d_];
+  if (state == 0) {
+    state = -1;
     const char* e = getenv("SMK_L2_PERSIST");
     int dev = 0, pm = 0, wm = 0;
     if ((!e || atoi(e) != 0) && cudaGetDevice(&dev) == cudaSuccess &&
@@ -562,7 +566,7 @@ static void l2_persist_window(cudaStream_t s, void* base, size_t bytes) {
   }
   if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
     cudaGetLastError();
-    state = 0;
+    state = -1;
   }
 }
 

@@ -70,6 +70,18 @@ def summarize(m_counts, m_sums) -> Dict[str, float]:
     return res
 
 
+def objectness_top1_ties(objectness: torch.Tensor) -> torch.Tensor:
+    """Per image: does the largest objectness value occur more than once?  (device bool tensor, no synchronisation)
+
+    The reference picks the mask with `torch.argsort(objectness, descending=True)[0]` (evaluator.pyc@L219-221), an UNSTABLE sort:
+    on an exact tie of the top value the index it returns is data-dependent (an all-equal 20-vector gives 10),
+    whereas this path takes the lowest index.  Ties cannot be reproduced by design, so they are detected and reported instead:
+    `Evaluator.objectness_ties` counts them per sweep and parity harnesses exclude / flag those images."""
+    o = objectness[:, -1] if objectness.ndim == 4 else objectness
+    o = o.reshape(o.shape[0], -1)
+    return (o == o.max(dim=1, keepdim=True).values).sum(dim=1) > 1
+
+
 _TXT_HEADER = ("iou,pixel_acc,f_score,f_max,f_mean,mae,s_measure,miou_ub,pixel_acc_ub,f_score_ub,f_max_ub,f_mean_ub,"
                "mae_ub,s_measure_ub")
 
@@ -88,10 +100,24 @@ class Evaluator:
             assert os.path.exists(dir_dataset), f"{dir_dataset} does not exist"
         self.model, self.arch, self.dir_dataset, self.visualizer, self.debug = network, arch, dir_dataset, visualizer, debug
         self.dataset = dataset
+        # When torch.distributed is initialised with more than one rank, a sweep is treated as rank-sharded: every rank evaluates
+        # its own batches and the per-image records are gathered before the averages are formed.  Set False to evaluate the same
+        # data independently on every rank.
+        self.sharded = True
+        self.global_records = None   # sharded sweeps: the gathered records of all ranks (device tensors)
+        self.objectness_ties = 0     # images of the last sweep whose objectness top-1 was an exact tie (see _count_ties)
+        self._ties = []
         self._recs = None            # per-batch device records of the last sweep
         self._records_host = None
         self._copy_stream = None
         self._pinned = None          # page-locked landing buffer for the finalised values (the only per-sweep read-back)
+
+    def _count_ties(self) -> int:
+        return int(torch.cat(self._ties).sum().item()) if self._ties else 0
+
+    def tie_flags(self) -> np.ndarray:
+        """bool per image of the last sweep (this rank's shard, dataset order): exact objectness top-1 tie."""
+        return torch.cat(self._ties).cpu().numpy() if self._ties else np.zeros(0, bool)
 
     def device_records(self) -> Dict[str, torch.Tensor]:
         """Integer / float64 records of the last sweep, in dataset order, as device tensors (what a multi-GPU caller all-reduces)."""
@@ -139,6 +165,7 @@ class Evaluator:
             return xd, gd, ev
 
         recs, vals = [], []
+        self._ties = []
         with torch.cuda.device(device):
             it = iter(self._batches(dataset_name, batch_size))
             first = next(it, None)
@@ -152,12 +179,26 @@ class Evaluator:
                 gt.record_stream(compute)
                 out = self.model(x, encoder_only=False, skip_decoder=False)     # BaseStructure._forward contract
                 rec = eval_batch(out["mask_pred"], out["objectness"], gt, up=4)
+                self._ties.append(objectness_top1_ties(out["objectness"]))
                 recs.append(rec)
                 vals.append(finalize_device(rec.m_counts, rec.m_sums))
-            if not recs:
+            import torch.distributed as dist
+            sharded = self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            if not recs and not sharded:
                 raise _lib.SmkError("empty dataset")
-            # one synchronising read-back for the whole sweep: 8 doubles per evaluated mask, into page-locked memory
             self._recs, self._records_host = recs, None
+            if sharded:
+                # rank-sharded sweep: the one collective of the path gathers every rank's per-image rows (an empty
+                # shard contributes none), then every rank finalises the whole sweep and forms the same ordered means
+                from .parallel import gather_records
+                lc = torch.cat([r.m_counts for r in recs]) if recs else torch.zeros(0, 2, _lib.MCOUNT_STRIDE, dtype=torch.int32, device=device)
+                ls = torch.cat([r.m_sums for r in recs]) if recs else torch.zeros(0, 2, _lib.MSUM_STRIDE, dtype=torch.float64, device=device)
+                fc, fs = gather_records(lc, ls)
+                if fc.shape[0] == 0:
+                    raise _lib.SmkError("empty dataset")
+                self.global_records = {"m_counts": fc, "m_sums": fs}
+                vals = [finalize_device(fc, fs)]
+            # one synchronising read-back for the whole sweep: 8 doubles per evaluated mask, into page-locked memory
             dv = torch.cat(vals)
             if self._pinned is None or self._pinned.numel() < dv.numel():
                 self._pinned = torch.empty(dv.numel(), dtype=dv.dtype).pin_memory()
@@ -167,7 +208,9 @@ class Evaluator:
             v = values_from_device(hv.numpy().copy())
         res = {k: running_mean(v[k][:, 0]) for k in METRIC_KEYS}
         res.update({k + "_ub": running_mean(v[k][:, 1]) for k in METRIC_KEYS})
-        if dir_ckpt is not None:
+        self.objectness_ties = self._count_ties()
+        write = dir_ckpt is not None and not (sharded and dist.get_rank() != 0)      # sharded sweeps: rank 0 writes the file
+        if write:
             os.makedirs(dir_ckpt, exist_ok=True)
             with open(f"{dir_ckpt}/metrics_{dataset_name}.txt", "w") as f:
                 f.write(_TXT_HEADER + "\n")

@@ -1,11 +1,10 @@
 """GPU parity tests of the whole path: model(image) -> {mask_pred, objectness} and the evaluator, CUDA vs
 the CPU oracle on identical synthetic weights / images, plus the committed reference fixtures.
 
-Tolerances (north_star): fp32 validation mode — mask logits max-abs 1e-4 is the goal; we assert 5e-4 because the
-contraction is done at patch resolution before the bilinear upsample (a re-association the oracle itself shows
-moves logits by ~8e-5) and report the measured value.  bf16 mode — logits 2e-2 / IoU agreement
-99.9 % are NOT reachable by a single-pass bf16-operand pipeline on these weights; the test
-asserts the measured envelope (mean IoU agreement >= 99 %) and writes the numbers to gpurun_out/parity_report.json."""
+Tolerances (north_star): fp32 validation mode — mask logits max-abs 1e-4 (asserted).  Tensor-core modes — logits 2e-2 / IoU
+agreement 99.9 %: asserted for fp16s (the benchmarked mode) and bf16x3.  They are NOT reachable by a single-pass bf16-operand
+pipeline on these weights (scripts/precision_emulation.py): the bf16 throughput mode is asserted against
+~1.5x its measured envelope and the numbers are written to gpurun_out/parity_report.json."""
 import json
 import os
 
@@ -68,7 +67,7 @@ def test_fp32_mode_matches_oracle(nq, B, H, W):
     assert out["mask_pred"].shape == ref["mask_pred"].shape and out["objectness"].shape == ref["objectness"].shape
     assert stats["tokens_maxabs"] <= 2e-4, stats
     assert stats["queries_maxabs"] <= 2e-4, stats
-    assert stats["logits_maxabs"] <= 5e-4, stats
+    assert stats["logits_maxabs"] <= 1e-4, stats                    # north_star: 1e-4 in the fp32 validation mode
     assert stats["objectness_maxabs"] <= 1e-5, stats
     assert stats["iou_agreement_min"] >= 0.999, stats
     assert stats["top1_match"], stats
@@ -117,9 +116,10 @@ def test_bf16_mode_parity_envelope():
         "top1_match": int((top_ours == top_ref).sum()), "top1_total": int(B),
     }
     _report("bf16_nq20_224x224_B8", stats)
-    assert np.isfinite(stats["logits_maxabs"])
-    assert stats["iou_agreement_mean"] >= 0.99, stats
-    assert stats["logits_maxabs"] <= 1.5, stats
+    # ~1.5x the measured envelope (0.30 / 0.17 last layer / 99.50 % mean, 95.6 % min): a real regression must not pass
+    assert stats["logits_maxabs"] <= 0.5 and stats["logits_last_layer_maxabs"] <= 0.3, stats
+    assert stats["iou_agreement_mean"] >= 0.99 and stats["iou_agreement_min"] >= 0.93, stats
+    assert stats["top1_match"] == B, stats
 
 
 def test_bf16_mode_long_sequence_384():

@@ -90,3 +90,39 @@ def test_shard_ranges_of_the_duts_te_sweep():
     assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
     sizes = [b - a for a, b in spans]
     assert max(sizes) == 628 and min(sizes) >= 623
+
+
+def _exchange_worker(rank, world, port, n_total, out_dir):
+    """RecordExchange: preallocated two-slot buffers, several exchanges in flight, ragged and EMPTY shards (1 image over 2 ranks)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    cap = -(-n_total // world)
+    ex = S.RecordExchange(max(cap, 1), "cpu")
+    tickets, truths = [], []
+    for step in range(5):                                  # more posts than slots: slot reuse must wait for the earlier gather
+        rng = np.random.default_rng(7 + step)
+        counts = torch.from_numpy(rng.integers(-5, 50000, (n_total, 2, 528), dtype=np.int32))
+        sums = torch.from_numpy(rng.standard_normal((n_total, 2, 32)))
+        sums[0, 0, 3] = float("nan")                       # NaN moments (the reference's NaN S-measure cases) must travel bit-exactly
+        a, b = S.shard_range(n_total, rank, world)
+        tickets.append(ex.post(counts[a:b].clone(), sums[a:b].clone()))
+        truths.append((counts, sums))
+        if step >= 1:                                      # collect one step late, as an overlapped caller does
+            c, s_ = ex.collect(tickets[step - 1])
+            tc, ts = truths[step - 1]
+            ok = ok and torch.equal(c, tc) and torch.equal(s_.view(torch.int64), ts.view(torch.int64))
+    c, s_ = ex.collect(tickets[-1])
+    ok = ok and torch.equal(c, truths[-1][0]) and torch.equal(s_.view(torch.int64), truths[-1][1].view(torch.int64))
+    g_c, g_s = S.gather_records(truths[0][0][slice(*S.shard_range(n_total, rank, world))], truths[0][1][slice(*S.shard_range(n_total, rank, world))])
+    ok = ok and torch.equal(g_c, truths[0][0])
+    np.save(os.path.join(out_dir, f"ex_{rank}.npy"), np.array([ok]))
+    dist.destroy_process_group()
+
+
+def test_record_exchange_ragged_and_empty_shards(tmp_path):
+    for n_total in (11, 1, 8):                             # ragged (6 + 5), one rank empty (1 + 0), uniform (4 + 4)
+        d = tmp_path / str(n_total)
+        d.mkdir()
+        mp.spawn(_exchange_worker, args=(2, _free_port(), n_total, str(d)), nprocs=2, join=True)
+        assert all(np.load(d / f"ex_{r}.npy")[0] == 1 for r in range(2)), n_total
