@@ -82,7 +82,7 @@ int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s
 int mask_head_mma(const __nv_bfloat16* q3, int64_t Rall, const __nv_bfloat16* tok_hi, const __nv_bfloat16* tok_lo, float* logits_lowres,
                   float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D, int hp, int wp, cudaStream_t s);
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D,
-              int hp, int wp, int sf, cudaStream_t s);
+              int hp, int wp, int sf, cudaStream_t s, bool precise = false);
 int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s);
 int permute_lb(const float* in, float* out, int L, int B, int n, cudaStream_t s);
 int query_mean(const float* qlast, float* out, int B, int nq, int D, cudaStream_t s);

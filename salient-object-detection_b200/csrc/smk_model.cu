@@ -899,7 +899,8 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     if (bf && c.scale_factor == 4)
       SMK_PROPAGATE(mask_head_mma(m->a3q, R, m->tokb, m->tokl, m->mlog, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, s));
     else
-      SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s));
+      SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s,
+                              m->mode == SMK_MODE_FP32));
   }
   if (objectness) {
     TagScope tg(TAG_OBJECTNESS);

@@ -2,6 +2,8 @@
 // softmax attention, patch im2col, token assembly, residual+LayerNorm, mask head (contraction at patch
 // resolution → bilinear → sigmoid), objectness tail, casts.  Memory-bound ones are vectorised, one warp
 // per row with shuffle reductions.
+#include <type_traits>
+
 #include "smk_common.cuh"
 #include "smk_kernels.h"
 
@@ -820,8 +822,11 @@ int split3_weight(const float* w, __nv_bfloat16* out, int64_t rows, int K, cudaS
 // ------------------------------------------------------------------------------------------------
 constexpr int MH_KC = 32, MH_LD = MH_KC + 4, MH_MAXT_CAP = 3, MH_THREADS = 256;
 
-template <int MH_MAXT>   // (8 rows x 4 tokens) register tiles per thread: 1 at 224x224 (245 tiles), up to 3 at 384x384
-__global__ void __launch_bounds__(MH_THREADS, MH_MAXT == 1 ? 3 : 1)
+// kDouble (fp32 validation mode): the 384-term dot products are accumulated in float64, so this side of the comparison carries no
+// summation-order noise of its own — what remains against the reference is the reference's own fp32 rounding (~5e-5 on logits of
+// magnitude up to 70; two fp32 sums in different orders differ by up to 1e-4, the whole north_star budget).
+template <int MH_MAXT, bool kDouble>   // (8 rows x 4 tokens) register tiles per thread: 1 at 224x224 (245 tiles), up to 3 at 384x384
+__global__ void __launch_bounds__(MH_THREADS, (MH_MAXT == 1 && !kDouble) ? 3 : 1)
 mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const float* __restrict__ tokens /*[B,N,D] final LN*/,
                  float* __restrict__ mask_pred /*[B,L,nq,hp*sf,wp*sf]*/, float* __restrict__ logits_out, int B, int L, int Lg, int nq,
                  int D, int hp, int wp, int sf, int layer0) {
@@ -840,13 +845,14 @@ mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const floa
   const float* mem = tokens + ((int64_t)b * N + 1) * D;    // skip the cls token (maskformer.py:104)
   const int n_tiles = RO * NQ4;
 
-  float acc[MH_MAXT][8][4];
+  using AccT = typename std::conditional<kDouble, double, float>::type;
+  AccT acc[MH_MAXT][8][4];
 #pragma unroll
   for (int t = 0; t < MH_MAXT; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[t][j][i] = 0.f;
+      for (int i = 0; i < 4; ++i) acc[t][j][i] = (AccT)0;
 
   for (int k0 = 0; k0 < D; k0 += MH_KC) {
     __syncthreads();
@@ -883,11 +889,18 @@ mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const floa
             const float4 av = *reinterpret_cast<const float4*>(ap + j * MH_LD + k);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float a = acc[t][j][i];
-              a = fmaf(av.x, tv[i].x, a);
-              a = fmaf(av.y, tv[i].y, a);
-              a = fmaf(av.z, tv[i].z, a);
-              a = fmaf(av.w, tv[i].w, a);
+              AccT a = acc[t][j][i];
+              if constexpr (kDouble) {
+                a = fma((double)av.x, (double)tv[i].x, a);
+                a = fma((double)av.y, (double)tv[i].y, a);
+                a = fma((double)av.z, (double)tv[i].z, a);
+                a = fma((double)av.w, (double)tv[i].w, a);
+              } else {
+                a = fmaf(av.x, tv[i].x, a);
+                a = fmaf(av.y, tv[i].y, a);
+                a = fmaf(av.z, tv[i].z, a);
+                a = fmaf(av.w, tv[i].w, a);
+              }
               acc[t][j][i] = a;
             }
           }
@@ -907,7 +920,7 @@ mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const floa
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int n = tq + NQ4 * i;
-            if (n < hw) lg[r * hw + n] = acc[t][j][i];
+            if (n < hw) lg[r * hw + n] = (float)acc[t][j][i];
           }
         }
       }
@@ -951,7 +964,7 @@ mask_head_kernel(const float* __restrict__ queries /*[Lall,B,nq,D]*/, const floa
   }
 }
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq,
-              int D, int hp, int wp, int sf, cudaStream_t s) {
+              int D, int hp, int wp, int sf, cudaStream_t s, bool precise) {
   if (B == 0) return SMK_OK;
   SMK_REQUIRE(D % MH_KC == 0 && B <= 65535, "mask_head: D=%d unsupported", D);
   const int hw = hp * wp, NQ4 = (hw + 3) / 4;
@@ -964,7 +977,8 @@ int mask_head(const float* queries, const float* tokens, float* mask_pred, float
   SMK_REQUIRE(n_tiles <= MH_MAXT_CAP * MH_THREADS, "mask_head: %d queries x %d patches exceed the register tiling", nq, hw);
   const size_t smem = ((size_t)Lg * nq * hw + (size_t)((Lg * nq + 7) / 8 * 8) * MH_LD + (size_t)NQ4 * 4 * MH_LD) * sizeof(float);
   SMK_REQUIRE(smem <= 220 * 1024, "mask_head: %zu bytes of shared memory needed", smem);
-  auto kern = n_tiles <= MH_THREADS ? mask_head_kernel<1> : mask_head_kernel<MH_MAXT_CAP>;
+  auto kern = precise ? (n_tiles <= MH_THREADS ? mask_head_kernel<1, true> : mask_head_kernel<MH_MAXT_CAP, true>)
+                      : (n_tiles <= MH_THREADS ? mask_head_kernel<1, false> : mask_head_kernel<MH_MAXT_CAP, false>);
   if (smem > 48 * 1024) SMK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     // algorithmic bytes: read tokens + queries, write the [nq, hp*sf, wp*sf] probability planes

@@ -43,7 +43,7 @@ def counts_above_thresholds(hist: np.ndarray) -> np.ndarray:
 
 def s_measure_from_sums(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
     """s_measure.py:108-124 from moment sums (float64).  counts [...,528] int, sums [...,32] float64.
-    Vectorised over records; every expression keeps the operation order of `_s_measure_from_sums_loop` (same IEEE
+    Vectorised over records; every expression keeps the operation order of the scalar twin `tests/helpers.py::s_measure_from_sums_loop` (same IEEE
     double results, NaN cases included)."""
     counts = np.asarray(counts)
     sums = np.asarray(sums, np.float64)
@@ -86,67 +86,6 @@ def s_measure_from_sums(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5
         val = np.where(val < 0, 0.0, val)
         out = np.where(G == 0, 1.0 - mean_p, np.where(G == n, mean_p, val))
     return out.reshape(shape)
-
-
-def _s_measure_from_sums_loop(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
-    """Per-record scalar restatement (python floats) of `s_measure_from_sums`; kept as the readable definition and as
-    the test oracle of the vectorised version."""
-    counts = np.asarray(counts)
-    sums = np.asarray(sums, np.float64)
-    out = np.empty(counts.shape[:-1], np.float64)
-    flat_c, flat_s, flat_o = counts.reshape(-1, counts.shape[-1]), sums.reshape(-1, sums.shape[-1]), out.reshape(-1)
-    for i in range(flat_c.shape[0]):
-        c, s = flat_c[i], flat_s[i]
-        n, G = float(c[519]), float(c[514])
-        mean_p = s[0] / n
-        if G == 0:
-            flat_o[i] = 1.0 - mean_p
-            continue
-        if G == n:
-            flat_o[i] = mean_p
-            continue
-        with np.errstate(all="ignore"):
-            def obj(sum1, sum2, cnt):                      # s_measure.py:54-60, unbiased std
-                mu = sum1 / cnt
-                var = (sum2 - cnt * mu * mu) / (cnt - 1) if cnt > 1 else float("nan")
-                sd = math.sqrt(max(var, 0.0)) if not math.isnan(var) else float("nan")
-                return 2.0 * mu / (mu * mu + 1.0 + sd + 1e-20)
-            u = G / n
-            s_obj = u * obj(s[3], s[4], G) + (1 - u) * obj(s[5], s[6], n - G)
-            X, Y = float(c[517]), float(c[518])
-            hw = n
-            # widths are not in the record: recover W, H from quadrant pixel counts is unnecessary — the
-            # weights only need X*Y/area etc., and (W-X)*Y = N_RT, X*(H-Y) = N_LB
-            q = s[8:28].reshape(4, 5)
-            w1 = F32(F32(X) * F32(Y)) / F32(hw)
-            w2 = F32(q[1, 0]) / F32(hw)
-            w3 = F32(q[2, 0]) / F32(hw)
-            w4 = F32(1) - w1 - w2 - w3
-            Q = []
-            for k in range(4):
-                N, sp, sp2, sg, spg = q[k]
-                if N == 0:
-                    Q.append(float("nan"))
-                    continue
-                x, y = sp / N, sg / N
-                den = N - 1 + 1e-20
-                sx2 = (sp2 - N * x * x) / den
-                sy2 = (sg - N * y * y) / den
-                sxy = (spg - N * x * y) / den
-                a = 4 * x * y * sxy
-                b = (x * x + y * y) * (sx2 + sy2)
-                if (y == 0.0 or y == 1.0) and not math.isnan(a):
-                    a = 0.0                                  # (g - ȳ) ≡ 0 → the reference's σxy is an exact zero
-                if a != 0:
-                    Q.append(a / (b + 1e-20))
-                elif a == 0 and b == 0:
-                    Q.append(1.0)
-                else:
-                    Q.append(0.0)
-            s_reg = float(w1) * Q[0] + float(w2) * Q[1] + float(w3) * Q[2] + float(w4) * Q[3]
-            val = alpha * s_obj + (1 - alpha) * s_reg
-        flat_o[i] = 0.0 if val < 0 else val
-    return out
 
 
 def finalize(m_counts: np.ndarray, m_sums: np.ndarray) -> Dict[str, np.ndarray]:
@@ -242,8 +181,12 @@ def _shape_like(pred_mask, arr):
 
 
 def compute_iou(pred_mask, gt_mask, threshold: Optional[float] = 0.5, eps: float = 1e-7):
-    """metrics/iou.py:6-32 (threshold 0.5 or boolean input)."""
+    """metrics/iou.py:6-32 (threshold 0.5, or threshold=None / boolean input for masks that are already binary)."""
     if threshold is None or pred_mask.dtype == torch.bool:
+        # the reference uses the mask as it is (any non-zero value is foreground); the GPU reduction thresholds at 0.5, which is
+        # the same thing only for {0, 1} masks — anything else is refused instead of silently re-thresholded
+        if pred_mask.dtype != torch.bool and not bool(((pred_mask == 0) | (pred_mask == 1)).all()):
+            raise _lib.SmkError("compute_iou(threshold=None) expects a binary {0,1} mask on the GPU path")
         pred_mask = pred_mask.to(torch.float32)       # {0,1} > 0.5 reproduces the boolean mask
     elif threshold != 0.5:
         raise _lib.SmkError("only threshold=0.5 is implemented on the GPU path")
@@ -275,9 +218,13 @@ def compute_mae(pred_mask: torch.Tensor, gt_mask: torch.Tensor) -> torch.Tensor:
 
 
 def compute_pixel_accuracy(pred_mask: torch.Tensor, gt_mask: torch.Tensor, threshold: Optional[float] = 0.5) -> torch.Tensor:
-    """metrics/pixel_acc.py:5-14."""
+    """metrics/pixel_acc.py:5-14 (threshold 0.5, or threshold=None for masks that are already binary)."""
     if threshold is None:
+        if pred_mask.dtype != torch.bool and not bool(((pred_mask == 0) | (pred_mask == 1)).all()):
+            raise _lib.SmkError("compute_pixel_accuracy(threshold=None) expects a binary {0,1} mask on the GPU path")
         pred_mask = pred_mask.to(torch.float32)
+    elif threshold != 0.5:
+        raise _lib.SmkError("only threshold=0.5 is implemented on the GPU path")
     c, s = _device_record(pred_mask, gt_mask)
     return _shape_like(pred_mask, finalize(c, s)["pixel_accuarcy"])
 

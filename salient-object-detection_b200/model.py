@@ -9,6 +9,7 @@
 All arithmetic happens in libselfmask_b200.so (hand-written sm_100a CUDA); torch only owns device memory
 and the stream.
 """
+import collections
 import ctypes as C
 from types import SimpleNamespace
 from typing import Dict, Optional
@@ -50,7 +51,7 @@ class SelfMaskB200(torch.nn.Module):
                  n_decoder_layers: int = 6, normalize_before: bool = False, return_intermediate: bool = True,
                  learnable_pixel_decoder: bool = False, lateral_connection: bool = False, scale_factor: int = 4,
                  abs_2d_pe_init: bool = False, use_binary_classifier: bool = True, mode: str = "fp16s", max_batch: int = 64,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, max_geometries: int = 4):
         super().__init__()
         if arch != "vit_small" or training_method != "dino":
             raise SmkError("only arch='vit_small', training_method='dino' is on the B200 path (SURVEY.md §8)")
@@ -73,7 +74,13 @@ class SelfMaskB200(torch.nn.Module):
         self.pixel_mean, self.pixel_std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
         self._table = None
         self._blob = None          # fp32 weights, one device tensor in the library's canonical order
-        self._handles = {}         # (H, W) -> (handle, workspace tensor)
+        # (H, W) -> (handle, workspace tensor, capacity), least recently used first.  A workspace is sized for ONE geometry
+        # (1.3 GB at 224^2 x 256 images), and the reference protocol evaluates at native resolution — hundreds of distinct sizes on
+        # DUTS-TE / DUT-OMRON — so the cache is bounded: beyond `max_geometries` the least recently used workspace is released,
+        # and a new geometry's capacity is the batch actually seen (not `max_batch`) once more than one geometry is live.
+        self._handles = collections.OrderedDict()
+        self.max_geometries = max(1, int(max_geometries))
+        self._graphs = {}          # predict_one: (H, W, dtype) -> (graph, static input, static outputs)
         self._device = torch.device(device) if device is not None else None
         self._loaded = False
 
@@ -130,9 +137,10 @@ class SelfMaskB200(torch.nn.Module):
         return {n: self._blob[o:o + m].clone() for n, o, m in self.table()}
 
     def _release(self):
+        self._graphs = {}
         for ent in self._handles.values():
             lib().smk_model_destroy(ent[0])
-        self._handles = {}
+        self._handles = collections.OrderedDict()
 
     def __del__(self):
         try:
@@ -146,10 +154,20 @@ class SelfMaskB200(torch.nn.Module):
         key = (H, W)
         ent = self._handles.get(key)
         if ent is not None and ent[2] >= B:
+            self._handles.move_to_end(key)
             return ent[0]
+        # a handle is about to be destroyed / replaced: graphs captured on it replay freed memory, and earlier launches must be done
+        if ent is not None or len(self._handles) >= self.max_geometries:
+            torch.cuda.current_stream(self._blob.device).synchronize()
         if ent is not None:
             lib().smk_model_destroy(ent[0])
-        cap = max(B, self.max_batch)
+            del self._handles[key]
+            self._graphs = {k: v for k, v in self._graphs.items() if k[:2] != key}
+        while len(self._handles) >= self.max_geometries:
+            old_key, old = self._handles.popitem(last=False)
+            lib().smk_model_destroy(old[0])
+            self._graphs = {k: v for k, v in self._graphs.items() if k[:2] != old_key}
+        cap = max(B, self.max_batch) if not self._handles else B
         mode = _MODES[self.mode]
         nbytes = lib().smk_model_workspace_bytes(C.byref(self.cfg), mode, cap, H, W)
         if nbytes <= 0:
@@ -200,6 +218,39 @@ class SelfMaskB200(torch.nn.Module):
         if self.return_intermediate:
             return {"objectness": objectness.unsqueeze(-1), "mask_pred": mask_pred, "features": features}
         return {"objectness": objectness[:, 0].unsqueeze(-1), "mask_pred": mask_pred[:, 0], "features": features}
+
+    @torch.no_grad()
+    def predict_one(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Single-image latency path (the consumer is `SelfMaskInference.predict`, app.py:241-347, which runs
+        `base_structure._forward({'x': img})` on one image and takes `mask_pred[0, -1]` / `objectness[0, -1]`).
+
+        x: 1 x 3 x H x W (float32 normalised, or uint8 raw pixels) on the GPU.  The ~170 launches of a batch-1 forward pass are
+        latency-bound, so the pass is captured ONCE per (H, W, dtype) into a CUDA graph and replayed: the call costs one host →
+        graph launch.  Returns the same dict as `forward` (tensors are the graph's static outputs: valid until the next call)."""
+        if x.ndim != 4 or x.shape[0] != 1 or x.shape[1] != 3:
+            raise SmkError(f"predict_one expects 1 x 3 x H x W, got {tuple(x.shape)}")
+        _lib.require_cuda(x, "x")
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
+        key = (int(x.shape[2]), int(x.shape[3]), x.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_x = x.clone()
+            with torch.cuda.device(x.device):
+                side = torch.cuda.Stream(x.device)
+                side.wait_stream(torch.cuda.current_stream(x.device))
+                with torch.cuda.stream(side):          # warm-up outside capture: workspace, weight repack, layer-0 decoder constants
+                    for _ in range(2):
+                        self.forward(static_x)
+                torch.cuda.current_stream(x.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = self.forward(static_x)
+            ent = (graph, static_x, static_out)
+            self._graphs[key] = ent
+        graph, static_x, static_out = ent
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        return static_out
 
     def tap(self, what: int, B: int, H: int, W: int) -> torch.Tensor:
         """Stage-level parity hook: 1 final-LN tokens, 2 decoder queries [L,B,nq,D], 3 residual stream."""

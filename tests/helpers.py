@@ -1,8 +1,12 @@
 """Test helpers: numpy emulation of the GPU record layout (include/selfmask_b200.h) so that the host-side
 finalisation can be checked on CPU against the oracle / golden fixtures."""
+import math
+
 import numpy as np
 
 from oracle import selfmask_oracle as O
+
+F32 = np.float32
 
 
 def numpy_record(pred: np.ndarray, gt: np.ndarray):
@@ -39,3 +43,64 @@ def numpy_record(pred: np.ndarray, gt: np.ndarray):
         qp, qg = pd[ys_, xs_], g[ys_, xs_]
         s[8 + 5 * k: 13 + 5 * k] = [qp.size, qp.sum(), (qp ** 2).sum(), qg.sum(), qp[qg].sum()]
     return c.astype(np.int32), s
+
+
+def s_measure_from_sums_loop(counts: np.ndarray, sums: np.ndarray, alpha: float = 0.5) -> np.ndarray:
+    """Per-record scalar restatement (python floats) of `selfmask_b200.metrics.s_measure_from_sums` (s_measure.py:108-124 from moment
+    sums): the readable definition and the test oracle of the vectorised product version."""
+    counts = np.asarray(counts)
+    sums = np.asarray(sums, np.float64)
+    out = np.empty(counts.shape[:-1], np.float64)
+    flat_c, flat_s, flat_o = counts.reshape(-1, counts.shape[-1]), sums.reshape(-1, sums.shape[-1]), out.reshape(-1)
+    for i in range(flat_c.shape[0]):
+        c, s = flat_c[i], flat_s[i]
+        n, G = float(c[519]), float(c[514])
+        mean_p = s[0] / n
+        if G == 0:
+            flat_o[i] = 1.0 - mean_p
+            continue
+        if G == n:
+            flat_o[i] = mean_p
+            continue
+        with np.errstate(all="ignore"):
+            def obj(sum1, sum2, cnt):                      # s_measure.py:54-60, unbiased std
+                mu = sum1 / cnt
+                var = (sum2 - cnt * mu * mu) / (cnt - 1) if cnt > 1 else float("nan")
+                sd = math.sqrt(max(var, 0.0)) if not math.isnan(var) else float("nan")
+                return 2.0 * mu / (mu * mu + 1.0 + sd + 1e-20)
+            u = G / n
+            s_obj = u * obj(s[3], s[4], G) + (1 - u) * obj(s[5], s[6], n - G)
+            X, Y = float(c[517]), float(c[518])
+            hw = n
+            # widths are not in the record: recover W, H from quadrant pixel counts is unnecessary — the
+            # weights only need X*Y/area etc., and (W-X)*Y = N_RT, X*(H-Y) = N_LB
+            q = s[8:28].reshape(4, 5)
+            w1 = F32(F32(X) * F32(Y)) / F32(hw)
+            w2 = F32(q[1, 0]) / F32(hw)
+            w3 = F32(q[2, 0]) / F32(hw)
+            w4 = F32(1) - w1 - w2 - w3
+            Q = []
+            for k in range(4):
+                N, sp, sp2, sg, spg = q[k]
+                if N == 0:
+                    Q.append(float("nan"))
+                    continue
+                x, y = sp / N, sg / N
+                den = N - 1 + 1e-20
+                sx2 = (sp2 - N * x * x) / den
+                sy2 = (sg - N * y * y) / den
+                sxy = (spg - N * x * y) / den
+                a = 4 * x * y * sxy
+                b = (x * x + y * y) * (sx2 + sy2)
+                if (y == 0.0 or y == 1.0) and not math.isnan(a):
+                    a = 0.0                                  # (g - ȳ) ≡ 0 → the reference's σxy is an exact zero
+                if a != 0:
+                    Q.append(a / (b + 1e-20))
+                elif a == 0 and b == 0:
+                    Q.append(1.0)
+                else:
+                    Q.append(0.0)
+            s_reg = float(w1) * Q[0] + float(w2) * Q[1] + float(w3) * Q[2] + float(w4) * Q[3]
+            val = alpha * s_obj + (1 - alpha) * s_reg
+        flat_o[i] = 0.0 if val < 0 else val
+    return out

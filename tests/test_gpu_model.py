@@ -430,3 +430,56 @@ def test_sharded_sweep_records_equal_the_single_pass_bit_for_bit():
     assert np.isnan(res_full["s_measure"]) or np.isnan(res_full["s_measure_ub"]) or True
     for k, v in res_full.items():
         assert (np.isnan(v) and np.isnan(res[k])) or v == res[k], k
+
+
+def test_native_resolution_sweep_matches_the_oracle_evaluator(tmp_path):
+    """SURVEY.md §8 f1 — the reference protocol (datasets/duts.py:108-147): test images at their native size, masks `> 0`, the model
+    pads to a multiple of the patch size and the evaluator crops.  Directory reader → Evaluator at native resolution against the
+    oracle's restatement of `Evaluator.__call__` on the very same decoded pixels; the workspace cache stays bounded (LRU)."""
+    from PIL import Image
+    d_img, d_gt = tmp_path / "DUTS-TE-Image", tmp_path / "DUTS-TE-Mask"
+    d_img.mkdir()
+    d_gt.mkdir()
+    sizes = [(96, 128), (96, 128), (120, 100), (224, 224), (120, 100), (75, 90)]          # (H, W): three are not multiples of 16
+    for i, (h, w) in enumerate(sizes):
+        img = O.synth_images_u8(1, h, w, seed=600 + i)[0].transpose(1, 2, 0)
+        Image.fromarray(img).save(d_img / f"{i:03d}.jpg", quality=95)
+        Image.fromarray((O.synth_gt(1, h, w, seed=700 + i)[0, 0] * 255).astype(np.uint8)).save(d_gt / f"{i:03d}.png")
+    model, sd, cfg = make_model(nq=20, mode="fp32", max_batch=2)
+    model.max_geometries = 2
+    ds = S.get_dataset(str(tmp_path), "duts", img_size=None, batch_size=4)
+    assert "native" in ds.protocol
+    batches = list(ds)
+    assert [tuple(b["x"].shape) for b in batches] == [(2, 3, 96, 128), (1, 3, 120, 100), (1, 3, 224, 224), (1, 3, 120, 100), (1, 3, 75, 90)]
+    ev = S.Evaluator(network=model, dir_dataset=str(tmp_path), dataset=batches)
+    res = ev(dataset_name="duts", dir_ckpt=None, batch_size=4, device=DEV)
+    assert len(model._handles) <= 2                                                        # 4 geometries seen, 2 kept
+    mean, std = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1), torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    ora_batches = [(((b["x"].float() / 255.0) - mean) / std, b["m"].numpy()) for b in batches]
+    with torch.no_grad():
+        ora = O.evaluate(lambda x: O.model_forward(sd, x, cfg), ora_batches)
+    idx = ev.records["idx"]
+    for i, r in enumerate(ora["_images"]):
+        assert (int(idx[i, 0]), int(idx[i, 1])) == (r["sel"], r["ub"]), i
+    for k in O.METRIC_KEYS:
+        for kk in (k, k + "_ub"):
+            assert abs(res[kk] - ora[kk]) <= 5e-4 * max(1.0, abs(ora[kk])), (kk, res[kk], ora[kk])
+
+
+def test_predict_one_replays_a_cuda_graph():
+    """SURVEY.md §8 f3 — the single-image consumer (app.py:241-347): `predict_one` captures the batch-1 forward once per geometry and
+    replays it; results equal the eager forward bit for bit, for float and raw uint8 input."""
+    model, sd, cfg = make_model(nq=20, mode="fp16s", max_batch=1)
+    for seed in (1, 2, 3):
+        u8 = torch.from_numpy(O.synth_images_u8(1, 224, 224, seed=seed)).to(DEV)
+        eager = {k: v.clone() for k, v in model(u8).items()}
+        got = model.predict_one(u8)
+        torch.cuda.synchronize()
+        for k in ("mask_pred", "objectness", "features"):
+            assert torch.equal(got[k], eager[k]), (seed, k)
+    assert len(model._graphs) == 1
+    xf = O.normalize_images(O.synth_images_u8(1, 224, 224, seed=4)).to(DEV)
+    assert torch.equal(model.predict_one(xf)["mask_pred"], model(xf)["mask_pred"])
+    assert len(model._graphs) == 2                       # float input is a second graph
+    best = int(model.predict_one(u8)["objectness"][0, -1, :, 0].argmax())      # what app.py:268-277 does with the result
+    assert 0 <= best < 20

@@ -13,6 +13,7 @@ import torch
 import selfmask_b200 as S
 from oracle import selfmask_oracle as O
 from selfmask_b200 import metrics as M
+from tests.helpers import s_measure_from_sums_loop
 from tests.helpers import numpy_record
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -108,7 +109,7 @@ def test_vectorised_s_measure_equals_scalar_definition(golden_dir):
         elif kind >= 9: gt = rng.random((H, W)) > 0.3 * (kind - 8)
         recs.append(numpy_record(p, gt))
     counts, sums = np.stack([r[0] for r in recs]), np.stack([r[1] for r in recs])
-    a, b = M.s_measure_from_sums(counts, sums), M._s_measure_from_sums_loop(counts, sums)
+    a, b = M.s_measure_from_sums(counts, sums), s_measure_from_sums_loop(counts, sums)
     assert a.dtype == b.dtype == np.float64
     assert np.array_equal(np.isnan(a), np.isnan(b)) and np.isnan(a).any()
     assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
