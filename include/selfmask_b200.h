@@ -179,6 +179,13 @@ int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, 
  * out_kind: 0 16-bit (same type as the operands), 1 fp32, 2 split [hi | hi | lo] (3N columns), 3 split [hi | lo] (2N columns). */
 int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
                    int epilogue, int out_kind, int f16, int n_terms, const int32_t* a_off, const int32_t* w_off, void* stream);
+/* Batched form: C_b [rows_a, rows_w] fp32 = sum over terms of A_b · W_b^T for b < n_batch, where A_b = rows
+ * [b*batch_a_rows + a_row0, +rows_a) of A [a_total_rows, lda] and W_b = rows [b*batch_w_rows + w_row0, +rows_w) of W [w_total_rows, ldw];
+ * C [n_batch, rows_a, rows_w] contiguous, rows_w % 4 == 0.  The mask-logit contraction (maskformer.py:223 at patch resolution):
+ * A = the decoder queries of image b (all layers), W = its patch tokens. */
+int smk_gemm_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W, int64_t ldw,
+                     int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K, int f16, int n_terms,
+                     const int32_t* a_off, const int32_t* w_off, void* stream);
 /* y = LN(x) * gamma + beta over the last dim D (fp32 statistics).  out_bf16 selects the output type. */
 int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
                   int out_bf16, void* stream);

@@ -126,7 +126,32 @@ struct TcGemmParams {
   // (token-major rows of 32 features) and the TMA store / reduce-add addresses C[token, feature] as usual.  fp32 output only.
   int trans;
   int credit_k;   // host-side bookkeeping only (profiler credit)
+  double credit_flops;   // host-side: algorithmic FLOPs when M / N are padded (batched form); 0 = 2·M·N·credit_k
+  // Batched form (mask logits: queries · tokens^T per image): problem b multiplies A rows [b·batch_a_rows + a_row0, +mb_per_batch·128)
+  // with W rows [b·batch_b_rows + b_row0, +N); tiles = (b, m-block, n-block); C is a 3-D tensor map {column, row in batch, batch}
+  // that clips the rows / columns beyond the valid ones.  mb_per_batch == 0: plain GEMM.
+  int mb_per_batch, batch_a_rows, a_row0, batch_b_rows, b_row0;
 };
+struct TileCoord { int a_row, b_row, c_row, n_blk, batch; };
+__device__ __forceinline__ TileCoord tile_coord(const TcGemmParams& p, int tile, int m_blocks, int n_blocks, int BN, int kCtas) {
+  TileCoord t;
+  if (p.mb_per_batch > 0) {
+    const int per = p.mb_per_batch * n_blocks, b = tile / per, rem = tile - b * per, mb = rem / n_blocks;
+    t.n_blk = rem - mb * n_blocks;
+    t.batch = b;
+    t.c_row = mb * TC_BM;
+    t.a_row = b * p.batch_a_rows + p.a_row0 + mb * TC_BM;
+    t.b_row = b * p.batch_b_rows + p.b_row0 + t.n_blk * BN;
+    return t;
+  }
+  const int m_blk = p.trans ? tile % m_blocks : tile / n_blocks;
+  t.n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
+  t.batch = 0;
+  t.a_row = m_blk * TC_BM * kCtas;
+  t.b_row = t.n_blk * BN;
+  t.c_row = t.a_row;
+  return t;
+}
 
 // kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
@@ -194,7 +219,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
         const int tile = p.rev ? num_tiles - 1 - tile_i : tile_i;
         // trans: the feature blocks of one token block are neighbours in the sequence (they share the activation tile in L2)
-        const int m_blk = p.trans ? tile % m_blocks : tile / n_blocks, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
+        const TileCoord tc_ = tile_coord(p, tile, m_blocks, n_blocks, BN, kCtas);
         int term = 0, kk = 0;                      // k-block kb = term * kpt + kk
         for (int kb = 0; kb < k_blocks; ++kb) {
           const int ka = p.ta[term] + kk * TC_BK, kw = p.tw[term] + kk * TC_BK;
@@ -209,12 +234,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // both CTAs' bytes complete on the even CTA's barrier (its MMA thread is the only consumer)
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2(sa, &tmA, bar, ka, (m_blk * 2 + (int)rank) * TC_BM);
-            tma_load_2d_cg2(sb, &tmB, bar, kw, n_blk * BN + (int)rank * Cfg::kBNL);
+            tma_load_2d_cg2(sa, &tmA, bar, ka, tc_.a_row + (int)rank * TC_BM);
+            tma_load_2d_cg2(sb, &tmB, bar, kw, tc_.b_row + (int)rank * Cfg::kBNL);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], ka, m_blk * TC_BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kw, n_blk * BN);
+            tma_load_2d(sa, &tmA, &full_bar[stage], ka, tc_.a_row);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kw, tc_.b_row);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -286,7 +311,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     w_all.begin();
     for (int tile_i = tile0; tile_i < tile_end; tile_i += tile_step) {
       const int tile = p.rev ? num_tiles - 1 - tile_i : tile_i;
-      const int m_blk = (p.trans ? tile % m_blocks : tile / n_blocks) * kCtas + (int)rank, n_blk = p.trans ? tile / m_blocks : tile % n_blocks;
+      const TileCoord tc_ = tile_coord(p, tile, m_blocks, n_blocks, BN, kCtas);
+      const int m_blk = tc_.c_row / TC_BM + (int)rank, n_blk = tc_.n_blk;     // c_row: first output row of the tile (row in batch when batched)
       ++n_tiles_done;
       w_tm.begin();
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -399,7 +425,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (p.epi & SMK_EPI_RESIDUAL) tma_reduce_add_2d(&tmC, stg, n0, row0);
+              if (p.mb_per_batch > 0) tma_store_3d(&tmC, stg, n0, row0, tc_.batch);
+              else if (p.epi & SMK_EPI_RESIDUAL) tma_reduce_add_2d(&tmC, stg, n0, row0);
               else tma_store_2d(&tmC, stg, n0, row0);
               bulk_commit();
             }
@@ -586,7 +613,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   {
     // credited work = ALGORITHMIC FLOPs of the contraction (one term; p.credit_k is the mathematical reduction length), whatever
     // number of split terms the tensor core is issued
-    ProfScope prof(PROF_GEMM_TC, 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * p.n_terms);
+    ProfScope prof(PROF_GEMM_TC, p.credit_flops > 0 ? p.credit_flops : 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * p.n_terms);
     SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
@@ -740,6 +767,49 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
   return launch_bn<false, 1, kF16>(BN, ta, tb, tcm, p, s);
 }
 
+// Batched C_b = A_b · W_b^T (fp32 output, no bias): problem b reads `rows_a` rows of A from row b·batch_a_rows + a_row0 and `rows_w`
+// rows of W from row b·batch_w_rows + w_row0; C [n_batch, rows_a, rows_w] fp32 contiguous.  Tiles are 128 x 256 per (batch, m, n)
+// block; operand rows beyond a problem's own (the next problem's, or zeros at the end of the tensor) only reach output rows /
+// columns that the 3-D output map clips.  Serves the mask-logit contraction (queries x memory tokens per image).
+template <bool kF16>
+static int gemm_tc_batched_impl(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W,
+                                int64_t ldw, int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K,
+                                const GemmTerms& tr, cudaStream_t s) {
+  SMK_REQUIRE(K % TC_BK == 0 && tr.n >= 1 && tr.n <= TC_MAX_TERMS && n_batch >= 0 && rows_a >= 1 && rows_w >= 1, "gemm_tc_batched: bad shape");
+  SMK_REQUIRE(((uintptr_t)C % 16) == 0 && rows_w % 4 == 0, "gemm_tc_batched: C rows must be 16-byte aligned (rows_w %% 4 == 0)");
+  if (n_batch == 0) return SMK_OK;
+  int64_t a_cols = 0, w_cols = 0;
+  for (int t = 0; t < tr.n; ++t) {
+    a_cols = std::max<int64_t>(a_cols, tr.a_off[t] + K);
+    w_cols = std::max<int64_t>(w_cols, tr.w_off[t] + K);
+  }
+  SMK_REQUIRE(lda >= a_cols && ldw >= w_cols, "gemm_tc_batched: operand rows shorter than the terms reach");
+  constexpr int BN = 256;
+  const int mb = (rows_a + TC_BM - 1) / TC_BM, nb = (rows_w + BN - 1) / BN;
+  TcGemmParams p{};
+  p.M = n_batch * mb * TC_BM; p.N = nb * BN; p.K = K; p.n_terms = tr.n;
+  for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.a_off[t]; p.tw[t] = tr.w_off[t]; }
+  p.bias = nullptr; p.C = C; p.ldc = rows_w; p.epi = SMK_EPI_NONE; p.out_f32 = 1; p.rev = 0; p.trans = 0; p.credit_k = K;
+  p.credit_flops = 2.0 * n_batch * rows_a * rows_w * K;
+  p.mb_per_batch = mb; p.batch_a_rows = batch_a_rows; p.a_row0 = a_row0; p.batch_b_rows = batch_w_rows; p.b_row0 = w_row0;
+  CUtensorMap ta, tb, tcm;
+  SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)a_cols, (uint64_t)a_total_rows, (uint64_t)lda * 2, TC_BK, TC_BM));
+  SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)w_cols, (uint64_t)w_total_rows, (uint64_t)ldw * 2, TC_BK, BN));
+  const uint64_t dims[3] = {(uint64_t)rows_w, (uint64_t)rows_a, (uint64_t)n_batch};
+  const uint64_t strides[2] = {(uint64_t)rows_w * 4, (uint64_t)rows_a * rows_w * 4};
+  const uint32_t box[3] = {32u, 32u, 1u};
+  SMK_PROPAGATE(make_tmap_nd(&tcm, 4, C, 3, dims, strides, box, 128));
+  return launch_tc<BN, false, 1, 8, kF16>(ta, tb, tcm, p, s);
+}
+int gemm_tc_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W, int64_t ldw,
+                    int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K, int f16, const GemmTerms& terms,
+                    cudaStream_t s) {
+  return f16 ? gemm_tc_batched_impl<true>(A, lda, a_total_rows, batch_a_rows, a_row0, rows_a, W, ldw, w_total_rows, batch_w_rows, w_row0, rows_w, C,
+                                          n_batch, K, terms, s)
+             : gemm_tc_batched_impl<false>(A, lda, a_total_rows, batch_a_rows, a_row0, rows_a, W, ldw, w_total_rows, batch_w_rows, w_row0, rows_w, C,
+                                           n_batch, K, terms, s);
+}
+
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K, int epi,
             int out_f32, int tok_hw, const float* tok_pos, int f16, const GemmTerms& terms, int credit_k, cudaStream_t s) {
   return f16 ? gemm_tc_impl<true>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, out_f32, tok_hw, tok_pos, terms, credit_k, s)
@@ -766,6 +836,16 @@ extern "C" int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const fl
   SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0, "smk_gemm_bf16: bad arguments");
   return smk::gemm_bf16_tc((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, K, bias, C, ldc, M, N, K, epilogue, out_f32, 0, nullptr,
                            (cudaStream_t)stream);
+}
+
+extern "C" int smk_gemm_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W,
+                                int64_t ldw, int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K,
+                                int f16, int n_terms, const int32_t* a_off, const int32_t* w_off, void* stream) {
+  SMK_REQUIRE(A && W && C && a_off && w_off && n_terms >= 1 && n_terms <= 3, "smk_gemm_batched: bad arguments");
+  smk::GemmTerms t{n_terms, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < n_terms; ++i) { t.a_off[i] = a_off[i]; t.w_off[i] = w_off[i]; }
+  return smk::gemm_tc_batched(A, lda, a_total_rows, batch_a_rows, a_row0, rows_a, W, ldw, w_total_rows, batch_w_rows, w_row0, rows_w, C, n_batch, K,
+                              f16, t, (cudaStream_t)stream);
 }
 
 extern "C" int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,

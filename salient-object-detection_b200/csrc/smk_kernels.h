@@ -21,12 +21,14 @@ int layernorm_f32(const float* x, const float* res, const float* gamma, const fl
                   int D, float eps, cudaStream_t s);
 int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int64_t rows, int D, float eps, cudaStream_t s);
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
-                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr);
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr, int64_t ldy = 0);
 int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
-                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s);
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt = 0);
+// y2s_period / y2s_stride: row r of the split final-norm output goes to row (r / period)·stride + r % period of y2s (image-major
+// [B][L][nq] layout of the mask / objectness head operand: period = nq, stride = L·nq, y2s pre-offset by layer·nq rows); 0 = row r
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
-                  int64_t rows, int D, cudaStream_t s);
+                  int64_t rows, int D, cudaStream_t s, int y2s_period = 0, int y2s_stride = 0);
 int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N, int K,
              int epi, cudaStream_t s);
 int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
@@ -37,6 +39,9 @@ struct GemmTerms { int n; int a_off[3]; int w_off[3]; };
 inline GemmTerms terms_plain() { return GemmTerms{1, {0, 0, 0}, {0, 0, 0}}; }
 inline GemmTerms terms_wsplit(int K) { return GemmTerms{2, {0, 0, 0}, {0, K, 0}}; }        // A_hi·(W_hi + W_lo)
 inline GemmTerms terms_full(int K) { return GemmTerms{3, {0, 0, K}, {0, K, 0}}; }          // hi·hi + hi·lo + lo·hi
+int gemm_tc_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W, int64_t ldw,
+                    int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K, int f16, const GemmTerms& terms,
+                    cudaStream_t s);
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K, int epi,
             int out_f32, int tok_hw, const float* tok_pos, int f16, const GemmTerms& terms, int credit_k, cudaStream_t s);
 template <typename T, typename TK>
@@ -78,9 +83,9 @@ int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, 
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
 int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t s);
 int tile_rows2(void* d0, const void* s0, int row_bytes0, void* d1, const void* s1, int row_bytes1, int64_t rows, int period, cudaStream_t s);
-// bf16 tensor-core mode, scale factor 4 (smk_mask_mma.cu): logits on mma.sync with the 3-term split, then upsample + sigmoid
-int mask_head_mma(const __nv_bfloat16* q3, int64_t Rall, const __nv_bfloat16* tok_hi, const __nv_bfloat16* tok_lo, float* logits_lowres,
-                  float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D, int hp, int wp, cudaStream_t s);
+// tensor-core modes, scale factor 4 (smk_mask_mma.cu): logits as a batched tcgen05 GEMM with the 3-term split, then upsample + sigmoid
+int mask_head_tc(const __nv_bfloat16* q3, int q_batch_rows, const __nv_bfloat16* tok16, float* logits_lowres, float* mask_pred,
+                 float* logits_out, int B, int L, int layer0, int nq, int D, int hp, int wp, cudaStream_t s);
 int mask_head(const float* queries, const float* tokens, float* mask_pred, float* logits_out, int B, int L, int layer0, int nq, int D,
               int hp, int wp, int sf, cudaStream_t s, bool precise = false);
 int rowdot_sigmoid(const float* h, const float* w, const float* bias, float* out, int64_t rows, int D, cudaStream_t s);

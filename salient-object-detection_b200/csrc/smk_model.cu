@@ -167,7 +167,7 @@ struct smk_model {
   float* X;                       // [B*N, D] residual stream (fp32)
   void *Xn, *QKV, *AO, *Hm, *KV;  // activations in the mode's GEMM input type
   float* tok32;                   // [B*N, D] final-LN encoder tokens (fp32)
-  __nv_bfloat16 *tokb, *tokl;     // bf16 copy and its rounding residue (bf16 mode)
+  __nv_bfloat16* tok16;           // [B*N, 2D] bf16 [hi | lo] of the final-LN tokens (tensor-core modes: mask-logit operand; bf16 mode: K/V GEMM A)
   float* mlog;                    // [B, L*nq, hw] mask logits at patch resolution (bf16 mode)
   float *tgt, *qin, *dqk, *dv, *dao, *t2, *ffh, *queries, *oh1, *oh2, *otmp;
   std::vector<Dec3> dec3;         // bf16 mode only
@@ -225,9 +225,8 @@ static void plan(smk_model& m, Plan& pl) {
   m.Hm = pl.take<uint8_t>(x3_mode(m) ? M * 3 * (int64_t)c.mlp_dim * 2 : M * (int64_t)c.mlp_dim * esz);
   m.KV = pl.take<uint8_t>(M * L * 2 * D * (x3 ? 6 : (m.mode == SMK_MODE_FP32 ? 4 : 2)));     // bf16x3: split [hi | hi | lo] rows of 3·L·2D bf16
   m.tok32 = pl.take<float>(M * D);
-  m.tokb = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
-  m.tokl = bf ? pl.take<__nv_bfloat16>(M * D) : nullptr;
-  m.mlog = bf ? pl.take<float>(B * L * nq * (N - 1)) : nullptr;
+  m.tok16 = bf ? pl.take<__nv_bfloat16>(M * 2 * D) : nullptr;
+  m.mlog = bf ? pl.take<float>(B * L * nq * (N + 3)) : nullptr;     // logit rows padded to a multiple of 4 floats (TMA store)
   const int64_t R = B * nq;
   m.tgt = pl.take<float>(R * D);
   m.qin = pl.take<float>(R * D);
@@ -649,7 +648,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       { TagScope tg(TAG_FC2); SMK_PROPAGATE(gemm_tc(Hm, F2, wh + 2 * b.f2w, F2, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_fc2, F), 0, s)); }
     }
     // final norm: fp32 tokens (mask head reference copy), bf16 hi / lo (mask-logit contraction), fp16 (decoder memory)
-    { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + m->o_enw, w + m->o_enb, m->tokh, nullptr, D, m->tok32, m->tokb, m->tokl, M, D, 1e-6f, s)); }
+    { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + m->o_enw, w + m->o_enb, m->tokh, nullptr, D, m->tok32, m->tok16, m->tok16 + D, M, D, 1e-6f, s, 2 * D)); }
     { TagScope tg(TAG_KV); SMK_PROPAGATE(gemm_tc(m->tokh, D, m->kvwh, 2 * D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_kv == 3 ? 2 : m->t_kv, D), 0, s)); }
   } else if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
@@ -700,9 +699,9 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         SMK_PROPAGATE(gemm_bf16_tc(Hm, F, wb + b.f2w, F, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, s));
       }
     }
-    { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tokb, m->tok32, nullptr, M, D, 1e-6f, s, m->tokl)); }
+    { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_bf16(m->X, nullptr, w + m->o_enw, w + m->o_enb, m->tok16, m->tok32, nullptr, M, D, 1e-6f, s, m->tok16 + D, 2 * D)); }
     // memory K/V of all decoder layers in one GEMM (memory is layer-invariant)
-    { TagScope tg(TAG_KV); SMK_PROPAGATE(gemm_bf16_tc(m->tokb, D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s)); }
+    { TagScope tg(TAG_KV); SMK_PROPAGATE(gemm_bf16_tc(m->tok16, 2 * D, m->kvwb, D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, s)); }
   } else {
     float *Xn = (float*)m->Xn, *QKV = (float*)m->QKV, *AO = (float*)m->AO, *Hm = (float*)m->Hm;
     if (x_u8) SMK_PROPAGATE((im2col<uint8_t, float>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s)));
@@ -842,8 +841,9 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         SMK_PROPAGATE(gemm3(a3a, d3.l1w, w + d.l1b, a3f, 3 * FD, R, FD, D, SMK_EPI_RELU, 2));
         SMK_PROPAGATE(gemm3(a3f, d3.l2w, w + d.l2b, t2, D, R, D, FD, SMK_EPI_NONE, 1));
         TagScope tg(TAG_DEC_LN);
+        // split final-norm queries in the image-major [B][L][nq] layout: an image's L·nq rows are one contiguous tile of the mask head
         SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n3w, w + d.n3b, 1e-5f, qpos, nq, a3a, a3b, w + m->o_dnw, w + m->o_dnb,
-                                    m->queries + ((int64_t)l * Rall + r0) * D, m->a3q + ((int64_t)l * Rall + r0) * 3 * D, R, D, s));
+                                    m->queries + ((int64_t)l * Rall + r0) * D, m->a3q + ((int64_t)b0 * L * nq + (int64_t)l * nq) * 3 * D, R, D, s, nq, L * nq));
       }
       return SMK_OK;
     };
@@ -897,25 +897,34 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   const int Lout = all_layers ? L : 1, layer0 = all_layers ? 0 : L - 1;
   if (mask_pred) {
     if (bf && c.scale_factor == 4)
-      SMK_PROPAGATE(mask_head_mma(m->a3q, R, m->tokb, m->tokl, m->mlog, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, s));
+      SMK_PROPAGATE(mask_head_tc(m->a3q, L * nq, m->tok16, m->mlog, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, s));
     else
       SMK_PROPAGATE(mask_head(m->queries, m->tok32, mask_pred, m->debug_logits, B, Lout, layer0, nq, D, m->hp, m->wp, c.scale_factor, s,
                               m->mode == SMK_MODE_FP32));
   }
   if (objectness) {
     TagScope tg(TAG_OBJECTNESS);
-    const float* qsrc = m->queries + (int64_t)layer0 * R * D;
-    const int rows = Lout * R;
     if (bf) {
-      const __nv_bfloat16* q3 = m->a3q + (int64_t)layer0 * R * 3 * D;
-      SMK_PROPAGATE(gemm_bf16_tc(q3, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->a3f, 3 * D, rows, D, 3 * D, SMK_EPI_RELU, 2, 0, nullptr, s, D));
+      // the split queries are image-major [B][L][nq]: the MLP runs over all L·R rows and its output already is objectness [B, L, nq]
+      // (maskformer.py:238 permute); last-layer-only callers get the strided [:, L-1, :] slice
+      const int rows = L * R;
+      SMK_PROPAGATE(gemm_bf16_tc(m->a3q, 3 * D, m->f0w3, 3 * D, w + m->o_f0b, m->a3f, 3 * D, rows, D, 3 * D, SMK_EPI_RELU, 2, 0, nullptr, s, D));
       SMK_PROPAGATE(gemm_bf16_tc(m->a3f, 3 * D, m->f1w3, 3 * D, w + m->o_f1b, m->oh2, D, rows, D, 3 * D, SMK_EPI_RELU, 1, 0, nullptr, s, D));
+      if (all_layers) {
+        SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, objectness, rows, D, s));
+      } else {
+        SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
+        SMK_CHECK_CUDA(cudaMemcpy2DAsync(objectness, (size_t)nq * 4, m->otmp + (int64_t)(L - 1) * nq, (size_t)L * nq * 4, (size_t)nq * 4, (size_t)B,
+                                         cudaMemcpyDeviceToDevice, s));
+      }
     } else {
+      const float* qsrc = m->queries + (int64_t)layer0 * R * D;
+      const int rows = Lout * R;
       SMK_PROPAGATE(gemm_hp(qsrc, D, w + m->o_f0w, D, w + m->o_f0b, m->oh1, D, rows, D, D, SMK_EPI_RELU, s));
       SMK_PROPAGATE(gemm_hp(m->oh1, D, w + m->o_f1w, D, w + m->o_f1b, m->oh2, D, rows, D, D, SMK_EPI_RELU, s));
+      SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
+      SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));
     }
-    SMK_PROPAGATE(rowdot_sigmoid(m->oh2, w + m->o_f2w, w + m->o_f2b, m->otmp, rows, D, s));
-    SMK_PROPAGATE(permute_lb(m->otmp, objectness, Lout, B, nq, s));
   }
   if (features) SMK_PROPAGATE(query_mean(m->queries + (int64_t)(L - 1) * R * D, features, B, nq, D, s));
   return SMK_OK;

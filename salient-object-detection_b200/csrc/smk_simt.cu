@@ -25,7 +25,7 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
                                              elements form the bf16x3 split [hi | hi | lo] a split GEMM consumes */,
                  __nv_bfloat16* __restrict__ alt_hi, __nv_bfloat16* __restrict__ alt_lo /* optional bf16 hi / lo copies (rows of D) next to
                                              a 16-bit y of another type: the final encoder norm feeds fp16 GEMMs and the bf16 mask head */,
-                 int64_t ldy, int64_t rows, int D, float eps, int rev) {
+                 int64_t ldy, int64_t ld_alt, int64_t rows, int D, float eps, int rev) {
   pdl_wait();
   pdl_trigger();
   const int64_t blk = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;     // descending: start on the rows written last
@@ -98,8 +98,8 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
           uint2 pk, pr;
           split16x2<__nv_bfloat16>(o.x, o.y, pk.x, pr.x);
           split16x2<__nv_bfloat16>(o.z, o.w, pk.y, pr.y);
-          reinterpret_cast<uint2*>(alt_hi + row * D)[i] = pk;
-          if (alt_lo) reinterpret_cast<uint2*>(alt_lo + row * D)[i] = pr;
+          reinterpret_cast<uint2*>(alt_hi + row * ld_alt)[i] = pk;
+          if (alt_lo) reinterpret_cast<uint2*>(alt_lo + row * ld_alt)[i] = pr;
         }
       }
     }
@@ -109,8 +109,9 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
 template <typename TOut>
 static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
                             float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s, TOut* y_dup = nullptr, int64_t ldy = 0,
-                            __nv_bfloat16* alt_hi = nullptr, __nv_bfloat16* alt_lo = nullptr) {
+                            __nv_bfloat16* alt_hi = nullptr, __nv_bfloat16* alt_lo = nullptr, int64_t ld_alt = 0) {
   if (ldy == 0) ldy = D;
+  if (ld_alt == 0) ld_alt = D;
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + 8 * LN_ROWS - 1) / (8 * LN_ROWS));
@@ -119,7 +120,7 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
                                                      (y_dup ? sizeof(TOut) : 0) + (alt_hi ? 2.0 : 0.0) + (alt_lo ? 2.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, alt_hi, alt_lo, ldy, rows, D, eps, rev)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, alt_hi, alt_lo, ldy, ld_alt, rows, D, eps, rev)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -132,15 +133,15 @@ int layernorm_f32(const float* x, const float* res, const float* gamma, const fl
   return launch_layernorm<float>(x, res, gamma, beta, y, nullptr, sum_out, nullptr, rows, D, eps, s);
 }
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
-                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo) {
-  return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps, s);
+                   float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo, int64_t ldy) {
+  return launch_layernorm<__nv_bfloat16>(x, res, gamma, beta, y, y32, sum_out, y_lo, rows, D, eps, s, nullptr, ldy);
 }
 
 // fp16 output for the fp16s mode: y = fp16(LN(x)) in rows of ldy elements; y_lo (optional) = fp16 rounding residue, normally at
 // y + D so that a row is the [hi | lo] split operand of a 3-term GEMM; y32 / alt_hi / alt_lo: optional fp32 and bf16 hi / lo copies
 int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
-                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s) {
-  return launch_layernorm<__half>(x, nullptr, gamma, beta, y, y32, nullptr, y_lo, rows, D, eps, s, nullptr, ldy, alt_hi, alt_lo);
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt) {
+  return launch_layernorm<__half>(x, nullptr, gamma, beta, y, y32, nullptr, y_lo, rows, D, eps, s, nullptr, ldy, alt_hi, alt_lo, ld_alt);
 }
 
 // LayerNorm whose output is the bf16x3 split [hi | hi | lo] (rows of 3D bf16) of the normalised row: the A operand of a split
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(DLN_THREADS)
 dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      const float* __restrict__ pos, int period, __nv_bfloat16* __restrict__ a3a, __nv_bfloat16* __restrict__ a3b,
                      const float* __restrict__ gamma2, const float* __restrict__ beta2, float* __restrict__ y2,
-                     __nv_bfloat16* __restrict__ y2s, int64_t rows, int D) {
+                     __nv_bfloat16* __restrict__ y2s, int64_t rows, int D, int y2s_period, int y2s_stride) {
   pdl_wait();
   pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * (DLN_THREADS / 32) + (threadIdx.x >> 5);
@@ -229,19 +230,20 @@ dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __res
     }
   }
   if (gamma2) {
+    const int64_t y2s_row = y2s_period > 0 ? (row / y2s_period) * y2s_stride + row % y2s_period : row;
     normalise(gamma2, beta2, s_y);
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int i = lane + 32 * c;
       if (y2) reinterpret_cast<float4*>(y2 + row * D)[i] = v[c];
-      if (y2s) store_split4(y2s + row * 3 * D, D, 4 * i, v[c]);
+      if (y2s) store_split4(y2s + y2s_row * 3 * D, D, 4 * i, v[c]);
     }
   }
 }
 
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
-                  int64_t rows, int D, cudaStream_t s) {
+                  int64_t rows, int D, cudaStream_t s, int y2s_period, int y2s_stride) {
   SMK_REQUIRE(D % 128 == 0 && D <= 512, "dec_layernorm: D=%d must be a multiple of 128 and <= 512", D);
   SMK_REQUIRE(!a3b || (pos && period > 0), "dec_layernorm: a3b needs the query positions");
   if (rows == 0) return SMK_OK;
@@ -250,7 +252,7 @@ int dec_layernorm(float* x, const float* res, const float* gamma, const float* b
                                                      (y2s ? 6.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_DLN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(DLN_THREADS), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(DLN_THREADS), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D, y2s_period, y2s_stride)); break;
     SMK_DLN_CASE(1) SMK_DLN_CASE(2) SMK_DLN_CASE(3) SMK_DLN_CASE(4)
 #undef SMK_DLN_CASE
   }

@@ -581,3 +581,28 @@ def test_attention_small_fp16_matches_torch(Lq, Lk, kv_rows, kv_row0, q_f32):
     assert torch.equal(out[:, :D], out[:, D:2 * D])
     got = out[:, :D].double() + out[:, 2 * D:].double()
     assert (got - ref).abs().max().item() <= 3e-3            # fp16 P: 2^-11 relative; bf16 operands give ~2e-2 here
+
+
+@pytest.mark.parametrize("B,Ra,a_row0,rows_a,hw", [(37, 120, 0, 120, 196), (5, 120, 100, 20, 196), (3, 60, 0, 60, 156), (2, 120, 0, 120, 576),
+                                                   (150, 120, 0, 120, 196), (1, 384, 0, 384, 784)])
+def test_gemm_batched_mask_logits_match_fp64(B, Ra, a_row0, rows_a, hw):
+    """smk_gemm_batched — the mask-logit contraction as ONE batched tcgen05 GEMM: per image the (up to 128-row) tile of split query
+    rows [hi | hi | lo] against that image's patch tokens [hi | lo] (cls row skipped), 3 terms, 3-D TMA store that clips pad rows."""
+    torch.manual_seed(50)
+    D, N = 384, hw + 1
+    q = torch.randn(B * Ra, D, device=DEV) * 2.0
+    t = torch.randn(B * N, D, device=DEV) * 1.5
+    qh, ql = _split16(q, torch.bfloat16)
+    th, tl = _split16(t, torch.bfloat16)
+    q3 = torch.cat([qh, qh, ql], dim=1).contiguous()
+    t2 = torch.cat([th, tl], dim=1).contiguous()
+    out = torch.full((B, rows_a, hw), 7.0, device=DEV)
+    ao, wo = (C.c_int32 * 3)(0, D, 2 * D), (C.c_int32 * 3)(0, D, 0)
+    check(lib().smk_gemm_batched(ptr(q3), 3 * D, B * Ra, Ra, a_row0, rows_a, ptr(t2), 2 * D, B * N, N, 1, hw, ptr(out), B, D, 0, 3, ao, wo, stream_ptr()),
+          "smk_gemm_batched")
+    torch.cuda.synchronize()
+    qq = q.double().view(B, Ra, D)[:, a_row0:a_row0 + rows_a]
+    tt = t.double().view(B, N, D)[:, 1:]
+    ref = qq @ tt.transpose(1, 2)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item() / 50), err          # 3-term bf16 split: ~2^-16 relative on |logit| up to ~150
