@@ -209,6 +209,7 @@ int smk_attention_tc_general(const void* q, int64_t ldq, const void* k, int64_t 
 /* tuning aid: phase trace of CTA 0 of the tcgen05 attention kernel ([16 items][10 warps][8 events] clock64 stamps in device
  * memory); NULL switches it off. */
 int smk_debug_attn_trace(long long* buf);
+int smk_debug_xattn_trace(long long* buf);  /* tuning aid: phase trace of CTA 0 of the cross-attention kernel ([8 images][2 roles][8 events]) */
 int smk_debug_gemm_trace(long long* buf);   /* tuning aid: per-CTA wait-cycle counters of the tcgen05 GEMM (16 per CTA); NULL = off */
 /* Few-query attention (decoder self / cross attention, transformer_decoder.py:271-291): Lq <= 32 queries and Lk <= 256 keys per
  * (image, head), head dim 64, bf16 inputs.  Image b: queries at rows b*Lq.., keys / values at rows b*kv_rows + kv_row0 ..
@@ -224,6 +225,18 @@ int smk_attention_small_f16(const void* q, int64_t ldq, const void* k, int64_t l
  * [0, heads*64) and k in [heads*64, 2*heads*64), v [B*nq, ldv] fp32 → out3 [B*nq, 3*heads*64] bf16 split [hi | hi | lo]. */
 int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, void* out3, int B, int nq, int heads,
                            float scale, void* stream);
+
+/* Decoder cross-attention against the memory, restructured (smk_xattn_tc.cu; transformer_decoder.py:283-291): per image the nq*heads
+ * rows of qp [n_img*nq, heads*D] fp16 (row (b, q), column (h, c): the query times the folded Wq_h^T Wk_h / 8) attend the image's hw
+ * final-LN patch tokens tok [n_img*t_rows_per_img, D] fp16 (rows b*t_rows_per_img + t_row0 ..) as keys AND values, on tcgen05:
+ * out [n_img*nq, 2*heads*D] fp16 split [hi | lo] = softmax(qp_h tok^T) tok per head h.  nq*heads <= 128, hw <= 208, D <= 384. */
+int smk_xattn_tc(const void* qp, const void* tok, int t_rows_per_img, int t_row0, void* out, int n_img, int nq, int heads, int D, int hw,
+                 void* stream);
+/* the weight folding that goes with it, from one decoder layer's multihead_attn in_proj_weight [3D, D] / in_proj_bias [3D] /
+ * out_proj.weight [D, D] / out_proj.bias [D]:  wg [heads*D, D] fp16 = (Wq_h^T Wk_h / 8) as GEMM weight rows (h, c), g [heads*D] its
+ * bias (bq_h Wk_h / 8), mcat [D, heads*D] fp32 = Wo_h Wv_h per head block, bo2 [D] = Wo bv + bo */
+int smk_xattn_fold_weights(const float* in_proj_w, const float* in_proj_b, const float* out_w, const float* out_b, void* wg, float* g,
+                           float* mcat, float* bo2, int D, int heads, void* stream);
 
 /* Online-softmax attention (64 queries x 64-key blocks per step, mma.sync) for any sequence length: 384x384 images (577 tokens),
  * ViT-S/8 (785 tokens) and, with q_lo / k_lo / v_lo non-NULL, the bf16x3 split mode (3-term products, ~fp32 accuracy).

@@ -53,6 +53,8 @@ SIGNATURES = {
     "smk_gemm_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_gemm_split": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "smk_gemm_batched": (_I, [_P, _L, _L, _I, _I, _I, _P, _L, _L, _I, _I, _I, _P, _I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "smk_xattn_tc": (_I, [_P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "smk_xattn_fold_weights": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "smk_attention_tc_f16": (_I, [_P, _P, _L, _I, _I, _I, _I, _F, _P]),
     "smk_attention_small_f16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, C.c_float, _I, _P]),
     "smk_dec_self_attention": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _F, _P]),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "smk_attention_fa": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_debug_attn_trace": (_I, [_P]),
     "smk_debug_gemm_trace": (_I, [_P]),
+    "smk_debug_xattn_trace": (_I, [_P]),
     "smk_gemm_ln": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "smk_split3": (_I, [_P, _L, _I, _P, _I, _P]),
     "smk_cast_bf16": (_I, [_P, _P, _L, _P]),

@@ -28,7 +28,13 @@ int layernorm_f16(const float* x, const float* gamma, const float* beta, __half*
 // [B][L][nq] layout of the mask / objectness head operand: period = nq, stride = L·nq, y2s pre-offset by layer·nq rows); 0 = row r
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
-                  int64_t rows, int D, cudaStream_t s, int y2s_period = 0, int y2s_stride = 0);
+                  int64_t rows, int D, cudaStream_t s, int y2s_period = 0, int y2s_stride = 0, __half* xh = nullptr);
+// restructured decoder cross-attention on tcgen05 (smk_xattn_tc.cu)
+bool xattn_supported(int nq, int heads, int D, int hw);
+int xattn_fold_weights(const float* in_proj_w, const float* in_proj_b, const float* out_w, const float* out_b, __half* wg, float* g, float* mcat,
+                       float* bo2, int D, int heads, cudaStream_t s);
+int xattn_tc(const __half* qp, const __half* tok, int t_rows_per_img, int t_row0, __half* out, int n_img, int nq, int heads, int D, int hw,
+             cudaStream_t s);
 int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N, int K,
              int epi, cudaStream_t s);
 int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,

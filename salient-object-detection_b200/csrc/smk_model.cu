@@ -176,6 +176,11 @@ struct smk_model {
   float* debug_logits;
   int last_B;
   // decoder state after layer 0's self-attention block (image-independent: tgt = 0), filled by the first forward pass
+  // fp16s mode, restructured cross-attention (smk_xattn_tc.cu): per layer the folded query weights Wg [heads·D, D] fp16 + bias g,
+  // the folded value/output weights Mcat [D, heads·D] as a bf16 split [hi | lo | hi] + bias; activations Q' / U / fp16(tgt + pos)
+  bool xattn = false;
+  __half *xa_wg, *xa_qp, *xa_xh, *dec0_xh, *xa_m2, *xa_u2;
+  float *xa_g, *xa_bo, *xa_scratch;
   float* dec0_tgt;                // [nq, D]
   __nv_bfloat16* dec0_a3b;        // [nq, 3D] split(tgt + query_pos)
   bool dec0_ready = false;
@@ -257,6 +262,19 @@ static void plan(smk_model& m, Plan& pl) {
     m.a3b = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(tgt + query_pos)
     m.a3c = pl.take<__nv_bfloat16>(R * 3 * D);                         // split(attention output)
     m.a3f = pl.take<__nv_bfloat16>(std::max(R * 3 * FD, L * R * 3 * D));   // split(FFN hidden) / split(objectness hidden)
+    m.xattn = hx && xattn_supported((int)nq, c.heads, (int)D, m.hw) && !(getenv("SMK_XATTN") && atoi(getenv("SMK_XATTN")) == 0);
+    if (m.xattn) {
+      const int64_t HD = (int64_t)c.heads * D;
+      m.xa_wg = pl.take<__half>(L * HD * D);
+      m.xa_g = pl.take<float>(L * HD);
+      m.xa_m2 = pl.take<__half>(L * D * 2 * HD);
+      m.xa_bo = pl.take<float>(L * D);
+      m.xa_scratch = pl.take<float>(D * HD);
+      m.xa_qp = pl.take<__half>(R * HD);
+      m.xa_u2 = pl.take<__half>(R * 2 * HD);
+      m.xa_xh = pl.take<__half>(R * D);
+      m.dec0_xh = pl.take<__half>(nq * D);
+    }
     m.dec0_tgt = pl.take<float>(nq * D);
     m.dec0_a3b = pl.take<__nv_bfloat16>(nq * 3 * D);
     m.a3q = pl.take<__nv_bfloat16>(L * R * 3 * D);                     // split(final-norm queries), all layers
@@ -488,6 +506,16 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
     }
     if ((st = split3_weight(weights + m->o_f0w, m->f0w3, D, (int)D, s)) != SMK_OK) return fail(st);
     if ((st = split3_weight(weights + m->o_f1w, m->f1w3, D, (int)D, s)) != SMK_OK) return fail(st);
+    if (m->xattn) {
+      const int64_t HD = (int64_t)cfg->heads * D;
+      for (int l = 0; l < cfg->dec_layers; ++l) {
+        const DecW& d = m->dec[l];
+        if ((st = xattn_fold_weights(weights + d.caw, weights + d.cab, weights + d.caow, weights + d.caob, m->xa_wg + l * HD * D, m->xa_g + l * HD,
+                                     m->xa_scratch, m->xa_bo + l * D, (int)D, cfg->heads, s)) != SMK_OK)
+          return fail(st);
+        if ((st = split2_f16(m->xa_scratch, HD, m->xa_m2 + l * D * 2 * HD, D, (int)HD, s)) != SMK_OK) return fail(st);
+      }
+    }
   }
   *out = m;
   return SMK_OK;
@@ -649,7 +677,8 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     }
     // final norm: fp32 tokens (mask head reference copy), bf16 hi / lo (mask-logit contraction), fp16 (decoder memory)
     { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + m->o_enw, w + m->o_enb, m->tokh, nullptr, D, m->tok32, m->tok16, m->tok16 + D, M, D, 1e-6f, s, 2 * D)); }
-    { TagScope tg(TAG_KV); SMK_PROPAGATE(gemm_tc(m->tokh, D, m->kvwh, 2 * D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_kv == 3 ? 2 : m->t_kv, D), 0, s)); }
+    // memory K/V projection: only for geometries the restructured cross-attention does not cover (it attends the tokens directly)
+    if (!m->xattn) { TagScope tg(TAG_KV); SMK_PROPAGATE(gemm_tc(m->tokh, D, m->kvwh, 2 * D, m->kvb, m->KV, (int64_t)L * 2 * D, M, L * 2 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_kv == 3 ? 2 : m->t_kv, D), 0, s)); }
   } else if (bf) {
     __nv_bfloat16 *Xn = (__nv_bfloat16*)m->Xn, *QKV = (__nv_bfloat16*)m->QKV, *AO = (__nv_bfloat16*)m->AO, *Hm = (__nv_bfloat16*)m->Hm;
     {
@@ -787,8 +816,11 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       for (int l = 0; l < L; ++l) {
         const DecW& d = m->dec[l];
         const Dec3& d3 = m->dec3[l];
+        const bool xa = m->xattn;
+        __half* xh = xa ? m->xa_xh + r0 * D : nullptr;
         if (l == 0 && reuse0) {
-          SMK_PROPAGATE(tile_rows2(tgt, m->dec0_tgt, D * 4, a3b, m->dec0_a3b, 3 * D * 2, R, nq, s));
+          if (xa) SMK_PROPAGATE(tile_rows2(tgt, m->dec0_tgt, D * 4, xh, m->dec0_xh, D * 2, R, nq, s));
+          else SMK_PROPAGATE(tile_rows2(tgt, m->dec0_tgt, D * 4, a3b, m->dec0_a3b, 3 * D * 2, R, nq, s));
         } else {
         // self-attention: q = k = tgt + query_pos, v = tgt
         if (hx && nq <= 32) {
@@ -806,20 +838,28 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
           else SMK_PROPAGATE(attention_tc_general(dqk_b, 2 * D, dqk_b + D, 2 * D, dv_b, D, R, nq, 0, a3c, 3 * D, 2, nb, nq, nq, c.heads, scale, s));
         }
         SMK_PROPAGATE(gemm3(a3c, d3.saow, w + d.saob, t2, D, R, D, D, SMK_EPI_NONE, 1));
-        { TagScope tg(TAG_DEC_LN); SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, a3b, nullptr, nullptr, nullptr, nullptr, R, D, s)); }
+        { TagScope tg(TAG_DEC_LN); SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n1w, w + d.n1b, 1e-5f, qpos, nq, nullptr, xa ? nullptr : a3b, nullptr, nullptr, nullptr, nullptr, R, D, s, 0, 0, xh)); }
         if (l == 0 && b0 == 0) {
           cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
           cudaStreamIsCapturing(s, &cap);
           if (cap == cudaStreamCaptureStatusNone) {
             SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_tgt, tgt, (size_t)nq * D * 4, cudaMemcpyDeviceToDevice, s));
-            SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_a3b, a3b, (size_t)nq * 3 * D * 2, cudaMemcpyDeviceToDevice, s));
+            if (xa) SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_xh, xh, (size_t)nq * D * 2, cudaMemcpyDeviceToDevice, s));
+            else SMK_CHECK_CUDA(cudaMemcpyAsync(m->dec0_a3b, a3b, (size_t)nq * 3 * D * 2, cudaMemcpyDeviceToDevice, s));
             m->dec0_ready = true;
           }
         }
         }
         // cross-attention: q = tgt + query_pos, k = v = memory (patch tokens, cls skipped; pos = None)
         const __nv_bfloat16* kl = KVg + (int64_t)l * 2 * D;       // layer l's keys in the all-layer K/V tensor; values D columns further
-        if (hx) {
+        if (xa) {
+          // fp16s mode, restructured form (smk_xattn_tc.cu): Q' = x·Wg^T + g (fp16) → per-image S = Q'·T^T, softmax, U = P·T on tcgen05
+          // → out = U·Mcat^T + (Wo bv + bo) as a 3-term split GEMM; no K/V projection of the memory
+          const int64_t HD = (int64_t)c.heads * D;
+          { TagScope tg(TAG_DEC_GEMM); SMK_PROPAGATE(gemm_tc(xh, D, m->xa_wg + l * HD * D, D, m->xa_g + l * HD, m->xa_qp + r0 * HD, HD, R, (int)HD, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms_plain(), D / c.heads, s)); }
+          { TagScope tg(TAG_DEC_ATTN); SMK_PROPAGATE(xattn_tc(m->xa_qp + r0 * HD, m->tokh + (int64_t)b0 * N * D, N, 1, m->xa_u2 + r0 * 2 * HD, nb, nq, c.heads, D, hw, s)); }
+          { TagScope tg(TAG_DEC_GEMM); SMK_PROPAGATE(gemm_tc(m->xa_u2 + r0 * 2 * HD, 2 * HD, m->xa_m2 + l * D * 2 * HD, 2 * HD, m->xa_bo + l * D, t2, D, R, D, (int)HD, SMK_EPI_NONE, 1, 0, nullptr, 1, terms_full((int)HD), D, s)); }
+        } else if (hx) {
           // fp16s mode: fp16 K / V (weight-split projection above), the query projected to fp32 and rounded to fp16 when staged
           SMK_PROPAGATE(gemm3(a3b, d3.caqw, w + d.cab, cq32, D, R, D, D, SMK_EPI_NONE, 1));
           TagScope tg(TAG_DEC_ATTN);
@@ -835,7 +875,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
           else if (hw <= 256) SMK_PROPAGATE(attention_tc_general(cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)nb * N, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
           else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));   // 384x384: 576 memory keys
         }
-        SMK_PROPAGATE(gemm3(a3c, d3.caow, w + d.caob, t2, D, R, D, D, SMK_EPI_NONE, 1));
+        if (!xa) SMK_PROPAGATE(gemm3(a3c, d3.caow, w + d.caob, t2, D, R, D, D, SMK_EPI_NONE, 1));
         { TagScope tg(TAG_DEC_LN); SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s)); }
         // FFN (ReLU); the shared final norm on every layer's output (transformer_decoder.py:138-145) rides on the last LayerNorm
         SMK_PROPAGATE(gemm3(a3a, d3.l1w, w + d.l1b, a3f, 3 * FD, R, FD, D, SMK_EPI_RELU, 2));

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(DLN_THREADS)
 dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                      const float* __restrict__ pos, int period, __nv_bfloat16* __restrict__ a3a, __nv_bfloat16* __restrict__ a3b,
                      const float* __restrict__ gamma2, const float* __restrict__ beta2, float* __restrict__ y2,
-                     __nv_bfloat16* __restrict__ y2s, int64_t rows, int D, int y2s_period, int y2s_stride) {
+                     __nv_bfloat16* __restrict__ y2s, int64_t rows, int D, int y2s_period, int y2s_stride,
+                     __half* __restrict__ xh /* optional: fp16(y + pos) rows of D — the fp16s mode's cross-attention query GEMM operand */) {
   pdl_wait();
   pdl_trigger();
   const int64_t row = (int64_t)blockIdx.x * (DLN_THREADS / 32) + (threadIdx.x >> 5);
@@ -228,6 +229,13 @@ dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __res
       const float4 pp = reinterpret_cast<const float4*>(prow)[i];
       store_split4(a3b + row * 3 * D, D, 4 * i, make_float4(v[c].x + pp.x, v[c].y + pp.y, v[c].z + pp.z, v[c].w + pp.w));
     }
+    if (xh) {
+      const float4 pp = reinterpret_cast<const float4*>(prow)[i];
+      uint2 u;
+      u.x = Pack16<__half>::pack(v[c].x + pp.x, v[c].y + pp.y);
+      u.y = Pack16<__half>::pack(v[c].z + pp.z, v[c].w + pp.w);
+      reinterpret_cast<uint2*>(xh + row * D)[i] = u;
+    }
   }
   if (gamma2) {
     const int64_t y2s_row = y2s_period > 0 ? (row / y2s_period) * y2s_stride + row % y2s_period : row;
@@ -243,16 +251,16 @@ dec_layernorm_kernel(float* x, const float* __restrict__ res, const float* __res
 
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
                   __nv_bfloat16* a3a, __nv_bfloat16* a3b, const float* gamma2, const float* beta2, float* y2, __nv_bfloat16* y2s,
-                  int64_t rows, int D, cudaStream_t s, int y2s_period, int y2s_stride) {
+                  int64_t rows, int D, cudaStream_t s, int y2s_period, int y2s_stride, __half* xh) {
   SMK_REQUIRE(D % 128 == 0 && D <= 512, "dec_layernorm: D=%d must be a multiple of 128 and <= 512", D);
-  SMK_REQUIRE(!a3b || (pos && period > 0), "dec_layernorm: a3b needs the query positions");
+  SMK_REQUIRE((!a3b && !xh) || (pos && period > 0), "dec_layernorm: a3b / xh need the query positions");
   if (rows == 0) return SMK_OK;
   const unsigned grid = (unsigned)((rows + DLN_THREADS / 32 - 1) / (DLN_THREADS / 32));
   ProfScope prof(PROF_LAYERNORM, (double)rows * D * (8.0 + (res ? 4.0 : 0.0) + (a3a ? 6.0 : 0.0) + (a3b ? 6.0 : 0.0) + (y2 ? 4.0 : 0.0) +
                                                      (y2s ? 6.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_DLN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(DLN_THREADS), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D, y2s_period, y2s_stride)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(dec_layernorm_kernel<c>, dim3(grid), dim3(DLN_THREADS), 0, s, x, res, gamma, beta, eps, pos, period, a3a, a3b, gamma2, beta2, y2, y2s, rows, D, y2s_period, y2s_stride, xh)); break;
     SMK_DLN_CASE(1) SMK_DLN_CASE(2) SMK_DLN_CASE(3) SMK_DLN_CASE(4)
 #undef SMK_DLN_CASE
   }

@@ -606,3 +606,47 @@ def test_gemm_batched_mask_logits_match_fp64(B, Ra, a_row0, rows_a, hw):
     ref = qq @ tt.transpose(1, 2)
     err = (out.double() - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item() / 50), err          # 3-term bf16 split: ~2^-16 relative on |logit| up to ~150
+
+
+def test_xattn_weight_folding_matches_fp64():
+    """Wg = Wq_h^T Wk_h / 8, g = bq_h Wk_h / 8, Mcat = Wo_h Wv_h, bo2 = Wo bv + bo (smk_xattn_tc.cu): the algebra that removes the
+    memory K/V projection from the decoder's cross-attention."""
+    torch.manual_seed(60)
+    D, H = 384, 6
+    w_in = torch.randn(3 * D, D, device=DEV) * 0.03
+    b_in = torch.randn(3 * D, device=DEV) * 0.02
+    w_o, b_o = torch.randn(D, D, device=DEV) * 0.03, torch.randn(D, device=DEV) * 0.02
+    wg = torch.empty(H * D, D, dtype=torch.float16, device=DEV)
+    g, mcat, bo2 = torch.empty(H * D, device=DEV), torch.empty(D, H * D, device=DEV), torch.empty(D, device=DEV)
+    check(lib().smk_xattn_fold_weights(ptr(w_in), ptr(b_in), ptr(w_o), ptr(b_o), ptr(wg), ptr(g), ptr(mcat), ptr(bo2), D, H, stream_ptr()))
+    torch.cuda.synchronize()
+    Wq, Wk, Wv = (t.double() for t in w_in.split(D))
+    bq, bk, bv = (t.double() for t in b_in.split(D))
+    for h in range(H):
+        sl = slice(h * 64, (h + 1) * 64)
+        G = Wq[sl].t() @ Wk[sl] / 8                     # [c', c]
+        assert (wg[h * D:(h + 1) * D].double() - G.t()).abs().max().item() <= 2e-3 * G.abs().max().item() + 1e-7     # fp16 storage
+        assert (g[h * D:(h + 1) * D].double() - bq[sl] @ Wk[sl] / 8).abs().max().item() <= 1e-7
+        assert (mcat[:, h * D:(h + 1) * D].double() - w_o.double()[:, sl] @ Wv[sl]).abs().max().item() <= 1e-7
+    assert (bo2.double() - (w_o.double() @ bv + b_o.double())).abs().max().item() <= 1e-7
+
+
+@pytest.mark.parametrize("B,nq,hw", [(3, 20, 196), (150, 20, 196), (37, 10, 196), (5, 20, 156), (2, 21, 208), (1, 1, 16)])
+def test_xattn_tcgen05_matches_torch(B, nq, hw):
+    """Restructured decoder cross-attention on tcgen05: per image the nq·6 (query, head) rows against the image's patch tokens as
+    keys and values (cls row skipped), fp16 operands, fp16 [hi | lo] split output."""
+    torch.manual_seed(61)
+    H, D, N = 6, 384, hw + 1
+    qp = (torch.randn(B * nq, H * D, device=DEV) * 0.25).to(torch.float16)
+    tok = (torch.randn(B * N, D, device=DEV) * 1.2).to(torch.float16)
+    out = torch.full((B * nq, 2 * H * D), 7.0, device=DEV, dtype=torch.float16)
+    check(lib().smk_xattn_tc(ptr(qp), ptr(tok), N, 1, ptr(out), B, nq, H, D, hw, stream_ptr()), "smk_xattn_tc")
+    torch.cuda.synchronize()
+    q = qp.double().view(B, nq * H, D)
+    t = tok.double().view(B, N, D)[:, 1:]
+    ref = (torch.softmax(q @ t.transpose(1, 2), -1) @ t).view(B * nq, H * D)
+    HD = H * D
+    got = out[:, :HD].double() + out[:, HD:].double()
+    err = (got - ref).abs().max().item()
+    assert err <= 4e-3, err                     # fp16 P (2^-11 relative), ex2.approx; values of magnitude ~1
+    assert (got - ref).abs().mean().item() <= 2e-4
