@@ -20,6 +20,22 @@
  *   smk_upsample_bilinear  evaluator.pyc@L209-211  F.interpolate(scale_factor=4, 'bilinear')[..., :h, :w]
  *   smk_mask_metrics   the same reductions for one full-resolution mask (the five metric callables)
  *   smk_gemm_*, smk_layernorm, smk_attention, ...   single kernels, exported for unit tests
+ *
+ * Mapping to the export list sketched in SURVEY.md §8b (the survey proposed per-stage entry points; the library keeps the stages in
+ * ONE forward call so that no intermediate tensor crosses the boundary, and exposes them through taps and single-kernel entries):
+ *   smk_encoder_forward(h, x, tokens_out)          → smk_model_forward(..., mask_pred = objectness = features = NULL) + smk_model_tap(h, 1, tokens_out)
+ *                                                     (the Python mirror's `model(x, encoder_only=True)`)
+ *   smk_decoder_forward(h, tokens, queries, obj)    → inside smk_model_forward; queries via smk_model_tap(h, 2, ...), objectness is an output
+ *   smk_mask_head(h, queries, tokens, mask_pred)    → inside smk_model_forward (all_layers selects 6-layer / last-layer masks); the
+ *                                                     contraction alone is smk_gemm_batched
+ *   smk_upsample_sigmoid / smk_hist_metrics / smk_smeasure → fused in smk_eval_batch (x4 upsample + every metric reduction in two
+ *                                                     launches) and, for one full-resolution mask, smk_mask_metrics; the upsample alone
+ *                                                     is smk_upsample_bilinear
+ *   smk_layernorm, smk_gemm_*, smk_attention*       → exported as sketched
+ *
+ * Threading contract: one host thread drives a device at a time.  Per-device one-time state (kernel attributes, SM count, the
+ * persisting-L2 carve-out) is keyed by the CUDA device ordinal, so one process may use several GPUs in turn; two host threads on
+ * the SAME device must serialise their calls (the optional event profiler and launch counter are process-wide).
  */
 #ifndef SELFMASK_B200_H_
 #define SELFMASK_B200_H_

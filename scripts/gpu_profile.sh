@@ -20,8 +20,8 @@ cap() { name=$1; skip=$2; count=$3
   echo "$name rc=$?"; }
 cap enc 10 7
 cap kv 87 2
-cap dec 97 12
-cap tail 157 9
+cap dec ${DEC_SKIP:-96} 12
+cap tail ${TAIL_SKIP:-156} 8
 ls -la gpurun_out/*.ncu-rep
 # summaries are produced ON the box (gpurun pulls at most 64 MiB back): tables + traffic JSON, then only the encoder-layer
 # report (source-level view of the GEMM / attention / LayerNorm kernels) travels home
