@@ -2,7 +2,7 @@
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread) and
 // TMEM owner, warps 2-9 = epilogue (two warpgroups, each owning half of the tile's columns).  Operands are staged
-// by TMA into a kStages-deep ring of 128-byte-swizzled shared-memory tiles; fp32 accumulators live in TMEM and are
+// by TMA into a ring of 128-byte-swizzled shared-memory tiles (a stage = all distinct operand tiles of a k-block); fp32 accumulators live in TMEM and are
 // double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Epilogue: TMEM → registers (tcgen05.ld, one accumulator row per thread) → bias / activation → swizzled
 // shared-memory staging tile (conflict-free 16-byte stores) → TMA tile store.  A per-thread row store straight to
@@ -106,7 +106,14 @@ struct TcGemmParams {
   // Split-operand products: C = Σ_t A[:, ta[t] : ta[t]+K] · W[:, tw[t] : tw[t]+K]^T.  Operands stored as [hi | lo] rows (hi = T(x),
   // lo = T(x − hi)) give  A·W^T ≈ hi·hi + hi·lo + lo·hi  (terms (0,0), (0,K), (K,0): ~fp32 accuracy)  or  A_hi·(W_hi + W_lo)^T
   // (terms (0,0), (0,K): the weight rounding removed) without a second copy of hi.  One term (0,0) = the plain GEMM.
-  int n_terms, ta[TC_MAX_TERMS], tw[TC_MAX_TERMS];
+  int n_terms;
+  // The terms as a product structure: n_a distinct A column offsets x n_w distinct W column offsets (<= 2 each) and the (i, j)
+  // pairs to multiply.  One pipeline stage carries all distinct operand tiles of a k-block — A_hi, A_lo, W_hi, W_lo: 4 tiles for the
+  // 3 products of a full split instead of the 6 a term-by-term k loop would load (these GEMMs are bound by the L2 → SM operand
+  // feed: 64 B/clk per SM wanted at the MMA rate against ~43 B/clk available) — and the issuer runs every pair on them.
+  int n_a, n_w, a_col[2], w_col[2], n_pairs, pair_a[TC_MAX_TERMS], pair_w[TC_MAX_TERMS];
+  int n_stages;   // ring depth at this stage size (<= the compile-time maximum)
+  int seq;        // 1: term-by-term k loop instead (a stage = one A tile + one W tile): only when a fused stage does not fit twice
   const float* bias;
   void* C;
   int64_t ldc;
@@ -175,7 +182,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = (p.N + BN - 1) / BN, m_blocks = (p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas);   // N % BN == 0 unless trans
   const int kpt = p.K / TC_BK;                                  // k-blocks per term
-  const int num_tiles = n_blocks * m_blocks, k_blocks = kpt * p.n_terms;
+  const int num_tiles = n_blocks * m_blocks, k_blocks = p.seq ? kpt * p.n_pairs : kpt;
+  const int na_s = p.seq ? 1 : p.n_a, nw_s = p.seq ? 1 : p.n_w;          // operand tiles per stage
+  // the term tables through registers with constant indices: a run-time index into the kernel-parameter arrays makes the compiler
+  // copy them to local memory, and the single issuing thread then pays a local load per k-block on the critical path
+  const int a_col0 = p.a_col[0], a_col1 = p.a_col[1], w_col0 = p.w_col[0], w_col1 = p.w_col[1];
+  const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2], pw0 = p.pair_w[0], pw1 = p.pair_w[1], pw2 = p.pair_w[2];
+  auto sel3 = [](int i, int x0, int x1, int x2) { return i == 0 ? x0 : (i == 1 ? x1 : x2); };
+  const int stage_bytes = na_s * Cfg::kABytes + nw_s * Cfg::kBBytes, n_stages = p.n_stages;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
   // tiles are owned by clusters, strided order (neighbouring CTAs work on neighbouring tiles)
   const int n_cl = gridDim.x / kCtas, cl = blockIdx.x / kCtas;
@@ -220,28 +234,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tile = p.rev ? num_tiles - 1 - tile_i : tile_i;
         // trans: the feature blocks of one token block are neighbours in the sequence (they share the activation tile in L2)
         const TileCoord tc_ = tile_coord(p, tile, m_blocks, n_blocks, BN, kCtas);
-        int term = 0, kk = 0;                      // k-block kb = term * kpt + kk
         for (int kb = 0; kb < k_blocks; ++kb) {
-          const int ka = p.ta[term] + kk * TC_BK, kw = p.tw[term] + kk * TC_BK;
-          if (++kk == kpt) { kk = 0; ++term; }
-          if ((dbg & TC_DBG_NOLOAD) && n_loads++ >= Cfg::kStages) continue;
+          if ((dbg & TC_DBG_NOLOAD) && n_loads++ >= n_stages) continue;
           w_slot.begin();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           w_slot.end();
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + na_s * Cfg::kABytes;
+          // seq: k-block kb belongs to term kb / kpt; fused: to all terms at once
+          const int term = p.seq ? kb / kpt : 0, kc = (p.seq ? kb - term * kpt : kb) * TC_BK;
+          const int ia0 = p.seq ? sel3(term, pa0, pa1, pa2) : 0, iw0 = p.seq ? sel3(term, pw0, pw1, pw2) : 0;
           if constexpr (kCtas == 2) {
             // both CTAs' bytes complete on the even CTA's barrier (its MMA thread is the only consumer)
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2(sa, &tmA, bar, ka, tc_.a_row + (int)rank * TC_BM);
-            tma_load_2d_cg2(sb, &tmB, bar, kw, tc_.b_row + (int)rank * Cfg::kBNL);
+            for (int i = 0; i < na_s; ++i) tma_load_2d_cg2(sa + i * Cfg::kABytes, &tmA, bar, (ia0 + i ? a_col1 : a_col0) + kc, tc_.a_row + (int)rank * TC_BM);
+            for (int j = 0; j < nw_s; ++j) tma_load_2d_cg2(sb + j * Cfg::kBBytes, &tmB, bar, (iw0 + j ? w_col1 : w_col0) + kc, tc_.b_row + (int)rank * Cfg::kBNL);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], ka, tc_.a_row);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kw, tc_.b_row);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            for (int i = 0; i < na_s; ++i) tma_load_2d(sa + i * Cfg::kABytes, &tmA, &full_bar[stage], (ia0 + i ? a_col1 : a_col0) + kc, tc_.a_row);
+            for (int j = 0; j < nw_s; ++j) tma_load_2d(sb + j * Cfg::kBBytes, &tmB, &full_bar[stage], (iw0 + j ? w_col1 : w_col0) + kc, tc_.b_row);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
       w_all.end();
@@ -266,24 +280,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
           w_ops.begin();
-          const bool skip_wait = (dbg & TC_DBG_NOLOAD) && n_used++ >= Cfg::kStages;
+          const bool skip_wait = (dbg & TC_DBG_NOLOAD) && n_used++ >= n_stages;
           if (!skip_wait) mbar_wait(&full_bar[stage], phase);
           w_ops.end();
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + (uint32_t)Cfg::kABytes;
-          const uint64_t a_desc = smem_desc_k_sw128(sa), b_desc = smem_desc_k_sw128(sb);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + (uint32_t)(na_s * Cfg::kABytes);
+          const int n_pr = p.seq ? 1 : p.n_pairs;
+          for (int pr = 0; pr < n_pr; ++pr) {
+            const uint64_t a_desc = smem_desc_k_sw128(sa + (uint32_t)((p.seq ? 0 : sel3(pr, pa0, pa1, pa2)) * Cfg::kABytes));
+            const uint64_t b_desc = smem_desc_k_sw128(sb + (uint32_t)((p.seq ? 0 : sel3(pr, pw0, pw1, pw2)) * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
-            if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
+              if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | pr | k) != 0);
+              else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | pr | k) != 0);
+            }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if (!(dbg & TC_DBG_NOCOMMIT)) {
             if constexpr (kCtas == 2) tc_commit_cg2(&empty_bar[stage], 3);
             else tc_commit(&empty_bar[stage]);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete → epilogue (of both CTAs)
         if constexpr (kCtas == 2) tc_commit_cg2(&tmem_full[acc], 3);
@@ -578,13 +596,44 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 
 static int num_sms() { return device_sm_count(); }
 
+// terms → distinct A / W column offsets + the (i, j) pairs; `swap`: the kernel's A operand is the caller's W (swap-AB form)
+static int set_terms(TcGemmParams& p, const GemmTerms& tr, bool swap) {
+  p.n_terms = tr.n;
+  p.n_a = p.n_w = p.n_pairs = 0;
+  for (int t = 0; t < tr.n; ++t) {
+    const int ao = swap ? tr.w_off[t] : tr.a_off[t], wo = swap ? tr.a_off[t] : tr.w_off[t];
+    int ia = -1, iw = -1;
+    for (int i = 0; i < p.n_a; ++i) if (p.a_col[i] == ao) ia = i;
+    for (int i = 0; i < p.n_w; ++i) if (p.w_col[i] == wo) iw = i;
+    if (ia < 0) { SMK_REQUIRE(p.n_a < 2, "gemm_tc: more than two distinct A parts"); ia = p.n_a; p.a_col[p.n_a++] = ao; }
+    if (iw < 0) { SMK_REQUIRE(p.n_w < 2, "gemm_tc: more than two distinct W parts"); iw = p.n_w; p.w_col[p.n_w++] = wo; }
+    p.pair_a[p.n_pairs] = ia;
+    p.pair_w[p.n_pairs++] = iw;
+  }
+  return SMK_OK;
+}
+
 template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p_in, cudaStream_t s) {
   using Cfg = TcCfg<BN, kCtas, kEW>;
   static DeviceOnce attr_set;
   if (attr_set.first()) {
     SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
+  }
+  TcGemmParams p = p_in;
+  {
+    // fused stages (all distinct operand tiles of a k-block, every product on them) or the term-by-term loop; SMK_GEMM_FUSE_TERMS = 0 / 1 forces
+    static int force = -2;
+    if (force == -2) {
+      const char* e = getenv("SMK_GEMM_FUSE_TERMS");
+      force = e ? atoi(e) : -1;
+    }
+    const int fused_stages = (Cfg::kStages * Cfg::kStageBytes) / (p.n_a * Cfg::kABytes + p.n_w * Cfg::kBBytes);
+    // measured on B200 (same box, fp16s step, profiles/r02_gemm_terms.md): fused stages 8.78 ms per step against 10.1 ms term by term
+    const bool fuse = force >= 0 ? (force != 0 && fused_stages >= 2) : fused_stages >= 2;
+    p.seq = (p.n_pairs > 1 && !fuse) ? 1 : 0;
+    p.n_stages = p.seq || p.n_pairs == 1 ? Cfg::kStages : fused_stages;
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas));
   const int slots = num_sms() / kCtas;                     // CTAs (kCtas = 1) or CTA pairs (2) that can be resident
@@ -734,8 +783,8 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   const int Ktot = K * tr.n;
   TcGemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.n_terms = tr.n;
-  for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.a_off[t]; p.tw[t] = tr.w_off[t]; }
+  p.M = M; p.N = N; p.K = K;
+  SMK_PROPAGATE(set_terms(p, tr, false));
   p.bias = bias; p.C = C; p.ldc = ldc; p.epi = epi; p.out_f32 = out_f32; p.tok_hw = tok_hw; p.tok_pos = tok_pos; p.dbg = dbg;
   p.rev = traverse_dir(); p.trans = 0; p.credit_k = credit_k > 0 ? credit_k : K;
   if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, Ktot)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
@@ -745,7 +794,7 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
     SMK_PROPAGATE(make_tmap_bf16_2d(&tb, A, (uint64_t)a_cols, (uint64_t)M, (uint64_t)lda * 2, TC_BK, 256));
     SMK_PROPAGATE(make_tmap_2d(&tcm, out_f32 ? 4 : 2, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * (out_f32 ? 4 : 2), 32, 32, out_f32 ? 128 : 64));
     p.M = N; p.N = M; p.trans = 1;
-    for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.w_off[t]; p.tw[t] = tr.a_off[t]; }
+    SMK_PROPAGATE(set_terms(p, tr, true));
     return launch_tc<256, false, 1, 8, kF16>(ta, tb, tcm, p, s);
   }
   const bool pair = tok_hw == 0 && use_cta_pair(M, Ktot);
@@ -787,8 +836,8 @@ static int gemm_tc_batched_impl(const void* A, int64_t lda, int64_t a_total_rows
   constexpr int BN = 256;
   const int mb = (rows_a + TC_BM - 1) / TC_BM, nb = (rows_w + BN - 1) / BN;
   TcGemmParams p{};
-  p.M = n_batch * mb * TC_BM; p.N = nb * BN; p.K = K; p.n_terms = tr.n;
-  for (int t = 0; t < tr.n; ++t) { p.ta[t] = tr.a_off[t]; p.tw[t] = tr.w_off[t]; }
+  p.M = n_batch * mb * TC_BM; p.N = nb * BN; p.K = K;
+  SMK_PROPAGATE(set_terms(p, tr, false));
   p.bias = nullptr; p.C = C; p.ldc = rows_w; p.epi = SMK_EPI_NONE; p.out_f32 = 1; p.rev = 0; p.trans = 0; p.credit_k = K;
   p.credit_flops = 2.0 * n_batch * rows_a * rows_w * K;
   p.mb_per_batch = mb; p.batch_a_rows = batch_a_rows; p.a_row0 = a_row0; p.batch_b_rows = batch_w_rows; p.b_row0 = w_row0;
@@ -821,6 +870,10 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
 int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                  int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s, int credit_k) {
   SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 2, "gemm_bf16: out_f32 must be 0 (bf16), 1 (fp32) or 2 (bf16x3 split)");
+  // K' = 3K of a [hi | hi | lo] x [hi | lo | hi] split pair (the caller names the mathematical K): the same three products as fused
+  // terms over the distinct halves — A columns {0, 2K}, W columns {0, K} — so that a k-block loads 4 operand tiles instead of 6
+  if (credit_k > 0 && K == 3 * credit_k && credit_k % TC_BK == 0)
+    return gemm_tc_impl<false>(A, lda, W, ldw, bias, C, ldc, M, N, credit_k, epi, out_f32, tok_hw, tok_pos, terms_legacy3(credit_k), credit_k, s);
   return gemm_tc_impl<false>(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, out_f32, tok_hw, tok_pos, GemmTerms{1, {0, 0, 0}, {0, 0, 0}}, credit_k, s);
 }
 

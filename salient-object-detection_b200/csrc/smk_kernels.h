@@ -45,6 +45,8 @@ struct GemmTerms { int n; int a_off[3]; int w_off[3]; };
 inline GemmTerms terms_plain() { return GemmTerms{1, {0, 0, 0}, {0, 0, 0}}; }
 inline GemmTerms terms_wsplit(int K) { return GemmTerms{2, {0, 0, 0}, {0, K, 0}}; }        // A_hi·(W_hi + W_lo)
 inline GemmTerms terms_full(int K) { return GemmTerms{3, {0, 0, K}, {0, K, 0}}; }          // hi·hi + hi·lo + lo·hi
+// the same three products on the round-1 layouts: activations [hi | hi | lo] (3K columns), weights [hi | lo | hi]
+inline GemmTerms terms_legacy3(int K) { return GemmTerms{3, {0, 0, 2 * K}, {0, K, 0}}; }
 int gemm_tc_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W, int64_t ldw,
                     int64_t w_total_rows, int batch_w_rows, int w_row0, int rows_w, float* C, int n_batch, int K, int f16, const GemmTerms& terms,
                     cudaStream_t s);

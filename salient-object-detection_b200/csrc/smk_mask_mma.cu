@@ -74,7 +74,7 @@ int mask_head_tc(const __nv_bfloat16* q3, int q_batch_rows, const __nv_bfloat16*
   SMK_REQUIRE(D % 64 == 0 && B <= 65535, "mask_head_tc: D=%d / B=%d unsupported", D, B);
   {
     TagScope tg(TAG_MASK_LOGITS);
-    const GemmTerms t3{3, {0, D, 2 * D}, {0, D, 0}};      // q_hi·t_hi + q_hi(dup)·t_lo + q_lo·t_hi
+    const GemmTerms t3{3, {0, 0, 2 * D}, {0, D, 0}};      // q_hi·t_hi + q_hi·t_lo + q_lo·t_hi (the duplicate hi columns are not read)
     SMK_PROPAGATE(gemm_tc_batched(q3, 3 * (int64_t)D, (int64_t)B * q_batch_rows, q_batch_rows, layer0 * nq, R, tok16, 2 * (int64_t)D, (int64_t)B * N, N, 1, ld,
                                   logits_lowres, B, D, 0, t3, s));
   }

@@ -597,7 +597,7 @@ def test_gemm_batched_mask_logits_match_fp64(B, Ra, a_row0, rows_a, hw):
     q3 = torch.cat([qh, qh, ql], dim=1).contiguous()
     t2 = torch.cat([th, tl], dim=1).contiguous()
     out = torch.full((B, rows_a, hw), 7.0, device=DEV)
-    ao, wo = (C.c_int32 * 3)(0, D, 2 * D), (C.c_int32 * 3)(0, D, 0)
+    ao, wo = (C.c_int32 * 3)(0, 0, 2 * D), (C.c_int32 * 3)(0, D, 0)
     check(lib().smk_gemm_batched(ptr(q3), 3 * D, B * Ra, Ra, a_row0, rows_a, ptr(t2), 2 * D, B * N, N, 1, hw, ptr(out), B, D, 0, 3, ao, wo, stream_ptr()),
           "smk_gemm_batched")
     torch.cuda.synchronize()
