@@ -216,6 +216,13 @@ int smk_attention_tc(const void* qkv, void* out, int B, int N, int heads, float 
 /* fp16 form of smk_attention_tc (fp16s mode): qkv / out fp16; out_mode 0 → out [B*N, ldo >= heads*64],
  * 3 → [hi | lo] split rows (ldo >= 2*heads*64): the A operand of a 3-term smk_gemm_split */
 int smk_attention_tc_f16(const void* qkv, void* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, void* stream);
+/* Multi-key-tile form for sequences longer than one tile (384 x 384: 577 tokens; ViT-S/8: 785; vision_transformer.py:110-130):
+ * 176-key tiles with an online rescale of the TMEM accumulator.  q / k / v: 16-bit matrices (bf16, or fp16 when f16 != 0), head h at
+ * columns [h*64, h*64+64) from each pointer; image b: queries at rows b*q_rows .. +Lq, keys / values at rows b*kv_rows + kv_row0 .. +Lk.
+ * Lk >= 176.  out [.., ldo]: out_mode 0 16-bit (operand type), 1 fp32, 2 [hi | hi | lo], 3 [hi | lo]. */
+int smk_attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t q_total_rows,
+                           int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq,
+                           int Lk, int heads, float scale, int f16, void* stream);
 /* general form: q [B*Lq, ldq], k / v [kv_total_rows, ld] bf16 (head h at columns [h*64, h*64+64) of each pointer); image b's
  * queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0; out [B*Lq, ldo]: out_f32 0 = bf16, 1 = fp32,
  * 2 = bf16x3 split ([hi | hi | lo], 3*heads*64 columns). */

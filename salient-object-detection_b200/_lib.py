@@ -61,6 +61,7 @@ SIGNATURES = {
     "smk_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "smk_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P]),
     "smk_attention_tc": (_I, [_P, _P, _I, _I, _I, _F, _P]),
+    "smk_attention_tc_multi": (_I, [_P, _L, _P, _L, _P, _L, _L, _L, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _I, _P]),
     "smk_attention_tc_general": (_I, [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "smk_attention_small": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, C.c_float, _P]),
     "smk_attention_fa": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, _L, _I, _I, _I, _I, _I, _F, _P]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libselfmask_b200.so")
-SOURCES = ["smk_model.cu", "smk_simt.cu", "smk_eval.cu", "smk_gemm_tc.cu", "smk_gemm_ln.cu", "smk_attn_tc.cu", "smk_attn_small.cu", "smk_attn_fa.cu", "smk_dec_attn.cu", "smk_xattn_tc.cu", "smk_mask_mma.cu", "smk_finalize.cu"]
+SOURCES = ["smk_model.cu", "smk_simt.cu", "smk_eval.cu", "smk_gemm_tc.cu", "smk_gemm_ln.cu", "smk_attn_tc.cu", "smk_attn_tc_multi.cu", "smk_attn_small.cu", "smk_attn_fa.cu", "smk_dec_attn.cu", "smk_xattn_tc.cu", "smk_mask_mma.cu", "smk_finalize.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 if os.environ.get("SMK_BUILD_TUNE") == "1":      # tuning build: GEMM wait-cycle trace + stage-isolation switches (scripts/gemm_trace.py)

@@ -60,6 +60,11 @@ int gemm_ln_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, cons
                const float* beta, __nv_bfloat16* Xn, int M, int N, int K, float eps, cudaStream_t s);
 int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, float scale, cudaStream_t s);
 int attention_tc_f16(const __half* qkv, __half* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, cudaStream_t s);
+// multi-key-tile tcgen05 attention for Lk >= 176 (577 / 785-token encoders; smk_attn_tc_multi.cu); 16-bit operands (fp16 when f16),
+// out_mode 0 16-bit, 1 fp32, 2 [hi | hi | lo], 3 [hi | lo]
+int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t q_total_rows,
+                       int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk,
+                       int heads, float scale, int f16, cudaStream_t s);
 // general form: q [B*Lq, ldq] / k / v [.., ld] bf16 matrices (head h at columns [h*64, h*64+64) from the given base pointer);
 // image b's queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0.  Lq <= 128, Lk <= 256.
 // out: [B*Lq, ldo], fp32 when out_f32 else bf16.

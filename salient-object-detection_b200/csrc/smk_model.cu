@@ -612,6 +612,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   const float* w = m->w;
   const __nv_bfloat16* wb = m->wb;
   const float scale = 0.125f;   // head_dim^-0.5, head_dim = 64
+  static const bool multi_attn = !(getenv("SMK_ATTN_MULTI") && atoi(getenv("SMK_ATTN_MULTI")) == 0);   // 0: mma.sync fallback for N > 256 (A/B runs)
   m->last_B = B;
 
   // fp32 validation mode: CUDA-core GEMM.  bf16x3 mode: the same call sites run on tcgen05 — A is split into
@@ -667,6 +668,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       {
         TagScope tg(TAG_ATTN);
         if (N <= 256) SMK_PROPAGATE(attention_tc_f16(QKV, AO, 2 * D, 3, B, N, c.heads, scale, s));
+        else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(QKV, 3 * D, QKV + D, 3 * D, QKV + 2 * D, 3 * D, M, M, N, N, 0, AO, 2 * D, 3, B, N, N, c.heads, scale, 1, s));
         else SMK_PROPAGATE(attention_fa((const __nv_bfloat16*)QKV, nullptr, 3 * D, (const __nv_bfloat16*)QKV + D, nullptr, 3 * D, (const __nv_bfloat16*)QKV + 2 * D, nullptr, 3 * D, N, N, 0,
                                         AO, 2 * D, 3, B, N, N, c.heads, scale, s, 1));
       }
@@ -707,7 +709,9 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         TagScope tg(TAG_ATTN);
         if (N <= 256) {
           SMK_PROPAGATE(attention_tc(QKV, AO, B, N, c.heads, scale, s));
-        } else {   // longer sequences (384x384 → 577 tokens, ViT-S/8 → 785): online-softmax mma.sync kernel
+        } else if (multi_attn) {   // longer sequences (384x384 → 577 tokens, ViT-S/8 → 785): multi-key-tile tcgen05 kernel
+          SMK_PROPAGATE(attention_tc_multi(QKV, 3 * D, QKV + D, 3 * D, QKV + 2 * D, 3 * D, M, M, N, N, 0, AO, D, 0, B, N, N, c.heads, scale, 0, s));
+        } else {   // SMK_ATTN_MULTI=0: online-softmax mma.sync kernel
           SMK_PROPAGATE(attention_fa(QKV, nullptr, 3 * D, QKV + D, nullptr, 3 * D, QKV + 2 * D, nullptr, 3 * D, N, N, 0, AO, D, 0, B, N, N, c.heads,
                                      scale, s));
         }

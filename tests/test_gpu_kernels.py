@@ -539,6 +539,38 @@ def test_attention_tcgen05_fp16_matches_torch(B, N, out_mode):
         assert (out[:, D:].float().abs() <= out[:, :D].float().abs() * 2.0 ** -10 + 1e-7).all()     # lo is the rounding residue of hi
 
 
+@pytest.mark.parametrize("B,N,f16,out_mode", [(3, 577, 1, 3), (2, 785, 1, 3), (3, 577, 0, 0), (2, 785, 0, 0), (40, 577, 1, 3), (1, 176, 1, 0),
+                                              (2, 177, 0, 1), (1, 352, 1, 3), (2, 600, 0, 2), (30, 785, 0, 0), (1, 1100, 1, 1)])
+def test_attention_tcgen05_multi_tile_matches_torch(B, N, f16, out_mode):
+    """Multi-key-tile tcgen05 attention (smk_attn_tc_multi.cu): 577 / 785-token encoders, online rescale of the TMEM accumulator across
+    176-key tiles, shifted last tile (N = 177: 175 of its 176 columns are masked duplicates), exact multiples (176, 352), every output
+    mode, both operand types; larger scores (x2) so that the running maximum really moves between tiles."""
+    torch.manual_seed(43)
+    H, dh = 6, 64
+    D = H * dh
+    dt = torch.float16 if f16 else torch.bfloat16
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 2.0).to(dt)
+    parts = {0: 1, 1: 1, 2: 3, 3: 2}[out_mode]
+    ldo = parts * D
+    out = torch.full((B * N, ldo), 7.0, device=DEV, dtype=torch.float32 if out_mode == 1 else dt)
+    check(lib().smk_attention_tc_multi(ptr(qkv), 3 * D, ptr(qkv[:, D:]), 3 * D, ptr(qkv[:, 2 * D:]), 3 * D, B * N, B * N, N, N, 0, ptr(out), ldo,
+                                       out_mode, B, N, N, H, 0.125, f16, stream_ptr()), "smk_attention_tc_multi")
+    torch.cuda.synchronize()
+    q, k, v = [t.double().view(B, N, H, dh).transpose(1, 2) for t in qkv.view(B, N, 3 * D).split(D, dim=-1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, D)
+    if out_mode == 2:
+        assert torch.equal(out[:, :D], out[:, D:2 * D])
+        got = out[:, :D].double() + out[:, 2 * D:].double()
+    elif out_mode == 3:
+        got = out[:, :D].double() + out[:, D:].double()
+    else:
+        got = out.double()
+    err = (got - ref).abs().max().item()
+    tol = {(1, 0): 8e-3, (1, 1): 5e-3, (1, 3): 5e-3, (0, 0): 0.06, (0, 1): 0.04, (0, 2): 0.04}[(f16, out_mode)]
+    assert err <= tol, err
+    assert (got - ref).abs().mean().item() <= (4e-4 if f16 else 3e-3)
+
+
 @pytest.mark.parametrize("nq,B", [(20, 37), (10, 5), (32, 3), (1, 2)])
 def test_decoder_self_attention_fp32_matches_torch(nq, B):
     torch.manual_seed(42)
