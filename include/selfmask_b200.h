@@ -195,6 +195,16 @@ int smk_gemm_bf16(const void* A, int64_t lda, const void* W, const float* bias, 
  * out_kind: 0 16-bit (same type as the operands), 1 fp32, 2 split [hi | hi | lo] (3N columns), 3 split [hi | lo] (2N columns). */
 int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
                    int epilogue, int out_kind, int f16, int n_terms, const int32_t* a_off, const int32_t* w_off, void* stream);
+/* fp16 product with fp8 correction terms (the fp16s mode's patch-embed / proj / fc1 / fc2; vision_transformer.py:88-94,131,184-188):
+ * C = A_hi·W_hi^T + (e4m3(A_hi)·e4m3(W_lo·2^15)^T + e4m3(A_lo·2^11)·e4m3(W_hi·2^4)^T)·2^-15 + bias — the accuracy of the 3-term fp16 split
+ * with the two correction products at the fp8 tensor-core rate.  A [M, lda >= 2K], W [N, ldw >= 2K]: rows as written by smk_split_q8
+ * ([hi fp16 (K) | 2K bytes of e4m3 operands]).  out_kind as smk_gemm_split, plus 4 = [hi fp16 | e4m3 operands] (2N fp16 columns: the A
+ * operand of the next smk_gemm_q8).  K % 64 == 0, N % 128 == 0. */
+int smk_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                int epilogue, int out_kind, void* stream);
+/* x [rows, ldx] fp32 → out [rows, 2K fp16 columns]: [hi fp16 (K) | per 32 columns 32 bytes "first" + 32 bytes "second" of e4m3];
+ * activations (is_weight == 0): first = e4m3(hi), second = e4m3(lo·2^11); weights: first = e4m3(lo·2^15), second = e4m3(hi·2^4). */
+int smk_split_q8(const float* x, int64_t ldx, void* out, int64_t rows, int K, int is_weight, void* stream);
 /* Batched form: C_b [rows_a, rows_w] fp32 = sum over terms of A_b · W_b^T for b < n_batch, where A_b = rows
  * [b*batch_a_rows + a_row0, +rows_a) of A [a_total_rows, lda] and W_b = rows [b*batch_w_rows + w_row0, +rows_w) of W [w_total_rows, ldw];
  * C [n_batch, rows_a, rows_w] contiguous, rows_w % 4 == 0.  The mask-logit contraction (maskformer.py:223 at patch resolution):

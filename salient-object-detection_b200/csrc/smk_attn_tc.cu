@@ -346,6 +346,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               st_shared_v4(srow + 4096 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
                            __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
             }
+          } else if (kF16 && p.out_f32 == 4) {
+            // [hi | e4m3 correction operands] (A operand of a terms_q8 GEMM): the second 128-byte box holds, per 32 columns, e4m3(hi) (32 B)
+            // and e4m3(lo·2^11) (32 B)
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              uint2 h[4];
+              uint32_t f8[4], s8[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c0 = 16 * j2 + 4 * e;
+                auto g = [&](int c) { return c < 32 ? f(oa[c < 32 ? c : 0]) : f(ob[c >= 32 ? c - 32 : 0]); };
+                split_q8x4<false>(g(c0), g(c0 + 1), g(c0 + 2), g(c0 + 3), h[e], f8[e], s8[e]);
+              }
+              st_shared_v4(srow + (((uint32_t)(2 * j2) << 4) ^ x7s), h[0].x, h[0].y, h[1].x, h[1].y);
+              st_shared_v4(srow + (((uint32_t)(2 * j2 + 1) << 4) ^ x7s), h[2].x, h[2].y, h[3].x, h[3].y);
+              const uint32_t base = (uint32_t)((j2 >> 1) * 4 + (j2 & 1));
+              st_shared_v4(srow + 4096 + ((base << 4) ^ x7s), f8[0], f8[1], f8[2], f8[3]);
+              st_shared_v4(srow + 4096 + (((base + 2) << 4) ^ x7s), s8[0], s8[1], s8[2], s8[3]);
+            }
           } else if (p.out_f32 >= 2) {
             // split output: hi and lo 64-column boxes (32 rows x 128 B each); mode 2: hi is stored twice ([hi | hi | lo]), mode 3: [hi | lo]
 #pragma unroll
@@ -381,7 +400,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               tma_store_3d(&tmO, stg_ptr, Dm + h * AT_DH, row0, b);
               tma_store_3d(&tmO, stg_ptr + 4096, 2 * Dm + h * AT_DH, row0, b);
             }
-            if (p.out_f32 == 3) tma_store_3d(&tmO, stg_ptr + 4096, p.heads * AT_DH + h * AT_DH, row0, b);
+            if (p.out_f32 >= 3) tma_store_3d(&tmO, stg_ptr + 4096, p.heads * AT_DH + h * AT_DH, row0, b);
             bulk_commit();
           }
         }
@@ -402,7 +421,7 @@ static int attention_tc_launch(const void* q, int64_t ldq, const void* k, int64_
   const int D = heads * AT_DH;
   SMK_REQUIRE(Lk >= 1 && Lk <= AT_MAXK && Lq >= 1 && Lq <= 2 * AT_BM, "attention_tc: Lq=%d / Lk=%d not supported (1..256)", Lq, Lk);
   SMK_REQUIRE(B >= 1 && heads >= 1 && (int64_t)B * heads < (1 << 30), "attention_tc: bad batch/heads");
-  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 3 && (out_f32 != 2 || ldo >= 3 * (int64_t)D) && (out_f32 != 3 || ldo >= 2 * (int64_t)D),
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 4 && (out_f32 != 4 || kF16) && (out_f32 != 2 || ldo >= 3 * (int64_t)D) && (out_f32 < 3 || ldo >= 2 * (int64_t)D),
               "attention_tc: bad output mode / ldo");
   const int esz = out_f32 == 1 ? 4 : 2;
   SMK_REQUIRE((ldo * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc: output must be 16-byte aligned");
@@ -414,7 +433,7 @@ static int attention_tc_launch(const void* q, int64_t ldq, const void* k, int64_
   SMK_PROPAGATE(make_tmap_bf16_2d(&tv, v, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldv * 2, AT_DH, (uint32_t)nk_pad));
   {
     // {column, query row within the image, image}: rows >= Lq of a 32-row output box are clipped by the TMA unit
-    const int parts = out_f32 == 2 ? 3 : (out_f32 == 3 ? 2 : 1);
+    const int parts = out_f32 == 2 ? 3 : (out_f32 >= 3 ? 2 : 1);
     const uint64_t dims[3] = {(uint64_t)(parts * D), (uint64_t)Lq, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)ldo * esz, (uint64_t)Lq * ldo * esz};
     const uint32_t box[3] = {out_f32 == 1 ? 32u : 64u, 32u, 1u};
@@ -453,7 +472,7 @@ int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int
 // fp16 encoder form — qkv: [B*N, 3*D] fp16; out: [B*N, ldo] fp16, out_mode 0 plain (ldo >= D) or 3 = [hi | lo] split (ldo >= 2D)
 int attention_tc_f16(const __half* qkv, __half* out, int64_t ldo, int out_mode, int B, int N, int heads, float scale, cudaStream_t s) {
   const int D = heads * AT_DH;
-  SMK_REQUIRE(out_mode == 0 || out_mode == 3, "attention_tc_f16: output mode 0 (fp16) or 3 ([hi | lo] fp16)");
+  SMK_REQUIRE(out_mode == 0 || out_mode == 3 || out_mode == 4, "attention_tc_f16: output mode 0 (fp16), 3 ([hi | lo] fp16) or 4 ([hi | q8])");
   return attention_tc_launch<true>(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, (int64_t)B * N, N, 0, out, ldo, out_mode, B, N, N, heads, scale, s);
 }
 

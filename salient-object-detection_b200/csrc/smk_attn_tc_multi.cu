@@ -327,6 +327,25 @@ attn_tc_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               st_shared_v4(srow + 4096 + (((uint32_t)j << 4) ^ x7s), __float_as_uint(f(ob[4 * j])), __float_as_uint(f(ob[4 * j + 1])),
                            __float_as_uint(f(ob[4 * j + 2])), __float_as_uint(f(ob[4 * j + 3])));
             }
+          } else if (kF16 && p.out_mode == 4) {
+            // [hi | e4m3 correction operands] (A operand of a terms_q8 GEMM): the second 128-byte box holds, per 32 columns, e4m3(hi) (32 B)
+            // and e4m3(lo·2^11) (32 B)
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              uint2 h[4];
+              uint32_t f8[4], s8[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c0 = 16 * j2 + 4 * e;
+                auto g = [&](int c) { return c < 32 ? f(oa[c < 32 ? c : 0]) : f(ob[c >= 32 ? c - 32 : 0]); };
+                split_q8x4<false>(g(c0), g(c0 + 1), g(c0 + 2), g(c0 + 3), h[e], f8[e], s8[e]);
+              }
+              st_shared_v4(srow + (((uint32_t)(2 * j2) << 4) ^ x7s), h[0].x, h[0].y, h[1].x, h[1].y);
+              st_shared_v4(srow + (((uint32_t)(2 * j2 + 1) << 4) ^ x7s), h[2].x, h[2].y, h[3].x, h[3].y);
+              const uint32_t base = (uint32_t)((j2 >> 1) * 4 + (j2 & 1));
+              st_shared_v4(srow + 4096 + ((base << 4) ^ x7s), f8[0], f8[1], f8[2], f8[3]);
+              st_shared_v4(srow + 4096 + (((base + 2) << 4) ^ x7s), s8[0], s8[1], s8[2], s8[3]);
+            }
           } else if (p.out_mode >= 2) {
             // split output: hi and lo 64-column boxes (32 rows x 128 B each); mode 2: hi is stored twice ([hi | hi | lo]), mode 3: [hi | lo]
 #pragma unroll
@@ -362,7 +381,7 @@ attn_tc_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tma_store_3d(&tmO, stg_ptr, Dm + h * AM_DH, row0, b);
               tma_store_3d(&tmO, stg_ptr + 4096, 2 * Dm + h * AM_DH, row0, b);
             }
-            if (p.out_mode == 3) tma_store_3d(&tmO, stg_ptr + 4096, p.heads * AM_DH + h * AM_DH, row0, b);
+            if (p.out_mode >= 3) tma_store_3d(&tmO, stg_ptr + 4096, p.heads * AM_DH + h * AM_DH, row0, b);
             bulk_commit();
           }
         }
@@ -385,7 +404,7 @@ int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int heads, float scale, int f16, cudaStream_t s) {
   const int D = heads * AM_DH;
   SMK_REQUIRE(Lk >= AM_KT && Lq >= 1 && B >= 1 && heads >= 1, "attention_tc_multi: Lq=%d / Lk=%d not supported (Lk >= 176)", Lq, Lk);
-  SMK_REQUIRE(out_mode >= 0 && out_mode <= 3 && (out_mode != 2 || ldo >= 3 * (int64_t)D) && (out_mode != 3 || ldo >= 2 * (int64_t)D),
+  SMK_REQUIRE(out_mode >= 0 && out_mode <= 4 && (out_mode != 4 || f16) && (out_mode != 2 || ldo >= 3 * (int64_t)D) && (out_mode < 3 || ldo >= 2 * (int64_t)D),
               "attention_tc_multi: bad output mode / ldo");
   const int esz = out_mode == 1 ? 4 : 2;
   SMK_REQUIRE((ldo * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0, "attention_tc_multi: output must be 16-byte aligned");
@@ -396,7 +415,7 @@ int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, c
   SMK_PROPAGATE(make_tmap_bf16_2d(&tk, k, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldk * 2, AM_DH, AM_KT));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tv, v, (uint64_t)D, (uint64_t)kv_total_rows, (uint64_t)ldv * 2, AM_DH, AM_KT));
   {
-    const int parts = out_mode == 2 ? 3 : (out_mode == 3 ? 2 : 1);
+    const int parts = out_mode == 2 ? 3 : (out_mode >= 3 ? 2 : 1);
     const uint64_t dims[3] = {(uint64_t)(parts * D), (uint64_t)Lq, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)ldo * esz, (uint64_t)q_rows * ldo * esz};
     const uint32_t box[3] = {out_mode == 1 ? 32u : 64u, 32u, 1u};

@@ -153,6 +153,34 @@ __device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32
   lo = Pack16<T>::pack(a - hf.x, b - hf.y);
 }
 
+// ---- fp8 correction operands of the fp16s GEMMs (smk_gemm_tc.cu TcGemmParams::q8) -------------------------------------------
+// A split row is [hi fp16 (K) | 2K bytes of e4m3]: per 32 operand columns, 32 bytes "first" then 32 bytes "second" —
+// activations: first = e4m3(hi), second = e4m3(lo·2^11); weights: first = e4m3(lo·2^15), second = e4m3(hi·2^4) — so that the fp8
+// contraction over the 64 bytes is (hi·lo + lo·hi)·2^15 for those 32 columns.  Conversions saturate (graceful: the terms are
+// corrections of relative size 2^-11).
+constexpr float kQ8ActLo = 2048.f, kQ8WLo = 32768.f, kQ8WHi = 16.f;
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {     // memory order a, b, c, d
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ int q8_byte_off(int col) { return ((col >> 5) << 6) + (col & 31); }   // of `first`; `second` is 32 bytes further
+// four consecutive values → fp16 hi pairs + the two e4m3 words
+template <bool kWeight>
+__device__ __forceinline__ void split_q8x4(float a, float b, float c, float d, uint2& hi16, uint32_t& first8, uint32_t& second8) {
+  hi16.x = Pack16<__half>::pack(a, b);
+  hi16.y = Pack16<__half>::pack(c, d);
+  const float2 h0 = Pack16<__half>::unpack(hi16.x), h1 = Pack16<__half>::unpack(hi16.y);
+  if constexpr (kWeight) {
+    first8 = e4m3x4((a - h0.x) * kQ8WLo, (b - h0.y) * kQ8WLo, (c - h1.x) * kQ8WLo, (d - h1.y) * kQ8WLo);
+    second8 = e4m3x4(h0.x * kQ8WHi, h0.y * kQ8WHi, h1.x * kQ8WHi, h1.y * kQ8WHi);
+  } else {
+    first8 = e4m3x4(h0.x, h0.y, h1.x, h1.y);
+    second8 = e4m3x4((a - h0.x) * kQ8ActLo, (b - h0.y) * kQ8ActLo, (c - h1.x) * kQ8ActLo, (d - h1.y) * kQ8ActLo);
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 

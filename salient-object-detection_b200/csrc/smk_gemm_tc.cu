@@ -114,12 +114,18 @@ struct TcGemmParams {
   int n_a, n_w, a_col[2], w_col[2], n_pairs, pair_a[TC_MAX_TERMS], pair_w[TC_MAX_TERMS];
   int n_stages;   // ring depth at this stage size (<= the compile-time maximum)
   int seq;        // 1: term-by-term k loop instead (a stage = one A tile + one W tile): only when a fused stage does not fit twice
+  // fp8 correction terms (fp16 operands only): term 0's tiles hold e4m3 values — per 32 operand columns 32 bytes e4m3(hi) | 32 bytes
+  // e4m3(lo·2^11) on the activation side, e4m3(lo·2^15) | e4m3(hi·2^4) on the weight side, so that one fp8 contraction over the
+  // box yields (hi·lo + lo·hi)·2^15 at TWICE the 16-bit tensor rate — and are issued first; the first MMA of term 1 (fp16 hi·hi)
+  // then takes the accumulator in with scale-input-d = 15.  Always term by term (seq).
+  int q8;
   const float* bias;
   void* C;
   int64_t ldc;
   int epi;        // SMK_EPI_* flags
   int out_f32;    // 0 → 16-bit output (bf16 / fp16 per kF16), 1 → fp32 output, 2 → 3-part split output [hi | hi | lo] (3N columns),
-                  // 3 → 2-part split output [hi | lo] (2N columns)
+                  // 3 → 2-part split output [hi | lo] (2N columns), 4 → [hi fp16 | e4m3 correction operands] (2N fp16 columns: the A
+                  // operand of a terms_q8 GEMM)
   // token assembly for patch-embed (kDirect): output row = m + m / tok_hw + 1, value += tok_pos[(1 + m % tok_hw) * N + n]
   int tok_hw;
   const float* tok_pos;
@@ -290,6 +296,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int pr = 0; pr < n_pr; ++pr) {
             const uint64_t a_desc = smem_desc_k_sw128(sa + (uint32_t)((p.seq ? 0 : sel3(pr, pa0, pa1, pa2)) * Cfg::kABytes));
             const uint64_t b_desc = smem_desc_k_sw128(sb + (uint32_t)((p.seq ? 0 : sel3(pr, pw0, pw1, pw2)) * Cfg::kBBytes));
+            if (kF16 && p.q8 && kb <= kpt) {
+              if (kb < kpt) {           // fp8 tiles: four K = 32 products per 128-byte row
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if constexpr (kCtas == 2) umma_f8_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                  else umma_f8_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+              } else {                  // first fp16 k-block: D = hi·hi + D·2^-15
+                if constexpr (kCtas == 2) umma_16_ss_cg2_sd15(d_tmem, a_desc, b_desc, idesc);
+                else umma_16_ss_sd15(d_tmem, a_desc, b_desc, idesc);
+#pragma unroll
+                for (int k = 1; k < TC_BK / 16; ++k) {
+                  if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1);
+                  else umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1);
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {  // +32 B per 16-element K step → +2 in the (addr >> 4) field
               if constexpr (kCtas == 2) umma_bf16_ss_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | pr | k) != 0);
@@ -454,6 +478,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             const uint32_t srow = stg_u32 + lane * 64;
+            if (kF16 && p.out_f32 == 4) {
+              // [hi | e4m3 correction operands]: the second 64-byte box holds e4m3(hi) (32 B) and e4m3(lo·2^11) (32 B) of the 32 columns
+              uint32_t f8[8], s8[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint2 ha, hb;
+                split_q8x4<false>(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], ha, f8[2 * j], s8[2 * j]);
+                split_q8x4<false>(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], hb, f8[2 * j + 1], s8[2 * j + 1]);
+                st_shared_v4(srow + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), ha.x, ha.y, hb.x, hb.y);
+              }
+              const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+              st_shared_v4(srow + 2048 + ((0u ^ sw) << 4), f8[0], f8[1], f8[2], f8[3]);
+              st_shared_v4(srow + 2048 + ((1u ^ sw) << 4), f8[4], f8[5], f8[6], f8[7]);
+              st_shared_v4(srow + 2048 + ((2u ^ sw) << 4), s8[0], s8[1], s8[2], s8[3]);
+              st_shared_v4(srow + 2048 + ((3u ^ sw) << 4), s8[4], s8[5], s8[6], s8[7]);
+            } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t h[4], l[4];
@@ -462,6 +502,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint32_t off = (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
               st_shared_v4(srow + off, h[0], h[1], h[2], h[3]);
               st_shared_v4(srow + 2048 + off, l[0], l[1], l[2], l[3]);
+            }
             }
             fence_proxy_async();
             __syncwarp();
@@ -632,7 +673,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     const int fused_stages = (Cfg::kStages * Cfg::kStageBytes) / (p.n_a * Cfg::kABytes + p.n_w * Cfg::kBBytes);
     // measured on B200 (same box, fp16s step, profiles/r02_gemm_terms.md): fused stages 8.78 ms per step against 10.1 ms term by term
     const bool fuse = force >= 0 ? (force != 0 && fused_stages >= 2) : fused_stages >= 2;
-    p.seq = (p.n_pairs > 1 && !fuse) ? 1 : 0;
+    p.seq = (p.n_pairs > 1 && (!fuse || p.q8)) ? 1 : 0;
     p.n_stages = p.seq || p.n_pairs == 1 ? Cfg::kStages : fused_stages;
   }
   const int tiles = (p.N / BN) * ((p.M + TC_BM * kCtas - 1) / (TC_BM * kCtas));
@@ -662,7 +703,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   {
     // credited work = ALGORITHMIC FLOPs of the contraction (one term; p.credit_k is the mathematical reduction length), whatever
     // number of split terms the tensor core is issued
-    ProfScope prof(PROF_GEMM_TC, p.credit_flops > 0 ? p.credit_flops : 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * p.n_terms);
+    ProfScope prof(PROF_GEMM_TC, p.credit_flops > 0 ? p.credit_flops : 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * (p.q8 ? 3 : p.n_terms));
     SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
@@ -741,7 +782,7 @@ static bool use_epi16(const TcGemmParams& p) {
     const char* e = getenv("SMK_GEMM_EPI16");
     mode = e ? atoi(e) : -1;
   }
-  if (p.out_f32 != 0) return false;
+  if (p.out_f32 != 0) return false;   // (split outputs with 16 epilogue warps on CTA pairs: measured slower, fc1 148 vs 141 us)
   return mode >= 0 ? mode != 0 : p.M >= 16384;
 }
 
@@ -768,10 +809,10 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
     w_cols = std::max<int64_t>(w_cols, tr.w_off[t] + K);
   }
   SMK_REQUIRE(lda >= a_cols && ldw >= w_cols, "gemm_tc: operand rows shorter than the terms reach (lda=%lld ldw=%lld)", (long long)lda, (long long)ldw);
-  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 3, "gemm_tc: out_f32 must be 0 (16-bit), 1 (fp32), 2 ([hi|hi|lo] split) or 3 ([hi|lo] split)");
+  SMK_REQUIRE(out_f32 >= 0 && out_f32 <= 4 && (out_f32 != 4 || kF16), "gemm_tc: out_f32 must be 0 (16-bit), 1 (fp32), 2 ([hi|hi|lo] split), 3 ([hi|lo] split) or 4 ([hi|q8], fp16)");
   SMK_REQUIRE(!(epi & SMK_EPI_RESIDUAL) || out_f32 == 1, "gemm_tc: residual epilogue needs fp32 output");
   SMK_REQUIRE(out_f32 != 2 || ldc >= 3 * (int64_t)N, "gemm_tc: split output needs ldc >= 3N");
-  SMK_REQUIRE(out_f32 != 3 || ldc >= 2 * (int64_t)N, "gemm_tc: split output needs ldc >= 2N");
+  SMK_REQUIRE(out_f32 < 3 || ldc >= 2 * (int64_t)N, "gemm_tc: split output needs ldc >= 2N");
   SMK_REQUIRE(ldc % 8 == 0 && ((uintptr_t)C % 16) == 0, "gemm_tc: C must be 16-byte aligned with ldc %% 8 == 0");
   SMK_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "gemm_tc: bias must be 16-byte aligned");
   SMK_REQUIRE(tok_hw == 0 || (out_f32 == 1 && !(epi & SMK_EPI_RESIDUAL) && tok_pos), "gemm_tc: token assembly needs a plain fp32 output");
@@ -781,12 +822,15 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
     const char* e = getenv("SMK_GEMM_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  const int Ktot = K * tr.n;
+  const int Ktot = K * (tr.q8 ? 3 : tr.n);   // tile-form heuristics go by the operand bytes streamed per output tile: a q8 row carries the same 4K bytes as [hi | lo]
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K;
   SMK_PROPAGATE(set_terms(p, tr, false));
   p.bias = bias; p.C = C; p.ldc = ldc; p.epi = epi; p.out_f32 = out_f32; p.tok_hw = tok_hw; p.tok_pos = tok_pos; p.dbg = dbg;
   p.rev = traverse_dir(); p.trans = 0; p.credit_k = credit_k > 0 ? credit_k : K;
+  p.q8 = tr.q8;
+  SMK_REQUIRE(!tr.q8 || (kF16 && tr.n == 2 && tr.a_off[0] == K && tr.w_off[0] == K && tr.a_off[1] == 0 && tr.w_off[1] == 0),
+              "gemm_tc: fp8 correction terms need fp16 operands and the terms_q8 layout");
   if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, Ktot)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
     // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
     CUtensorMap ta, tb, tcm;
@@ -797,7 +841,8 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
     SMK_PROPAGATE(set_terms(p, tr, true));
     return launch_tc<256, false, 1, 8, kF16>(ta, tb, tcm, p, s);
   }
-  const bool pair = tok_hw == 0 && use_cta_pair(M, Ktot);
+  // q8: single CTAs (fc1 133 us against 141 us as CTA pairs, scripts/gemm_q8_bench.py) — the pair rule goes by the MMA time per k-block
+  const bool pair = tok_hw == 0 && use_cta_pair(M, K * tr.n);
   const int kc = pair ? 2 : 1;
   int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
   if (tok_hw > 0 && !getenv("SMK_GEMM_BN")) BN = 128;   // direct-store epilogue (patch embed): per-thread row stores favour narrow tiles (78 vs 82 us)
@@ -810,7 +855,7 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (16-bit, 64-byte swizzle) per row
   const int esz = out_f32 == 1 ? 4 : 2;
-  const int parts = out_f32 == 2 ? 3 : (out_f32 == 3 ? 2 : 1);
+  const int parts = out_f32 == 2 ? 3 : (out_f32 >= 3 ? 2 : 1);
   SMK_PROPAGATE(make_tmap_2d(&tcm, esz, C, (uint64_t)(parts * N), (uint64_t)M, (uint64_t)ldc * esz, 32, 32, out_f32 == 1 ? 128 : 64));
   if (pair) return launch_bn<false, 2, kF16>(BN, ta, tb, tcm, p, s);
   return launch_bn<false, 1, kF16>(BN, ta, tb, tcm, p, s);
@@ -908,4 +953,10 @@ extern "C" int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t
   smk::GemmTerms t{n_terms, {0, 0, 0}, {0, 0, 0}};
   for (int i = 0; i < n_terms; ++i) { t.a_off[i] = a_off[i]; t.w_off[i] = w_off[i]; }
   return smk::gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, epilogue, out_kind, 0, nullptr, f16, t, 0, (cudaStream_t)stream);
+}
+
+extern "C" int smk_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                           int epilogue, int out_kind, void* stream) {
+  SMK_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0, "smk_gemm_q8: bad arguments");
+  return smk::gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, epilogue, out_kind, 0, nullptr, 1, smk::terms_q8(K), 0, (cudaStream_t)stream);
 }

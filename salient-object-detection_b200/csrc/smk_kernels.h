@@ -23,7 +23,7 @@ int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv
 int layernorm_bf16(const float* x, const float* res, const float* gamma, const float* beta, __nv_bfloat16* y, float* y32,
                    float* sum_out, int64_t rows, int D, float eps, cudaStream_t s, __nv_bfloat16* y_lo = nullptr, int64_t ldy = 0);
 int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
-                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt = 0);
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt = 0, int q8 = 0);
 // y2s_period / y2s_stride: row r of the split final-norm output goes to row (r / period)·stride + r % period of y2s (image-major
 // [B][L][nq] layout of the mask / objectness head operand: period = nq, stride = L·nq, y2s pre-offset by layer·nq rows); 0 = row r
 int dec_layernorm(float* x, const float* res, const float* gamma, const float* beta, float eps, const float* pos, int period,
@@ -41,10 +41,12 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
                  int M, int N, int K, int epi, int out_f32, int tok_hw, const float* tok_pos, cudaStream_t s, int credit_k = 0);
 // split-operand tcgen05 GEMM (smk_gemm_tc.cu): C = Σ_t A[:, a_off[t] : +K] · W[:, w_off[t] : +K]^T, 16-bit operands (fp16 when f16),
 // out_f32: 0 16-bit, 1 fp32, 2 [hi | hi | lo] split, 3 [hi | lo] split
-struct GemmTerms { int n; int a_off[3]; int w_off[3]; };
+struct GemmTerms { int n; int a_off[3]; int w_off[3]; int q8 = 0; };
 inline GemmTerms terms_plain() { return GemmTerms{1, {0, 0, 0}, {0, 0, 0}}; }
 inline GemmTerms terms_wsplit(int K) { return GemmTerms{2, {0, 0, 0}, {0, K, 0}}; }        // A_hi·(W_hi + W_lo)
 inline GemmTerms terms_full(int K) { return GemmTerms{3, {0, 0, K}, {0, K, 0}}; }          // hi·hi + hi·lo + lo·hi
+// fp16 hi·hi + the two correction products on e4m3 tiles stored in place of the fp16 `lo` half (TcGemmParams::q8, split_q8 below)
+inline GemmTerms terms_q8(int K) { return GemmTerms{2, {K, 0, 0}, {K, 0, 0}, 1}; }
 // the same three products on the round-1 layouts: activations [hi | hi | lo] (3K columns), weights [hi | lo | hi]
 inline GemmTerms terms_legacy3(int K) { return GemmTerms{3, {0, 0, 2 * K}, {0, K, 0}}; }
 int gemm_tc_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch_a_rows, int a_row0, int rows_a, const void* W, int64_t ldw,
@@ -86,8 +88,10 @@ template <typename TIn, typename T>
 int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std /* host, 6 floats or null */,
            cudaStream_t s);
 template <typename TIn>
-int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s);
+int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s, int q8 = 0);
 int split2_f16(const float* w, int64_t ldw, __half* out, int64_t rows, int K, cudaStream_t s);
+// row → [hi fp16 (K) | e4m3 correction operands (2K bytes)] for the fp8-corrected GEMMs (terms_q8); is_weight picks the weight-side scales
+int split_q8(const float* x, int64_t ldx, __half* out, int64_t rows, int K, int is_weight, cudaStream_t s);
 int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, __nv_bfloat16* out3, int B, int nq, int heads, float scale,
                        cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,

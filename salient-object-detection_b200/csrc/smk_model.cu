@@ -465,28 +465,33 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
     if ((st = split3_weight(m->kvw32, m->kvw3, (int64_t)cfg->dec_layers * 2 * D, (int)D, s)) != SMK_OK) return fail(st);
   }
   if (mode == SMK_MODE_FP16S) {
-    // [N,K] fp32 at offset o → [N,2K] fp16 ([hi | lo]) at offset 2·o, for every encoder matrix and the memory K/V projection
-    auto sp = [&](int64_t off, int64_t rows, int64_t K) { return split2_f16(weights + off, K, m->wh + 2 * off, rows, (int)K, s); };
+    // terms per contraction: the schedule scripts/precision_emulation.py derives from the 2e-2 logit budget.  Patch embed, proj, fc1,
+    // fc2: the full split hi·hi + hi·lo + lo·hi with the two correction products on e4m3 operands at the fp8 tensor rate (4 = q8,
+    // smk_gemm_tc.cu TcGemmParams::q8; 3 = all three products in fp16); qkv and the memory K/V projection: weight split only (2);
+    // attention: single-pass fp16.  SMK_FP16S_TERMS="qkv=2,fc1=3,..." overrides single entries (tuning / error-budget experiments).
+    m->t_pe = 4; m->t_qkv = 2; m->t_proj = 4; m->t_fc1 = 4; m->t_fc2 = 4; m->t_kv = 2;
+    if (const char* e = getenv("SMK_FP16S_TERMS")) {
+      struct { const char* k; int* v; int hi; } keys[] = {{"pe=", &m->t_pe, 4}, {"qkv=", &m->t_qkv, 3}, {"proj=", &m->t_proj, 4}, {"fc1=", &m->t_fc1, 4},
+                                                          {"fc2=", &m->t_fc2, 4}, {"kv=", &m->t_kv, 3}};
+      for (auto& kv : keys) {
+        const char* q = strstr(e, kv.k);
+        if (q && (q == e || q[-1] == ',')) { const int n = atoi(q + strlen(kv.k)); if (n >= 1 && n <= kv.hi) *kv.v = n; }
+      }
+    }
+    // the mma.sync fallback attention (SMK_ATTN_MULTI=0 at more than 256 tokens) writes [hi | lo] only
+    if (m->N > 256 && getenv("SMK_ATTN_MULTI") && atoi(getenv("SMK_ATTN_MULTI")) == 0 && m->t_proj == 4) m->t_proj = 3;
+    // [N,K] fp32 at offset o → [N,2K] fp16 columns at offset 2·o: [hi | lo] fp16, or [hi | e4m3 correction operands] for a q8 contraction
+    auto sp = [&](int64_t off, int64_t rows, int64_t K, int t = 0) {
+      return t == 4 ? split_q8(weights + off, K, m->wh + 2 * off, rows, (int)K, 1, s) : split2_f16(weights + off, K, m->wh + 2 * off, rows, (int)K, s);
+    };
     const int64_t F = cfg->mlp_dim, Kpe = 3 * cfg->patch * cfg->patch;
-    if ((st = sp(m->o_pew, D, Kpe)) != SMK_OK) return fail(st);
+    if ((st = sp(m->o_pew, D, Kpe, m->t_pe)) != SMK_OK) return fail(st);
     for (const BlockW& b : m->blk) {
-      if ((st = sp(b.qkvw, 3 * D, D)) != SMK_OK || (st = sp(b.pw, D, D)) != SMK_OK || (st = sp(b.f1w, F, D)) != SMK_OK ||
-          (st = sp(b.f2w, D, F)) != SMK_OK)
+      if ((st = sp(b.qkvw, 3 * D, D)) != SMK_OK || (st = sp(b.pw, D, D, m->t_proj)) != SMK_OK || (st = sp(b.f1w, F, D, m->t_fc1)) != SMK_OK ||
+          (st = sp(b.f2w, D, F, m->t_fc2)) != SMK_OK)
         return fail(st);
     }
     if ((st = split2_f16(m->kvw32, D, m->kvwh, (int64_t)cfg->dec_layers * 2 * D, (int)D, s)) != SMK_OK) return fail(st);
-    // terms per contraction: the schedule scripts/precision_emulation.py derives from the 2e-2 logit budget (patch embed, proj, fc1,
-    // fc2: full 3-term split; qkv and the memory K/V projection: weight split only; attention: single-pass fp16).
-    // SMK_FP16S_TERMS="qkv=2,fc1=2,..." overrides single entries (tuning / error-budget experiments).
-    m->t_pe = 3; m->t_qkv = 2; m->t_proj = 3; m->t_fc1 = 3; m->t_fc2 = 3; m->t_kv = 2;
-    if (const char* e = getenv("SMK_FP16S_TERMS")) {
-      struct { const char* k; int* v; } keys[] = {{"pe=", &m->t_pe}, {"qkv=", &m->t_qkv}, {"proj=", &m->t_proj}, {"fc1=", &m->t_fc1},
-                                                  {"fc2=", &m->t_fc2}, {"kv=", &m->t_kv}};
-      for (auto& kv : keys) {
-        const char* q = strstr(e, kv.k);
-        if (q && (q == e || q[-1] == ',')) { const int n = atoi(q + strlen(kv.k)); if (n >= 1 && n <= 3) *kv.v = n; }
-      }
-    }
   }
   if (mode == SMK_MODE_BF16 || mode == SMK_MODE_FP16S) {
     if (mode == SMK_MODE_BF16) {
@@ -649,11 +654,11 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
     __half *Xn = (__half*)m->Xn, *QKV = (__half*)m->QKV, *AO = (__half*)m->AO, *Hm = (__half*)m->Hm;
     const __half* wh = m->wh;
     const int F2 = 2 * F;
-    auto terms = [](int n, int K) { return n >= 3 ? terms_full(K) : (n == 2 ? terms_wsplit(K) : terms_plain()); };
+    auto terms = [](int n, int K) { return n == 4 ? terms_q8(K) : (n == 3 ? terms_full(K) : (n == 2 ? terms_wsplit(K) : terms_plain())); };
     {
       TagScope tg(TAG_IM2COL);
-      if (x_u8) SMK_PROPAGATE(im2col_split_f16<uint8_t>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s));
-      else SMK_PROPAGATE(im2col_split_f16<float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s));
+      if (x_u8) SMK_PROPAGATE(im2col_split_f16<uint8_t>(x_u8, Hm, B, H, W, c.patch, m->hp, m->wp, mean_std, s, m->t_pe == 4));
+      else SMK_PROPAGATE(im2col_split_f16<float>(x, Hm, B, H, W, c.patch, m->hp, m->wp, nullptr, s, m->t_pe == 4));
     }
     {
       TagScope tg(TAG_PATCH_EMBED);
@@ -667,14 +672,15 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       { TagScope tg(TAG_QKV); SMK_PROPAGATE(gemm_tc(Xn, m->t_qkv >= 3 ? 2 * D : D, wh + 2 * b.qkvw, 2 * D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_qkv, D), 0, s)); }
       {
         TagScope tg(TAG_ATTN);
-        if (N <= 256) SMK_PROPAGATE(attention_tc_f16(QKV, AO, 2 * D, 3, B, N, c.heads, scale, s));
-        else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(QKV, 3 * D, QKV + D, 3 * D, QKV + 2 * D, 3 * D, M, M, N, N, 0, AO, 2 * D, 3, B, N, N, c.heads, scale, 1, s));
+        const int ao_mode = m->t_proj == 4 ? 4 : 3;
+        if (N <= 256) SMK_PROPAGATE(attention_tc_f16(QKV, AO, 2 * D, ao_mode, B, N, c.heads, scale, s));
+        else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(QKV, 3 * D, QKV + D, 3 * D, QKV + 2 * D, 3 * D, M, M, N, N, 0, AO, 2 * D, ao_mode, B, N, N, c.heads, scale, 1, s));
         else SMK_PROPAGATE(attention_fa((const __nv_bfloat16*)QKV, nullptr, 3 * D, (const __nv_bfloat16*)QKV + D, nullptr, 3 * D, (const __nv_bfloat16*)QKV + 2 * D, nullptr, 3 * D, N, N, 0,
                                         AO, 2 * D, 3, B, N, N, c.heads, scale, s, 1));
       }
       { TagScope tg(TAG_PROJ); SMK_PROPAGATE(gemm_tc(AO, 2 * D, wh + 2 * b.pw, 2 * D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_proj, D), 0, s)); }
-      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + b.n2w, w + b.n2b, Xn, Xn + D, 2 * D, nullptr, nullptr, nullptr, M, D, 1e-6f, s)); }
-      { TagScope tg(TAG_FC1); SMK_PROPAGATE(gemm_tc(Xn, 2 * D, wh + 2 * b.f1w, 2 * D, w + b.f1b, Hm, F2, M, F, D, SMK_EPI_GELU, 3, 0, nullptr, 1, terms(m->t_fc1, D), 0, s)); }
+      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + b.n2w, w + b.n2b, Xn, Xn + D, 2 * D, nullptr, nullptr, nullptr, M, D, 1e-6f, s, 0, m->t_fc1 == 4)); }
+      { TagScope tg(TAG_FC1); SMK_PROPAGATE(gemm_tc(Xn, 2 * D, wh + 2 * b.f1w, 2 * D, w + b.f1b, Hm, F2, M, F, D, SMK_EPI_GELU, m->t_fc2 == 4 ? 4 : 3, 0, nullptr, 1, terms(m->t_fc1, D), 0, s)); }
       { TagScope tg(TAG_FC2); SMK_PROPAGATE(gemm_tc(Hm, F2, wh + 2 * b.f2w, F2, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_fc2, F), 0, s)); }
     }
     // final norm: fp32 tokens (mask head reference copy), bf16 hi / lo (mask-logit contraction), fp16 (decoder memory)

@@ -25,7 +25,8 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
                                              elements form the bf16x3 split [hi | hi | lo] a split GEMM consumes */,
                  __nv_bfloat16* __restrict__ alt_hi, __nv_bfloat16* __restrict__ alt_lo /* optional bf16 hi / lo copies (rows of D) next to
                                              a 16-bit y of another type: the final encoder norm feeds fp16 GEMMs and the bf16 mask head */,
-                 int64_t ldy, int64_t ld_alt, int64_t rows, int D, float eps, int rev) {
+                 int64_t ldy, int64_t ld_alt, int64_t rows, int D, float eps, int rev,
+                 int q8 /* fp16 only: y_lo receives the e4m3 correction operands (smk_common.cuh split_q8x4) instead of the fp16 residue */) {
   pdl_wait();
   pdl_trigger();
   const int64_t blk = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;     // descending: start on the rows written last
@@ -86,11 +87,25 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
           reinterpret_cast<float4*>(y + row * ldy)[i] = o;
         } else {
           uint2 pk, pr;
-          split16x2<TOut>(o.x, o.y, pk.x, pr.x);
-          split16x2<TOut>(o.z, o.w, pk.y, pr.y);
-          reinterpret_cast<uint2*>(y + row * ldy)[i] = pk;
-          if (y_dup) reinterpret_cast<uint2*>(y_dup + row * ldy)[i] = pk;
-          if (y_lo) reinterpret_cast<uint2*>(y_lo + row * ldy)[i] = pr;
+          bool done = false;
+          if constexpr (std::is_same<TOut, __half>::value) {
+            if (q8 && y_lo) {
+              uint32_t f8, s8;
+              split_q8x4<false>(o.x, o.y, o.z, o.w, pk, f8, s8);
+              uint8_t* q = reinterpret_cast<uint8_t*>(y_lo + row * ldy) + q8_byte_off(4 * i);
+              *reinterpret_cast<uint32_t*>(q) = f8;
+              *reinterpret_cast<uint32_t*>(q + 32) = s8;
+              reinterpret_cast<uint2*>(y + row * ldy)[i] = pk;
+              done = true;
+            }
+          }
+          if (!done) {
+            split16x2<TOut>(o.x, o.y, pk.x, pr.x);
+            split16x2<TOut>(o.z, o.w, pk.y, pr.y);
+            reinterpret_cast<uint2*>(y + row * ldy)[i] = pk;
+            if (y_dup) reinterpret_cast<uint2*>(y_dup + row * ldy)[i] = pk;
+            if (y_lo) reinterpret_cast<uint2*>(y_lo + row * ldy)[i] = pr;
+          }
         }
       }
       if constexpr (sizeof(TOut) == 2) {
@@ -109,7 +124,7 @@ layernorm_kernel(const float* x /* may alias y: a row is fully read before it is
 template <typename TOut>
 static int launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, TOut* y, float* y32,
                             float* sum_out, TOut* y_lo, int64_t rows, int D, float eps, cudaStream_t s, TOut* y_dup = nullptr, int64_t ldy = 0,
-                            __nv_bfloat16* alt_hi = nullptr, __nv_bfloat16* alt_lo = nullptr, int64_t ld_alt = 0) {
+                            __nv_bfloat16* alt_hi = nullptr, __nv_bfloat16* alt_lo = nullptr, int64_t ld_alt = 0, int q8 = 0) {
   if (ldy == 0) ldy = D;
   if (ld_alt == 0) ld_alt = D;
   SMK_REQUIRE(D % 128 == 0 && D <= 1024, "layernorm: D=%d must be a multiple of 128 and <= 1024", D);
@@ -120,7 +135,7 @@ static int launch_layernorm(const float* x, const float* res, const float* gamma
                                                      (y_dup ? sizeof(TOut) : 0) + (alt_hi ? 2.0 : 0.0) + (alt_lo ? 2.0 : 0.0)), s);
   switch (D / 128) {
 #define SMK_LN_CASE(c) \
-  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, alt_hi, alt_lo, ldy, ld_alt, rows, D, eps, rev)); break;
+  case c: SMK_CHECK_CUDA(launch_pdl(layernorm_kernel<TOut, c>, dim3(grid), dim3(256), 0, s, x, res, gamma, beta, y, y32, sum_out, y_lo, y_dup, alt_hi, alt_lo, ldy, ld_alt, rows, D, eps, rev, q8)); break;
     SMK_LN_CASE(1) SMK_LN_CASE(2) SMK_LN_CASE(3) SMK_LN_CASE(4) SMK_LN_CASE(5) SMK_LN_CASE(6) SMK_LN_CASE(7) SMK_LN_CASE(8)
 #undef SMK_LN_CASE
   }
@@ -140,8 +155,8 @@ int layernorm_bf16(const float* x, const float* res, const float* gamma, const f
 // fp16 output for the fp16s mode: y = fp16(LN(x)) in rows of ldy elements; y_lo (optional) = fp16 rounding residue, normally at
 // y + D so that a row is the [hi | lo] split operand of a 3-term GEMM; y32 / alt_hi / alt_lo: optional fp32 and bf16 hi / lo copies
 int layernorm_f16(const float* x, const float* gamma, const float* beta, __half* y, __half* y_lo, int64_t ldy, float* y32,
-                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt) {
-  return launch_layernorm<__half>(x, nullptr, gamma, beta, y, y32, nullptr, y_lo, rows, D, eps, s, nullptr, ldy, alt_hi, alt_lo, ld_alt);
+                  __nv_bfloat16* alt_hi, __nv_bfloat16* alt_lo, int64_t rows, int D, float eps, cudaStream_t s, int64_t ld_alt, int q8) {
+  return launch_layernorm<__half>(x, nullptr, gamma, beta, y, y32, nullptr, y_lo, rows, D, eps, s, nullptr, ldy, alt_hi, alt_lo, ld_alt, q8);
 }
 
 // LayerNorm whose output is the bf16x3 split [hi | hi | lo] (rows of 3D bf16) of the normalised row: the A operand of a split
@@ -533,7 +548,7 @@ im2col_kernel(const TIn* __restrict__ x, T* __restrict__ cols, int H, int W, int
 // an fp32 strip; phase 2 splits 4 pixels per thread into 8 B of hi and 8 B of lo.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-im2col_split_kernel(const TIn* __restrict__ x, __half* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc, bool vec_ok) {
+im2col_split_kernel(const TIn* __restrict__ x, __half* __restrict__ cols, int H, int W, int P, int hp, int wp, NormConst nc, bool vec_ok, int q8) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t im2col_smem[];
@@ -572,15 +587,23 @@ im2col_split_kernel(const TIn* __restrict__ x, __half* __restrict__ cols, int H,
     const int r = j / vec_per_row, kxv = j - r * vec_per_row;
     const float4 v = *reinterpret_cast<const float4*>(strip + r * ws + px * P + kxv * 4);
     uint2 hi, lo;
-    split16x2<__half>(v.x, v.y, hi.x, lo.x);
-    split16x2<__half>(v.z, v.w, hi.y, lo.y);
-    __half* o = dst + (int64_t)px * 2 * K + j * 4;
-    *reinterpret_cast<uint2*>(o) = hi;
-    *reinterpret_cast<uint2*>(o + K) = lo;
+    __half* o = dst + (int64_t)px * 2 * K;
+    if (q8) {
+      split_q8x4<false>(v.x, v.y, v.z, v.w, hi, lo.x, lo.y);
+      uint8_t* q = reinterpret_cast<uint8_t*>(o + K) + q8_byte_off(j * 4);
+      *reinterpret_cast<uint2*>(o + j * 4) = hi;
+      *reinterpret_cast<uint32_t*>(q) = lo.x;
+      *reinterpret_cast<uint32_t*>(q + 32) = lo.y;
+    } else {
+      split16x2<__half>(v.x, v.y, hi.x, lo.x);
+      split16x2<__half>(v.z, v.w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(o + j * 4) = hi;
+      *reinterpret_cast<uint2*>(o + K + j * 4) = lo;
+    }
   }
 }
 template <typename TIn>
-int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s) {
+int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s, int q8) {
   if (B == 0) return SMK_OK;
   SMK_REQUIRE(B <= 65535 && P % 4 == 0, "im2col_split: bad batch / patch size");
   NormConst nc{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
@@ -596,13 +619,13 @@ int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int
   {
     ProfScope prof(PROF_OTHER, (double)B * hp * wp * 3 * P * P * ((double)sizeof(TIn) + 4.0), s);
     const bool vec_ok = (W & 3) == 0 && ((uintptr_t)x % (4 * sizeof(TIn))) == 0;
-    SMK_CHECK_CUDA(launch_pdl(im2col_split_kernel<TIn>, dim3(hp, B), dim3(256), (size_t)smem, s, x, cols, H, W, P, hp, wp, nc, vec_ok));
+    SMK_CHECK_CUDA(launch_pdl(im2col_split_kernel<TIn>, dim3(hp, B), dim3(256), (size_t)smem, s, x, cols, H, W, P, hp, wp, nc, vec_ok, q8));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
 }
-template int im2col_split_f16<float>(const float*, __half*, int, int, int, int, int, int, const float*, cudaStream_t);
-template int im2col_split_f16<uint8_t>(const uint8_t*, __half*, int, int, int, int, int, int, const float*, cudaStream_t);
+template int im2col_split_f16<float>(const float*, __half*, int, int, int, int, int, int, const float*, cudaStream_t, int);
+template int im2col_split_f16<uint8_t>(const uint8_t*, __half*, int, int, int, int, int, int, const float*, cudaStream_t, int);
 
 template <typename TIn, typename T>
 int im2col(const TIn* x, T* cols, int B, int H, int W, int P, int hp, int wp, const float* mean_std, cudaStream_t s) {
@@ -805,6 +828,34 @@ split2_f16_kernel(const float* __restrict__ w, int64_t ldw, __half* __restrict__
   __half* o = out + r * 2 * K;
   o[k] = hi;
   o[K + k] = __float2half_rn(v - __half2float(hi));
+}
+// fp16s mode with fp8 correction terms: row → [hi fp16 (K) | e4m3 correction operands (2K bytes)], smk_common.cuh split_q8x4
+template <bool kWeight>
+__global__ void __launch_bounds__(256)
+split_q8_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ out, int64_t rows, int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 4 columns
+  const int kq = K >> 2;
+  if (i >= rows * kq) return;
+  const int64_t r = i / kq;
+  const int c = (int)(i - r * kq) << 2;
+  const float* src = x + r * ldx + c;
+  uint2 hi;
+  uint32_t f8, s8;
+  split_q8x4<kWeight>(src[0], src[1], src[2], src[3], hi, f8, s8);
+  __half* o = out + r * 2 * K;
+  *reinterpret_cast<uint2*>(o + c) = hi;
+  uint8_t* q = reinterpret_cast<uint8_t*>(o + K) + q8_byte_off(c);
+  *reinterpret_cast<uint32_t*>(q) = f8;
+  *reinterpret_cast<uint32_t*>(q + 32) = s8;
+}
+int split_q8(const float* x, int64_t ldx, __half* out, int64_t rows, int K, int is_weight, cudaStream_t s) {
+  SMK_REQUIRE(K % 32 == 0, "split_q8: K must be a multiple of 32");
+  if (rows == 0) return SMK_OK;
+  const unsigned grid = (unsigned)((rows * (K / 4) + 255) / 256);
+  if (is_weight) split_q8_kernel<true><<<grid, 256, 0, s>>>(x, ldx, out, rows, K);
+  else split_q8_kernel<false><<<grid, 256, 0, s>>>(x, ldx, out, rows, K);
+  SMK_CHECK_LAUNCH();
+  return SMK_OK;
 }
 int split2_f16(const float* w, int64_t ldw, __half* out, int64_t rows, int K, cudaStream_t s) {
   if (rows == 0) return SMK_OK;
@@ -1108,6 +1159,11 @@ int pos_bicubic(const float* pos, float* out, int g, int hp, int wp, int D, cuda
 }  // namespace smk
 
 using namespace smk;
+
+extern "C" int smk_split_q8(const float* x, int64_t ldx, void* out, int64_t rows, int K, int is_weight, void* stream) {
+  SMK_REQUIRE(x && out && rows >= 0 && K > 0 && ldx >= K, "smk_split_q8: bad arguments");
+  return split_q8(x, ldx, (__half*)out, rows, K, is_weight, (cudaStream_t)stream);
+}
 
 extern "C" int smk_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc, int M, int N,
                             int K, int epilogue, void* stream) {

@@ -41,6 +41,12 @@ def mm(a, w_t, scheme):
         return rnd(a, dt) @ rnd(w_t, dt)
     ah, al = split(a, dt)
     wh, wl = split(w_t, dt)
+    if kind == "3q":
+        # fp16 main term + the two correction terms on e4m3 operands (fp8 tensor-core rate): A_hi8·(W_lo·2^15)8 + (A_lo·2^11)8·(W_hi·2^4)8,
+        # accumulated first and scaled by 2^-15 when the fp16 term joins (tcgen05 scale-input-d)
+        q8 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).to(torch.float32)
+        corr = q8(ah) @ q8(wl * 2.0 ** 15) + q8(al * 2.0 ** 11) @ q8(wh * 2.0 ** 4)
+        return ah @ wh + corr * 2.0 ** -15
     if kind == "2a":
         return ah @ wh + al @ wh
     if kind == "2w":

@@ -517,6 +517,111 @@ def test_gemm_split_terms_match_fp64(M_, N, K, epi, terms, out_kind, f16):
         assert (got - full).abs().max().item() <= (2e-4 if f16 else 6e-4) * scale
 
 
+def _q8(t):
+    return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).double()
+
+
+def _unpack_q8(rows2k, K):
+    """[rows, 2K fp16 columns] → (hi fp64 [rows, K], first fp64 [rows, K], second fp64 [rows, K]) of the split_q8 row layout."""
+    hi = rows2k[:, :K].double()
+    q = rows2k[:, K:].contiguous().view(torch.uint8).view(rows2k.shape[0], K // 32, 2, 32)
+    first = q[:, :, 0, :].reshape(-1, K).view(torch.float8_e4m3fn).double()
+    second = q[:, :, 1, :].reshape(-1, K).view(torch.float8_e4m3fn).double()
+    return hi, first, second
+
+
+def test_split_q8_layout_and_values():
+    """smk_split_q8: fp16 hi + the e4m3 correction operands (activation and weight scalings), 32-column interleave."""
+    torch.manual_seed(44)
+    rows, K = 37, 192
+    x = torch.randn(rows, K, device=DEV) * 3.0
+    x[0, :8] = torch.tensor([500.0, -700.0, 1e-6, 0.0, 447.0, -3e-4, 60000.0, 1.0], device=DEV)      # saturation / underflow corners
+    for is_w in (0, 1):
+        out = torch.zeros(rows, 2 * K, dtype=torch.float16, device=DEV)
+        check(lib().smk_split_q8(ptr(x), K, ptr(out), rows, K, is_w, stream_ptr()), "smk_split_q8")
+        torch.cuda.synchronize()
+        hi, first, second = _unpack_q8(out, K)
+        h = x.to(torch.float16)
+        lo = (x - h.float())
+        assert torch.equal(hi, h.double())
+        if is_w:
+            assert torch.equal(first, _q8(lo * 2.0 ** 15)) and torch.equal(second, _q8(h.float() * 16.0))
+        else:
+            assert torch.equal(first, _q8(h.float())) and torch.equal(second, _q8(lo * 2.0 ** 11))
+
+
+@pytest.mark.parametrize("M_,N,K,epi,out_kind", [
+    (300, 384, 384, 0, 1), (50432, 1536, 384, 1, 4), (50432, 384, 1536, 4, 1), (50176, 384, 768, 0, 1), (50432, 384, 384, 4, 1),
+    (20000, 512, 1024, 0, 0), (130, 128, 64, 2, 3), (5000, 256, 192, 0, 4)])
+def test_gemm_fp8_correction_terms(M_, N, K, epi, out_kind):
+    """smk_gemm_q8: fp16 hi·hi + the two correction products on e4m3 operands (fp8 tensor-core rate, accumulated first at 2^15 and
+    scaled into the fp16 term by scale-input-d).  Checked against (1) the exact value of the issued terms and (2) the fp64 product of
+    the unsplit operands: ~fp32-grade like the 3-term fp16 split.  Shapes: fc1 (GELU, q8 output), fc2 (swap-AB, residual), patch
+    embed, proj, a CTA-pair shape, small ragged ones."""
+    torch.manual_seed(45)
+    A32 = torch.randn(M_, K, device=DEV) * 1.5
+    W32 = torch.randn(N, K, device=DEV) * 0.05
+    bias = torch.randn(N, device=DEV)
+    A2 = torch.zeros(M_, 2 * K, dtype=torch.float16, device=DEV)
+    W2 = torch.zeros(N, 2 * K, dtype=torch.float16, device=DEV)
+    check(lib().smk_split_q8(ptr(A32), K, ptr(A2), M_, K, 0, stream_ptr()), "smk_split_q8")
+    check(lib().smk_split_q8(ptr(W32), K, ptr(W2), N, K, 1, stream_ptr()), "smk_split_q8")
+    C0 = torch.randn(M_, N, device=DEV) if epi & 4 else None
+    if out_kind == 1:
+        out = C0.clone() if C0 is not None else torch.empty(M_, N, device=DEV)
+    else:
+        out = torch.full((M_, N * (1 if out_kind == 0 else 2)), 7.0, dtype=torch.float16, device=DEV)
+    check(lib().smk_gemm_q8(ptr(A2), 2 * K, ptr(W2), 2 * K, ptr(bias), ptr(out), out.shape[1], M_, N, K, epi, out_kind, stream_ptr()), "smk_gemm_q8")
+    torch.cuda.synchronize()
+    ah, a1, a2 = _unpack_q8(A2, K)
+    wh, w1, w2 = _unpack_q8(W2, K)
+    issued = ah @ wh.t() + (a1 @ w1.t() + a2 @ w2.t()) * 2.0 ** -15 + bias.double()
+    act = (lambda t: torch.nn.functional.gelu(t)) if epi & 1 else ((lambda t: torch.relu(t)) if epi & 2 else (lambda t: t))
+    ref = act(issued) + (C0.double() if C0 is not None else 0)
+    if out_kind == 1 or out_kind == 0:
+        got = out.double()
+    elif out_kind == 3:
+        got = out[:, :N].double() + out[:, N:].double()
+    else:
+        hi, first, second = _unpack_q8(out, N)
+        got = hi + second * 2.0 ** -11
+        assert torch.equal(first, _q8(hi.float()))
+    scale = max(1.0, ref.abs().max().item())
+    err = (got - ref).abs().max().item()
+    tol = 2.0 ** -10 if out_kind == 0 else (2.0 ** -13 if out_kind == 4 else 2e-4)   # q8 output: lo keeps ~3 bits below the fp16 ulp
+    assert err <= tol * scale, err
+    # against the unsplit product: the dropped lo·lo term and the e4m3 rounding of the correction operands
+    full = act(A32.double() @ W32.double().t() + bias.double()) + (C0.double() if C0 is not None else 0)
+    err_full = (got - full).abs().max().item()
+    assert err_full <= max(tol, 4e-4) * scale, err_full
+    print(f"q8 gemm M={M_} N={N} K={K}: issued err {err / scale:.2e}, vs exact {err_full / scale:.2e}")
+
+
+@pytest.mark.parametrize("B,N", [(3, 197), (2, 577)])
+def test_attention_q8_output_equals_split_of_fp32_output(B, N):
+    """Attention out mode 4 ([hi | e4m3 operands], the proj GEMM's A operand): identical to smk_split_q8 of the kernel's fp32-grade
+    output ([hi | lo] mode 3 summed)."""
+    torch.manual_seed(46)
+    H, dh = 6, 64
+    D = H * dh
+    qkv = (torch.randn(B * N, 3 * D, device=DEV) * 1.5).to(torch.float16)
+    o3 = torch.zeros(B * N, 2 * D, dtype=torch.float16, device=DEV)
+    o4 = torch.zeros(B * N, 2 * D, dtype=torch.float16, device=DEV)
+    for mode, o in ((3, o3), (4, o4)):
+        if N <= 256:
+            check(lib().smk_attention_tc_f16(ptr(qkv), ptr(o), 2 * D, mode, B, N, H, 0.125, stream_ptr()), "smk_attention_tc_f16")
+        else:
+            check(lib().smk_attention_tc_multi(ptr(qkv), 3 * D, ptr(qkv[:, D:]), 3 * D, ptr(qkv[:, 2 * D:]), 3 * D, B * N, B * N, N, N, 0, ptr(o), 2 * D,
+                                               mode, B, N, N, H, 0.125, 1, stream_ptr()), "smk_attention_tc_multi")
+    torch.cuda.synchronize()
+    hi, first, second = _unpack_q8(o4, D)
+    assert torch.equal(hi, o3[:, :D].double())
+    assert torch.equal(first, _q8(o3[:, :D].float()))
+    # lo of mode 3 is fp16(x − hi); mode 4 stores e4m3((x − hi)·2^11): equal up to the e4m3 rounding of the same residue
+    lo = o3[:, D:].double()
+    assert ((second * 2.0 ** -11 - lo).abs() <= lo.abs() * (2.0 ** -4 + 2.0 ** -9) + 2.0 ** -21).all()
+
+
 @pytest.mark.parametrize("B,N,out_mode", [(3, 197, 0), (64, 197, 3), (2, 256, 3), (5, 130, 0), (150, 197, 3), (2, 17, 3)])
 def test_attention_tcgen05_fp16_matches_torch(B, N, out_mode):
     """fp16 operands on the tcgen05 attention kernel (fp16s mode): plain fp16 output and the [hi | lo] fp16 split output."""
