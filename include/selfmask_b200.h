@@ -255,9 +255,11 @@ int smk_attention_small_f16(const void* q, int64_t ldq, const void* k, int64_t l
                             int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk, int heads, float scale,
                             int q_f32, void* stream);
 /* Decoder self-attention in fp32 on the CUDA cores (nq <= 32 queries = keys per image): qk [B*nq, ldqk] fp32 with q in columns
- * [0, heads*64) and k in [heads*64, 2*heads*64), v [B*nq, ldv] fp32 → out3 [B*nq, 3*heads*64] bf16 split [hi | hi | lo]. */
-int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, void* out3, int B, int nq, int heads,
-                           float scale, void* stream);
+ * [0, heads*64) and k in [heads*64, 2*heads*64), v [B*nq, ldv] fp32 → out3 [B*nq, 3*heads*64] bf16 split [hi | hi | lo].
+ * v_sub: NULL, or [nq, heads*64] fp32 subtracted from every image's V rows (v then comes from ONE q|k|v projection of tgt + query_pos and
+ * v_sub = query_pos · Wv^T removes the positional part: value = tgt, transformer_decoder.py:277). */
+int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, const float* v_sub, void* out3, int B, int nq,
+                           int heads, float scale, void* stream);
 
 /* Decoder cross-attention against the memory, restructured (smk_xattn_tc.cu; transformer_decoder.py:283-291): per image the nq*heads
  * rows of qp [n_img*nq, heads*D] fp16 (row (b, q), column (h, c): the query times the folded Wq_h^T Wk_h / 8) attend the image's hw

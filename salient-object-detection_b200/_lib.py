@@ -59,7 +59,7 @@ SIGNATURES = {
     "smk_xattn_fold_weights": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "smk_attention_tc_f16": (_I, [_P, _P, _L, _I, _I, _I, _I, _F, _P]),
     "smk_attention_small_f16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, C.c_float, _I, _P]),
-    "smk_dec_self_attention": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _F, _P]),
+    "smk_dec_self_attention": (_I, [_P, _L, _P, _L, _P, _P, _I, _I, _I, _F, _P]),
     "smk_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "smk_attention": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _I, _P]),
     "smk_attention_tc": (_I, [_P, _P, _I, _I, _I, _F, _P]),

@@ -15,8 +15,8 @@ namespace {
 constexpr int DSA_THREADS = 128, DSA_MAXQ = 32, DSA_DH = 64;
 
 __global__ void __launch_bounds__(DSA_THREADS)
-dec_self_attn_kernel(const float* __restrict__ qk, int64_t ldqk, const float* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ out3,
-                     int nq, int heads, float scale) {
+dec_self_attn_kernel(const float* __restrict__ qk, int64_t ldqk, const float* __restrict__ v, int64_t ldv, const float* __restrict__ v_sub,
+                     __nv_bfloat16* __restrict__ out3, int nq, int heads, float scale) {
   __shared__ float sq[DSA_MAXQ][DSA_DH];
   __shared__ float sk[DSA_MAXQ][DSA_DH + 1];
   __shared__ float sv[DSA_MAXQ][DSA_DH];
@@ -30,7 +30,11 @@ dec_self_attn_kernel(const float* __restrict__ qk, int64_t ldqk, const float* __
     const int r = i >> 4, c = (i & 15) << 2;
     const float4 a = *reinterpret_cast<const float4*>(qk + (row0 + r) * ldqk + h * DSA_DH + c);
     const float4 kk = *reinterpret_cast<const float4*>(qk + (row0 + r) * ldqk + D + h * DSA_DH + c);
-    const float4 vv = *reinterpret_cast<const float4*>(v + (row0 + r) * ldv + h * DSA_DH + c);
+    float4 vv = *reinterpret_cast<const float4*>(v + (row0 + r) * ldv + h * DSA_DH + c);
+    if (v_sub) {      // v is the V slice of a merged q|k|v projection of (tgt + query_pos): take query_pos · Wv^T out again (value = tgt)
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(v_sub + (int64_t)r * D + h * DSA_DH + c));
+      vv.x -= cs.x; vv.y -= cs.y; vv.z -= cs.z; vv.w -= cs.w;
+    }
     sq[r][c] = a.x * scale; sq[r][c + 1] = a.y * scale; sq[r][c + 2] = a.z * scale; sq[r][c + 3] = a.w * scale;   // q scaled first, as torch does
     sk[r][c] = kk.x; sk[r][c + 1] = kk.y; sk[r][c + 2] = kk.z; sk[r][c + 3] = kk.w;
     *reinterpret_cast<float4*>(&sv[r][c]) = vv;
@@ -72,15 +76,21 @@ dec_self_attn_kernel(const float* __restrict__ qk, int64_t ldqk, const float* __
 
 }  // namespace
 
-// qk: [B*nq, ldqk] fp32 (q in columns [0, D), k in [D, 2D)); v: [B*nq, ldv] fp32; out3: [B*nq, 3D] bf16 split [hi | hi | lo]
-int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, __nv_bfloat16* out3, int B, int nq, int heads, float scale,
-                       cudaStream_t s) {
+// qk: [B*nq, ldqk] fp32 (q in columns [0, D), k in [D, 2D)); v: [B*nq, ldv] fp32; v_sub: nullptr or [nq, D] fp32 subtracted from every image's
+// V rows (v = the V slice of ONE q|k|v projection of tgt + query_pos, v_sub = query_pos · Wv^T: value = tgt, transformer_decoder.py:277);
+// out3: [B*nq, 3D] bf16 split [hi | hi | lo].
+// (A one-warp-per-unit variant — lane = query row, everything in registers, no block barrier — was measured slower: 27.6 us against
+// this kernel's 24.6 us warm at B = 256: its 2560-FMA serial chains per lane leave the schedulers idle.  This kernel is bound by
+// shared-memory wavefronts — ~2800 per CTA for the scalar score / P·V reads — not by the 0.6 MFLOP of math.)
+int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, const float* v_sub, __nv_bfloat16* out3, int B, int nq, int heads,
+                       float scale, cudaStream_t s) {
   SMK_REQUIRE(nq >= 1 && nq <= DSA_MAXQ, "dec_self_attention: nq=%d not supported (1..32)", nq);
   SMK_REQUIRE(ldqk % 4 == 0 && ldv % 4 == 0 && ((uintptr_t)qk % 16) == 0 && ((uintptr_t)v % 16) == 0, "dec_self_attention: misaligned q/k/v");
+  SMK_REQUIRE(((uintptr_t)v_sub % 16) == 0, "dec_self_attention: misaligned v_sub");
   if (B == 0) return SMK_OK;
   {
     ProfScope prof(PROF_ATTENTION, 4.0 * nq * nq * DSA_DH * heads * B, s);
-    SMK_CHECK_CUDA(launch_pdl(dec_self_attn_kernel, dim3((unsigned)(B * heads)), dim3(DSA_THREADS), 0, s, qk, ldqk, v, ldv, out3, nq, heads, scale));
+    SMK_CHECK_CUDA(launch_pdl(dec_self_attn_kernel, dim3((unsigned)(B * heads)), dim3(DSA_THREADS), 0, s, qk, ldqk, v, ldv, v_sub, out3, nq, heads, scale));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
@@ -88,8 +98,8 @@ int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ld
 
 }  // namespace smk
 
-extern "C" int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, void* out3, int B, int nq, int heads,
-                                      float scale, void* stream) {
+extern "C" int smk_dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, const float* v_sub, void* out3, int B, int nq,
+                                      int heads, float scale, void* stream) {
   SMK_REQUIRE(qk && v && out3, "smk_dec_self_attention: null pointer");
-  return smk::dec_self_attention(qk, ldqk, v, ldv, (__nv_bfloat16*)out3, B, nq, heads, scale, (cudaStream_t)stream);
+  return smk::dec_self_attention(qk, ldqk, v, ldv, v_sub, (__nv_bfloat16*)out3, B, nq, heads, scale, (cudaStream_t)stream);
 }

@@ -92,8 +92,8 @@ int im2col_split_f16(const TIn* x, __half* cols, int B, int H, int W, int P, int
 int split2_f16(const float* w, int64_t ldw, __half* out, int64_t rows, int K, cudaStream_t s);
 // row → [hi fp16 (K) | e4m3 correction operands (2K bytes)] for the fp8-corrected GEMMs (terms_q8); is_weight picks the weight-side scales
 int split_q8(const float* x, int64_t ldx, __half* out, int64_t rows, int K, int is_weight, cudaStream_t s);
-int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, __nv_bfloat16* out3, int B, int nq, int heads, float scale,
-                       cudaStream_t s);
+int dec_self_attention(const float* qk, int64_t ldqk, const float* v, int64_t ldv, const float* v_sub, __nv_bfloat16* out3, int B, int nq, int heads,
+                       float scale, cudaStream_t s);
 int assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* tokens, int B, int hw, int D, bool cls_only,
                     cudaStream_t s);
 int add_rows(const float* a, const float* pos, float* out, int64_t rows, int D, int period, cudaStream_t s);

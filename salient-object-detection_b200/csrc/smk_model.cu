@@ -181,6 +181,7 @@ struct smk_model {
   bool xattn = false;
   __half *xa_wg, *xa_qp, *xa_xh, *dec0_xh, *xa_m2, *xa_u2;
   float *xa_g, *xa_bo, *xa_scratch;
+  float* dec_cv;                // [L, nq, D] query_pos · Wv^T per decoder layer (merged self-attention projection, fp16s mode)
   float* dec0_tgt;                // [nq, D]
   __nv_bfloat16* dec0_a3b;        // [nq, 3D] split(tgt + query_pos)
   bool dec0_ready = false;
@@ -235,7 +236,7 @@ static void plan(smk_model& m, Plan& pl) {
   const int64_t R = B * nq;
   m.tgt = pl.take<float>(R * D);
   m.qin = pl.take<float>(R * D);
-  m.dqk = pl.take<float>(R * 2 * D);
+  m.dqk = pl.take<float>(R * 3 * D);          // q | k (| v: fp16s mode, merged self-attention projection)
   m.dv = pl.take<float>(R * D);
   m.dao = pl.take<float>(R * D);
   m.x3qkv = x3 ? pl.take<__nv_bfloat16>(R * 9 * D) : nullptr;     // bf16x3 decoder: split q|k [R, 3·2D] and split v / cross q [R, 3D]
@@ -276,6 +277,7 @@ static void plan(smk_model& m, Plan& pl) {
       m.dec0_xh = pl.take<__half>(nq * D);
     }
     m.dec0_tgt = pl.take<float>(nq * D);
+    m.dec_cv = pl.take<float>(L * nq * D);
     m.dec0_a3b = pl.take<__nv_bfloat16>(nq * 3 * D);
     m.a3q = pl.take<__nv_bfloat16>(L * R * 3 * D);                     // split(final-norm queries), all layers
     m.dqk_b = pl.take<__nv_bfloat16>(R * 2 * D);
@@ -508,6 +510,12 @@ extern "C" int smk_model_create(const smk_config* cfg, int mode, const float* we
       if ((st = split3_weight(weights + d.caow, d3.caow, D, (int)D, s)) != SMK_OK) return fail(st);
       if ((st = split3_weight(weights + d.l1w, d3.l1w, FD, (int)D, s)) != SMK_OK) return fail(st);
       if ((st = split3_weight(weights + d.l2w, d3.l2w, D, FD, s)) != SMK_OK) return fail(st);
+    }
+    for (int l = 0; l < cfg->dec_layers; ++l) {      // query_pos · Wv^T (no bias): what the merged q|k|v projection adds to the values
+      const DecW& d = m->dec[l];
+      if ((st = gemm_f32(weights + m->o_query, D, weights + d.saw + (int64_t)2 * D * D, D, nullptr, m->dec_cv + (int64_t)l * cfg->n_queries * D, D,
+                         cfg->n_queries, (int)D, (int)D, SMK_EPI_NONE, s)) != SMK_OK)
+        return fail(st);
     }
     if ((st = split3_weight(weights + m->o_f0w, m->f0w3, D, (int)D, s)) != SMK_OK) return fail(st);
     if ((st = split3_weight(weights + m->o_f1w, m->f1w3, D, (int)D, s)) != SMK_OK) return fail(st);
@@ -808,7 +816,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
       float *tgt = m->tgt + r0 * D, *t2 = m->t2 + r0 * D;
       __nv_bfloat16 *a3a = m->a3a + r0 * 3 * D, *a3b = m->a3b + r0 * 3 * D, *a3c = m->a3c + r0 * 3 * D, *a3f = m->a3f + r0 * 3 * FD;
       __nv_bfloat16 *dqk_b = m->dqk_b + r0 * 2 * D, *dv_b = m->dv_b + r0 * D, *cq_b = m->cq_b + r0 * D;
-      float *dqk32 = m->dqk + r0 * 2 * D, *dv32 = m->dv + r0 * D, *cq32 = m->qin + r0 * D;
+      float* cq32 = m->qin + r0 * D;
       const __nv_bfloat16* KVg = KVb + (int64_t)b0 * N * ldkv;
       auto gemm3 = [&](const __nv_bfloat16* a3, const __nv_bfloat16* w3, const float* bias, void* C, int64_t ldc, int rows, int N_, int K_,
                        int epi, int out_f32) {
@@ -836,10 +844,12 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
         if (hx && nq <= 32) {
           // fp16s mode: fp32 projections and CUDA-core fp32 attention — query_embed is N(0, 1), the nq x nq scores are large and this
           // tiny contraction is the most rounding-sensitive of the path (bf16 operands: 7e-2 on the mask logits, smk_dec_attn.cu)
-          SMK_PROPAGATE(gemm3(a3b, d3.saw, w + d.sab, dqk32, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 1));
-          SMK_PROPAGATE(gemm3(a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, dv32, D, R, D, D, SMK_EPI_NONE, 1));
+          // ONE q | k | v projection of (tgt + query_pos); the value's positional part, query_pos · Wv^T (a per-layer constant computed
+          // at creation), is taken out again when the attention kernel stages V
+          float* dqkv32 = m->dqk + r0 * 3 * D;
+          SMK_PROPAGATE(gemm3(a3b, d3.saw, w + d.sab, dqkv32, 3 * D, R, 3 * D, D, SMK_EPI_NONE, 1));
           TagScope tg(TAG_DEC_ATTN);
-          SMK_PROPAGATE(dec_self_attention(dqk32, 2 * D, dv32, D, a3c, nb, nq, c.heads, scale, s));
+          SMK_PROPAGATE(dec_self_attention(dqkv32, 3 * D, dqkv32 + 2 * D, 3 * D, m->dec_cv + (int64_t)l * nq * D, a3c, nb, nq, c.heads, scale, s));
         } else {
           SMK_PROPAGATE(gemm3(a3b, d3.saw, w + d.sab, dqk_b, 2 * D, R, 2 * D, D, SMK_EPI_NONE, 0));
           SMK_PROPAGATE(gemm3(a3a, d3.saw + (int64_t)2 * D * 3 * D, w + d.sab + 2 * D, dv_b, D, R, D, D, SMK_EPI_NONE, 0));

@@ -676,19 +676,26 @@ def test_attention_tcgen05_multi_tile_matches_torch(B, N, f16, out_mode):
     assert (got - ref).abs().mean().item() <= (4e-4 if f16 else 3e-3)
 
 
-@pytest.mark.parametrize("nq,B", [(20, 37), (10, 5), (32, 3), (1, 2)])
-def test_decoder_self_attention_fp32_matches_torch(nq, B):
+@pytest.mark.parametrize("nq,B,sub", [(20, 37, 0), (10, 5, 1), (32, 3, 0), (1, 2, 1), (20, 256, 1)])
+def test_decoder_self_attention_fp32_matches_torch(nq, B, sub):
+    """fp32 CUDA-core decoder self-attention; `sub`: V is the slice of a merged q|k|v projection (row stride 3D) and a per-query
+    constant [nq, D] is subtracted from it on the way in."""
     torch.manual_seed(42)
     H, dh = 6, 64
     D = H * dh
-    qk = torch.randn(B * nq, 2 * D, device=DEV) * 3.0            # large scores: a peaked softmax, as with query_embed ~ N(0, 1)
-    v = torch.randn(B * nq, D, device=DEV)
+    qkv = torch.randn(B * nq, 3 * D, device=DEV) * 3.0            # large scores: a peaked softmax, as with query_embed ~ N(0, 1)
+    qkv[:, 2 * D:] /= 3.0
+    vsub = torch.randn(nq, D, device=DEV) if sub else None
     out = torch.full((B * nq, 3 * D), 7.0, device=DEV, dtype=torch.bfloat16)
-    check(lib().smk_dec_self_attention(ptr(qk), 2 * D, ptr(v), D, ptr(out), B, nq, H, 0.125, stream_ptr()), "smk_dec_self_attention")
+    check(lib().smk_dec_self_attention(ptr(qkv), 3 * D, ptr(qkv[:, 2 * D:]), 3 * D, ptr(vsub), ptr(out), B, nq, H, 0.125, stream_ptr()),
+          "smk_dec_self_attention")
     torch.cuda.synchronize()
-    qh = qk[:, :D].double().view(B, nq, H, dh).transpose(1, 2)
-    kh = qk[:, D:].double().view(B, nq, H, dh).transpose(1, 2)
-    vh = v.double().view(B, nq, H, dh).transpose(1, 2)
+    qh = qkv[:, :D].double().view(B, nq, H, dh).transpose(1, 2)
+    kh = qkv[:, D:2 * D].double().view(B, nq, H, dh).transpose(1, 2)
+    v = qkv[:, 2 * D:].double().view(B, nq, D)
+    if sub:
+        v = v - vsub.double()[None]
+    vh = v.view(B, nq, H, dh).transpose(1, 2)
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).transpose(1, 2).reshape(B * nq, D)
     assert torch.equal(out[:, :D], out[:, D:2 * D])
     got = out[:, :D].double() + out[:, 2 * D:].double()
