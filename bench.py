@@ -207,6 +207,11 @@ def workload_config(args, **extra):
          "images": f"{args.batch} distinct synthetic images per rank (no tiling)",
          "l2": "working set larger than L2: every step streams > 1 GB of activations through the 126 MB L2, so the 51 MB of "
                "inputs (x uint8 + GT) are evicted between steps"}
+    if args.mode == "fp16s":
+        c["numeric_mode_detail"] = ("fp16 tcgen05 operands, fp32 accumulate (TMEM), fp32 residual stream / LayerNorm / softmax; patch embed, proj, fc1, "
+                                    "fc2 = fp16 hi·hi + the two correction products hi·lo + lo·hi on e4m3 operands (fp8 tensor-core rate, scale-input-d); "
+                                    "qkv = A_hi·(W_hi + W_lo); encoder attention single-pass fp16; decoder self-attention fp32 on the CUDA cores; "
+                                    "cross-attention restructured fp16 on tcgen05; decoder tail / heads = 3-term bf16 splits")
     c.update(extra)
     return c
 
@@ -498,7 +503,8 @@ def main():
                 "peak_source": f"MEASURED_PEAKS.json ({pk['src']}; sustained bf16 for a kernel timed inside a long step; burst {pk['tensor_burst']})",
                 "avg_launch_ms": d["us_per_launch"] / 1e3,
                 "definition": "achieved = algorithmic FLOPs (2·M·N·K of the contraction, SURVEY.md §8d; split-operand terms are NOT credited) "
-                              "per launch / the kernel's CUDA-event launch time; issued = the same with the tensor-core terms really issued",
+                              "per launch / the kernel's CUDA-event launch time; issued = the same with the tensor-core terms really issued "
+                              "(the e4m3 correction products of the fp16s GEMMs count as 2·M·N·2K issued at the fp8 rate, i.e. twice the peak this fraction is taken against)",
                 "kernels": rows, "event_timed_ms_per_step": prof_ms, "plain_ms_per_step": ms / K,
                 "note": "event pairs around every launch defeat the PDL overlap, so the per-kernel rows sum to more than the plain step",
                 "whole_step": ({"algorithmic_gflop_per_image": gflop_img, "achieved_tflops": value / world * gflop_img / 1e3,

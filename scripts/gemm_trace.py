@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from selfmask_b200._lib import check, lib, ptr, stream_ptr
 ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default="qkv:50432:1152:384:0:0,proj:50432:384:384:4:1,fc1:50432:1536:384:1:0,fc2:50432:384:1536:4:1")
+ap.add_argument("--q8", action="store_true", help="fp16s-mode form: smk_gemm_q8 on [hi | q8] rows; the last shape field is then the output kind (0 / 1 / 3 / 4)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 for sh in args.shapes.split(","):
@@ -15,6 +16,11 @@ for sh in args.shapes.split(","):
     bias = torch.randn(N, device=dev)
     C = torch.zeros(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
     run = lambda: check(lib().smk_gemm_bf16(ptr(A), K, ptr(W), ptr(bias), ptr(C), N, M, N, K, epi, f32, stream_ptr()))
+    if args.q8:
+        A = (torch.randn(M, 2 * K, device=dev) * 0.01).to(torch.float16)
+        W = (torch.randn(N, 2 * K, device=dev) * 0.01).to(torch.float16)
+        C = torch.zeros(M, N * (1 if f32 in (0, 1) else 2), device=dev, dtype=torch.float32 if f32 == 1 else torch.float16)
+        run = lambda: check(lib().smk_gemm_q8(ptr(A), 2 * K, ptr(W), 2 * K, ptr(bias), ptr(C), C.shape[1], M, N, K, epi, f32, stream_ptr()))
     for _ in range(3):
         run()
     tr = torch.zeros(16 * 148, dtype=torch.int64, device=dev)
