@@ -229,7 +229,8 @@ int smk_attention_tc_f16(const void* qkv, void* out, int64_t ldo, int out_mode, 
 /* Multi-key-tile form for sequences longer than one tile (384 x 384: 577 tokens; ViT-S/8: 785; vision_transformer.py:110-130):
  * 176-key tiles with an online rescale of the TMEM accumulator.  q / k / v: 16-bit matrices (bf16, or fp16 when f16 != 0), head h at
  * columns [h*64, h*64+64) from each pointer; image b: queries at rows b*q_rows .. +Lq, keys / values at rows b*kv_rows + kv_row0 .. +Lk.
- * Lk >= 176.  out [.., ldo]: out_mode 0 16-bit (operand type), 1 fp32, 2 [hi | hi | lo], 3 [hi | lo]. */
+ * Lk >= 176.  out [.., ldo]: out_mode 0 16-bit (operand type), 1 fp32, 2 [hi | hi | lo], 3 [hi | lo], 4 [hi fp16 | e4m3 operands] (the
+ * A operand of smk_gemm_q8; f16 only); out_mode | 8 with f16: the parts of modes 2 / 3 are bf16 (consumer: a bf16 split GEMM). */
 int smk_attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t q_total_rows,
                            int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq,
                            int Lk, int heads, float scale, int f16, void* stream);

@@ -38,6 +38,7 @@ struct AttnMultiParams {
   int heads, n_items, out_mode; // items = images x heads x query groups; out_mode 0 16-bit, 1 fp32, 2 [hi | hi | lo], 3 [hi | lo]
   float scale_log2e;
   int rev;
+  int out_bf16;                 // fp16 operands only: the [hi | hi | lo] / [hi | lo] output parts are bf16 (consumer: a bf16 split GEMM)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -355,7 +356,8 @@ attn_tc_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               for (int e = 0; e < 4; ++e) {
                 const int c0 = 8 * j + 2 * e;
                 const float a = c0 < 32 ? f(oa[c0]) : f(ob[c0 - 32]), bb = c0 + 1 < 32 ? f(oa[c0 + 1]) : f(ob[c0 + 1 - 32]);
-                split16x2<T16>(a, bb, hh[e], ll[e]);
+                if (kF16 && p.out_bf16) split16x2<__nv_bfloat16>(a, bb, hh[e], ll[e]);
+                else split16x2<T16>(a, bb, hh[e], ll[e]);
               }
               const uint32_t off = ((uint32_t)j << 4) ^ x7s;
               st_shared_v4(srow + off, hh[0], hh[1], hh[2], hh[3]);
@@ -398,11 +400,13 @@ attn_tc_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // q / k / v: 16-bit matrices (bf16, or fp16 when f16), head h at columns [h*64, h*64+64) of each pointer; image b's queries start at row
 // b*q_rows, its keys / values at row b*kv_rows + kv_row0.  Lq >= 1, Lk >= 176 (shorter sequences: smk_attn_tc.cu).  out [B*Lq, ldo]:
-// out_mode 0 16-bit (operand type), 1 fp32, 2 [hi | hi | lo], 3 [hi | lo] in the operand type.
+// out_mode 0 16-bit (operand type), 1 fp32, 2 [hi | hi | lo], 3 [hi | lo] in the operand type (out_bf16: bf16 parts next to fp16 operands),
+// 4 [hi fp16 | e4m3 correction operands] (fp16 only).
 int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t q_total_rows,
                        int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk,
-                       int heads, float scale, int f16, cudaStream_t s) {
+                       int heads, float scale, int f16, cudaStream_t s, int out_bf16) {
   const int D = heads * AM_DH;
+  SMK_REQUIRE(!out_bf16 || (f16 && (out_mode == 2 || out_mode == 3)), "attention_tc_multi: bf16 output parts go with fp16 operands and a split output mode");
   SMK_REQUIRE(Lk >= AM_KT && Lq >= 1 && B >= 1 && heads >= 1, "attention_tc_multi: Lq=%d / Lk=%d not supported (Lk >= 176)", Lq, Lk);
   SMK_REQUIRE(out_mode >= 0 && out_mode <= 4 && (out_mode != 4 || f16) && (out_mode != 2 || ldo >= 3 * (int64_t)D) && (out_mode < 3 || ldo >= 2 * (int64_t)D),
               "attention_tc_multi: bad output mode / ldo");
@@ -427,7 +431,7 @@ int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, c
     SMK_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AM_SMEM));
   }
   const int n_items = B * heads * n_qgroups;
-  AttnMultiParams p{Lq, Lk, n_qgroups, n_ktiles, q_rows, kv_rows, kv_row0, heads, n_items, out_mode, scale * 1.4426950408889634f, traverse_dir()};
+  AttnMultiParams p{Lq, Lk, n_qgroups, n_ktiles, q_rows, kv_rows, kv_row0, heads, n_items, out_mode, scale * 1.4426950408889634f, traverse_dir(), out_bf16};
   const int grid = n_items < device_sm_count() ? n_items : device_sm_count();
   {
     ProfScope prof(PROF_ATTENTION_TC, 4.0 * Lq * Lk * AM_DH * heads * B, s);
@@ -444,6 +448,6 @@ extern "C" int smk_attention_tc_multi(const void* q, int64_t ldq, const void* k,
                                       int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B,
                                       int Lq, int Lk, int heads, float scale, int f16, void* stream) {
   SMK_REQUIRE(q && k && v && out, "smk_attention_tc_multi: null pointer");
-  return smk::attention_tc_multi(q, ldq, k, ldk, v, ldv, q_total_rows, kv_total_rows, q_rows, kv_rows, kv_row0, out, ldo, out_mode, B, Lq, Lk, heads,
-                                 scale, f16, (cudaStream_t)stream);
+  return smk::attention_tc_multi(q, ldq, k, ldk, v, ldv, q_total_rows, kv_total_rows, q_rows, kv_rows, kv_row0, out, ldo, out_mode & 7, B, Lq, Lk, heads,
+                                 scale, f16, (cudaStream_t)stream, (out_mode >> 3) & 1);
 }

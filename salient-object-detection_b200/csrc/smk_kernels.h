@@ -66,7 +66,7 @@ int attention_tc_f16(const __half* qkv, __half* out, int64_t ldo, int out_mode, 
 // out_mode 0 16-bit, 1 fp32, 2 [hi | hi | lo], 3 [hi | lo]
 int attention_tc_multi(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t q_total_rows,
                        int64_t kv_total_rows, int q_rows, int kv_rows, int kv_row0, void* out, int64_t ldo, int out_mode, int B, int Lq, int Lk,
-                       int heads, float scale, int f16, cudaStream_t s);
+                       int heads, float scale, int f16, cudaStream_t s, int out_bf16 = 0);
 // general form: q [B*Lq, ldq] / k / v [.., ld] bf16 matrices (head h at columns [h*64, h*64+64) from the given base pointer);
 // image b's queries start at row b*Lq, its keys/values at row b*kv_rows + kv_row0.  Lq <= 128, Lk <= 256.
 // out: [B*Lq, ldo], fp32 when out_f32 else bf16.

@@ -886,14 +886,17 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
           if (small_attn) SMK_PROPAGATE(attention_small((const __nv_bfloat16*)cq32, D, kl, ldkv, kl + D, ldkv, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s, 1, 1));
           else {
             SMK_PROPAGATE(cast_f16(cq32, (__half*)cq_b, (int64_t)R * D, s));
-            SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s, 1));
+            // 384 x 384: 576 memory keys → the multi-key-tile tcgen05 kernel (fp16 operands, bf16 [hi | hi | lo] output)
+            if (multi_attn && hw >= 176) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 1, s, 1));
+            else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s, 1));
           }
         } else {
           SMK_PROPAGATE(gemm3(a3b, d3.caqw, w + d.cab, cq_b, D, R, D, D, SMK_EPI_NONE, 0));
           TagScope tg(TAG_DEC_ATTN);
           if (small_attn) SMK_PROPAGATE(attention_small(cq_b, D, kl, ldkv, kl + D, ldkv, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
           else if (hw <= 256) SMK_PROPAGATE(attention_tc_general(cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)nb * N, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
-          else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));   // 384x384: 576 memory keys
+          else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 0, s));   // 384x384: 576 memory keys
+          else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
         }
         if (!xa) SMK_PROPAGATE(gemm3(a3c, d3.caow, w + d.caob, t2, D, R, D, D, SMK_EPI_NONE, 1));
         { TagScope tg(TAG_DEC_LN); SMK_PROPAGATE(dec_layernorm(tgt, t2, w + d.n2w, w + d.n2b, 1e-5f, nullptr, 0, a3a, nullptr, nullptr, nullptr, nullptr, nullptr, R, D, s)); }

@@ -517,6 +517,32 @@ def test_gemm_split_terms_match_fp64(M_, N, K, epi, terms, out_kind, f16):
         assert (got - full).abs().max().item() <= (2e-4 if f16 else 6e-4) * scale
 
 
+@pytest.mark.parametrize("f16,Lk", [(1, 576), (0, 576), (1, 784), (0, 200)])
+def test_attention_tcgen05_multi_tile_decoder_cross_layout(f16, Lk):
+    """Decoder cross-attention at 384 x 384 / ViT-S/8 on the multi-key-tile kernel: 20 queries per image against the patch tokens of the
+    all-layer K/V tensor (row stride L·2·D, cls row skipped); fp16 operands write bf16 [hi | hi | lo] parts (out_mode | 8)."""
+    torch.manual_seed(47)
+    B, nq, H, dh, L = 5, 20, 6, 64, 6
+    D = H * dh
+    N = Lk + 1
+    dt = torch.float16 if f16 else torch.bfloat16
+    q = (torch.randn(B * nq, D, device=DEV) * 1.5).to(dt)
+    kv = (torch.randn(B * N, L * 2 * D, device=DEV) * 1.5).to(dt)
+    layer = 3
+    kl = kv[:, layer * 2 * D:]
+    out = torch.full((B * nq, 3 * D), 7.0, device=DEV, dtype=torch.bfloat16 if f16 else dt)
+    check(lib().smk_attention_tc_multi(ptr(q), D, ptr(kl), L * 2 * D, ptr(kl[:, D:]), L * 2 * D, B * nq, B * N, nq, N, 1, ptr(out), 3 * D,
+                                       2 | (8 if f16 else 0), B, nq, Lk, H, 0.125, f16, stream_ptr()), "smk_attention_tc_multi")
+    torch.cuda.synchronize()
+    k = kv.view(B, N, L * 2 * D)[:, 1:, layer * 2 * D:layer * 2 * D + D].double().reshape(B, Lk, H, dh).transpose(1, 2)
+    v = kv.view(B, N, L * 2 * D)[:, 1:, layer * 2 * D + D:layer * 2 * D + 2 * D].double().reshape(B, Lk, H, dh).transpose(1, 2)
+    qq = q.double().view(B, nq, H, dh).transpose(1, 2)
+    ref = (torch.softmax(qq @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * nq, D)
+    assert torch.equal(out[:, :D], out[:, D:2 * D])
+    got = out[:, :D].double() + out[:, 2 * D:].double()
+    assert (got - ref).abs().max().item() <= (5e-3 if f16 else 0.04)
+
+
 def _q8(t):
     return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).double()
 
