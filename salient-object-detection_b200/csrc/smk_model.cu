@@ -626,6 +626,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
   const __nv_bfloat16* wb = m->wb;
   const float scale = 0.125f;   // head_dim^-0.5, head_dim = 64
   static const bool multi_attn = !(getenv("SMK_ATTN_MULTI") && atoi(getenv("SMK_ATTN_MULTI")) == 0);   // 0: mma.sync fallback for N > 256 (A/B runs)
+  static const bool xattn_multi = getenv("SMK_XATTN_MULTI") && atoi(getenv("SMK_XATTN_MULTI")) != 0;    // decoder cross-attention at > 256 keys on the multi-tile kernel
   m->last_B = B;
 
   // fp32 validation mode: CUDA-core GEMM.  bf16x3 mode: the same call sites run on tcgen05 — A is split into
@@ -886,8 +887,10 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
           if (small_attn) SMK_PROPAGATE(attention_small((const __nv_bfloat16*)cq32, D, kl, ldkv, kl + D, ldkv, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s, 1, 1));
           else {
             SMK_PROPAGATE(cast_f16(cq32, (__half*)cq_b, (int64_t)R * D, s));
-            // 384 x 384: 576 memory keys → the multi-key-tile tcgen05 kernel (fp16 operands, bf16 [hi | hi | lo] output)
-            if (multi_attn && hw >= 176) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 1, s, 1));
+            // 384 x 384: 576 memory keys.  The multi-key-tile tcgen05 kernel serves this layout too (attention_tc_multi(..., out_bf16 = 1),
+            // tests/test_gpu_kernels.py) but a 256-row query group holds only nq = 20 valid rows per (image, head): measured 43 us per launch
+            // against 25 us for the 2-warp online-softmax kernel at B = 128 — SMK_XATTN_MULTI=1 selects it
+            if (xattn_multi && hw >= 176) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 1, s, 1));
             else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s, 1));
           }
         } else {
@@ -895,7 +898,7 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
           TagScope tg(TAG_DEC_ATTN);
           if (small_attn) SMK_PROPAGATE(attention_small(cq_b, D, kl, ldkv, kl + D, ldkv, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
           else if (hw <= 256) SMK_PROPAGATE(attention_tc_general(cq_b, D, kl, ldkv, kl + D, ldkv, (int64_t)nb * N, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
-          else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 0, s));   // 384x384: 576 memory keys
+          else if (xattn_multi) SMK_PROPAGATE(attention_tc_multi(cq_b, D, kl, ldkv, kl + D, ldkv, R, (int64_t)nb * N, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, 0, s));   // 384x384: 576 memory keys
           else SMK_PROPAGATE(attention_fa(cq_b, nullptr, D, kl, nullptr, ldkv, kl + D, nullptr, ldkv, nq, N, 1, a3c, 3 * D, 2, nb, nq, hw, c.heads, scale, s));
         }
         if (!xa) SMK_PROPAGATE(gemm3(a3c, d3.caow, w + d.caob, t2, D, R, D, D, SMK_EPI_NONE, 1));
