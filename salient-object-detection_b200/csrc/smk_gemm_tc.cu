@@ -170,7 +170,9 @@ __device__ __forceinline__ TileCoord tile_coord(const TcGemmParams& p, int tile,
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
 // M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
 // the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
-template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
+// kQ8 (fp16 only): the fp8-corrected form (TcGemmParams::q8) and the [hi | e4m3] output kind 4 — a separate instantiation, so that the
+// issue loop and the epilogue of every other GEMM stay exactly as they were (the run-time branches cost qkv 79 → 88 us)
+template <int BN, bool kDirect, int kCtas, int kEW, bool kF16, bool kQ8>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const TcGemmParams p) {
@@ -296,7 +298,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int pr = 0; pr < n_pr; ++pr) {
             const uint64_t a_desc = smem_desc_k_sw128(sa + (uint32_t)((p.seq ? 0 : sel3(pr, pa0, pa1, pa2)) * Cfg::kABytes));
             const uint64_t b_desc = smem_desc_k_sw128(sb + (uint32_t)((p.seq ? 0 : sel3(pr, pw0, pw1, pw2)) * Cfg::kBBytes));
-            if (kF16 && p.q8 && kb <= kpt) {
+            if (kQ8 && kb <= kpt) {
               if (kb < kpt) {           // fp8 tiles: four K = 32 products per 128-byte row
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -478,7 +480,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             const uint32_t srow = stg_u32 + lane * 64;
-            if (kF16 && p.out_f32 == 4) {
+            if (kQ8 && p.out_f32 == 4) {
               // [hi | e4m3 correction operands]: the second 64-byte box holds e4m3(hi) (32 B) and e4m3(lo·2^11) (32 B) of the 32 columns
               uint32_t f8[8], s8[8];
 #pragma unroll
@@ -654,12 +656,12 @@ static int set_terms(TcGemmParams& p, const GemmTerms& tr, bool swap) {
   return SMK_OK;
 }
 
-template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p_in, cudaStream_t s) {
+template <int BN, bool kDirect, int kCtas, int kEW, bool kF16, bool kQ8>
+static int launch_tc_q(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p_in, cudaStream_t s) {
   using Cfg = TcCfg<BN, kCtas, kEW>;
   static DeviceOnce attr_set;
   if (attr_set.first()) {
-    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16, kQ8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
   }
   TcGemmParams p = p_in;
@@ -704,10 +706,19 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     // credited work = ALGORITHMIC FLOPs of the contraction (one term; p.credit_k is the mathematical reduction length), whatever
     // number of split terms the tensor core is issued
     ProfScope prof(PROF_GEMM_TC, p.credit_flops > 0 ? p.credit_flops : 2.0 * p.M * p.N * p.credit_k, s, 2.0 * p.M * p.N * p.K * (p.q8 ? 3 : p.n_terms));
-    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16>, ta, tb, tcm, p));
+    SMK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, kDirect, kCtas, kEW, kF16, kQ8>, ta, tb, tcm, p));
   }
   SMK_CHECK_LAUNCH();
   return SMK_OK;
+}
+
+template <int BN, bool kDirect, int kCtas, int kEW, bool kF16>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
+  if constexpr (kF16 && kEW == 8) {
+    if (p.q8) return launch_tc_q<BN, kDirect, kCtas, kEW, kF16, true>(ta, tb, tcm, p, s);
+  }
+  SMK_REQUIRE(!p.q8 && p.out_f32 != 4, "gemm_tc: the fp8-corrected form / [hi | e4m3] output needs fp16 operands, q8 terms and 8 epilogue warps");
+  return launch_tc_q<BN, kDirect, kCtas, kEW, kF16, false>(ta, tb, tcm, p, s);
 }
 
 // Tile width: minimise (waves over the SMs) x (BN + 64): measured, a k-block of MMAs costs a fixed part plus a part
@@ -789,7 +800,7 @@ static bool use_epi16(const TcGemmParams& p) {
 template <bool kDirect, int kCtas, bool kF16>
 static int launch_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const TcGemmParams& p, cudaStream_t s) {
   if constexpr (!kDirect) {
-    if (BN == 256 && use_epi16(p)) return launch_tc<256, false, kCtas, 16, kF16>(ta, tb, tcm, p, s);
+    if (BN == 256 && !p.q8 && use_epi16(p)) return launch_tc<256, false, kCtas, 16, kF16>(ta, tb, tcm, p, s);
   }
   return BN == 256 ? launch_tc<256, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s)
                    : (BN == 192 ? launch_tc<192, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s) : launch_tc<128, kDirect, kCtas, 8, kF16>(ta, tb, tcm, p, s));
