@@ -773,17 +773,20 @@ static bool use_swap_ab(int M, int N, int K) {
 }
 
 // swap-AB for 16-bit outputs whose width is not a multiple of 256 (qkv: 1152 = 9 x 128 features → every MMA 128 x 256 over tokens
-// instead of 128 x 192; 1773 tiles = 11.98 waves of 148).  OFF unless SMK_GEMM_SWAP_AB=1: measured on B200 qkv 48.4 / 48.5 us in
-// the normal form vs 49.5 / 49.3 us swapped — qkv is paced by its epilogue (TMEM read + pack + stores of 116 MB), not by the MMA
-// width, and the transposed store costs one 2-byte st.shared per element.  Never for GELU epilogues (fc1).
-static bool use_swap_ab_bf16(int M, int N, int epi) {
+// instead of 128 x 192; 1773 tiles = 11.98 waves of 148).  Single-term bf16 (round 1): 48.4 us normal vs 49.5 us swapped — paced by its
+// epilogue, and the transposed store costs one 2-byte st.shared per element: off.  With split terms the k loop streams 64 KB of
+// operands per k-block either way, so the wider tile is 25 % fewer bytes per FLOP into the SM: the fp16s qkv (A_hi·(W_hi + W_lo))
+// measures 87.5 → 71.0 us swapped (scripts/gemm_q8_bench.py --only qkv; CTA pairs: 83.3 us): ON for multi-term products.
+// SMK_GEMM_SWAP_AB = 0 / 1 forces.  Never for GELU epilogues (fc1).
+static bool use_swap_ab_bf16(int M, int N, int epi, int n_terms) {
   static int mode = -2;
   if (mode == -2) {
     const char* e = getenv("SMK_GEMM_SWAP_AB");
     mode = e ? atoi(e) : -1;
   }
   if (N % TC_BM != 0 || (epi & SMK_EPI_GELU)) return false;
-  return mode == 1 && N % 256 != 0 && M >= 16384;
+  if (N % 256 == 0 || M < 16384) return false;
+  return mode >= 0 ? mode == 1 : n_terms >= 2;
 }
 
 // 16 epilogue warps: 16-bit-output 256-column tiles of many-row problems (fc1, memory K/V); SMK_GEMM_EPI16 = 0 / 1 overrides (tuning)
@@ -842,7 +845,7 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
   p.q8 = tr.q8;
   SMK_REQUIRE(!tr.q8 || (kF16 && tr.n == 2 && tr.a_off[0] == K && tr.w_off[0] == K && tr.a_off[1] == 0 && tr.w_off[1] == 0),
               "gemm_tc: fp8 correction terms need fp16 operands and the terms_q8 layout");
-  if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, Ktot)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi)))) {
+  if (tok_hw == 0 && ((out_f32 == 1 && use_swap_ab(M, N, Ktot)) || (out_f32 == 0 && use_swap_ab_bf16(M, N, epi, tr.n)))) {
     // C^T = W · A^T: kernel M axis = output features (N), kernel N axis = tokens (M); see TcGemmParams::trans
     CUtensorMap ta, tb, tcm;
     SMK_PROPAGATE(make_tmap_bf16_2d(&ta, W, (uint64_t)w_cols, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, TC_BM));

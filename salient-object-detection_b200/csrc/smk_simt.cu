@@ -17,7 +17,7 @@ namespace smk {
 constexpr int LN_ROWS = 2;   // rows per warp, all loads issued before the first reduction (bytes in flight: the kernel is HBM-bound)
 
 template <typename TOut, int kChunks>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kChunks <= 3 ? 4 : 1)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
                  const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
                  TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */,

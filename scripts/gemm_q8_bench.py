@@ -59,6 +59,20 @@ def case(name, N, K, epi, kind3, kind8, Mrows=None):
 
 CASES = {"pe": (384, 768, 0, 1, 1, args.batch * 196), "proj": (384, 384, 4, 1, 1, None), "fc1": (1536, 384, 1, 3, 4, None),
          "fc1p": (1536, 384, 1, 0, 0, None), "fc2": (384, 1536, 4, 1, 1, None)}
+def qkv_case():
+    """qkv of the fp16s mode: A_hi·(W_hi + W_lo), fp16 output (not a q8 contraction)."""
+    N, K, nbuf = 1152, 384, 4
+    A = [torch.randn(M, K, device=dev).to(torch.float16) * 0.01 for _ in range(nbuf)]
+    W = (torch.randn(N, 2 * K, device=dev) * 0.01).to(torch.float16)
+    bias = torch.randn(N, device=dev)
+    o = [torch.zeros(M, N, device=dev, dtype=torch.float16) for _ in range(nbuf)]
+    ao, wo = (C.c_int32 * 3)(0, 0, 0), (C.c_int32 * 3)(0, K, 0)
+    t = timeit(lambda i: check(lib().smk_gemm_split(ptr(A[i]), K, ptr(W), 2 * K, ptr(bias), ptr(o[i]), N, M, N, K, 0, 0, 1, 2, ao, wo, stream_ptr()), "qkv"), nbuf)
+    print(f"qkv    M={M} N={N:5d} K={K:5d}: 2-term fp16 {t:7.1f} us ({2.0 * M * N * K / 1e6 / t:6.1f} TF/s algorithmic)")
+
+
+if not args.only or "qkv" in args.only.split(","):
+    qkv_case()
 for nm, (N, K, epi, k3, k8, mr) in CASES.items():
     if not args.only or nm in args.only.split(","):
         case(nm, N, K, epi, k3, k8, mr)
