@@ -202,6 +202,11 @@ int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, const
  * operand of the next smk_gemm_q8).  K % 64 == 0, N % 128 == 0. */
 int smk_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
                 int epilogue, int out_kind, void* stream);
+/* Patch-embed form of the GEMM (vision_transformer.py:184-188, :269-287): C is [n_img, hw + 1, N] token rows (row stride ldc); GEMM row m =
+ * patch m % hw of image m / hw is written to token row 1 + m % hw with pos[1 + m % hw, :] (pos [hw + 1, N] fp32) and the bias added;
+ * the class-token rows are not touched.  A [n_img*hw, lda], W [N, ldw]: bf16 (f16 = 0), fp16 (1) or smk_split_q8 rows (2). */
+int smk_gemm_tokens(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* pos, float* C, int64_t ldc,
+                    int n_img, int hw, int N, int K, int f16, void* stream);
 /* x [rows, ldx] fp32 → out [rows, 2K fp16 columns]: [hi fp16 (K) | per 32 columns 32 bytes "first" + 32 bytes "second" of e4m3];
  * activations (is_weight == 0): first = e4m3(hi), second = e4m3(lo·2^11); weights: first = e4m3(lo·2^15), second = e4m3(hi·2^4). */
 int smk_split_q8(const float* x, int64_t ldx, void* out, int64_t rows, int K, int is_weight, void* stream);

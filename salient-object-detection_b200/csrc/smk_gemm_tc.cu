@@ -166,7 +166,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcGemmParams& p, int tile,
   return t;
 }
 
-// kDirect: per-thread row stores straight to global memory (row re-indexing of the patch-embed GEMM; C tensor map unused)
+// kDirect: token assembly of the patch-embed GEMM (row re-indexing around the class-token rows + position embedding, 3-D output map)
 // kCtas = 2: CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, MMAs issued by the even CTA with
 // M = 256; each CTA loads its own 128 rows of A and BN/2 rows of B, which halves the B bytes every SM pulls from L2 —
 // the single-CTA kernel is bound by L2→SM bandwidth (BM·BN/(BM+BN) FLOP per operand byte: 64 at BN=128, 85 at 256).
@@ -208,7 +208,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (!kDirect) tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEW * kCtas); }
     fence_barrier_init();
@@ -420,17 +420,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if constexpr (kDirect) {
-          if (m < p.M) {
-            const int64_t out_row = (int64_t)m + m / p.tok_hw + 1;
-            const float* pos_row = p.tok_pos + (int64_t)(1 + m % p.tok_hw) * p.N;
+          // token assembly (patch embed): tiles are per IMAGE (batched form: tile rows = patches of one image, the rows past its hw
+          // patches compute the next image's and are clipped), so a 32-row chunk never crosses an image: patch r of image b → token row
+          // 1 + r (row 0 is the class token) through a 3-D map {column, patch, image} based at token row 1; position embedding added
+          // here.  (A flat tiling with one store per image touched needs NEGATIVE start coordinates for the second image: the TMA store
+          // raises an illegal-instruction fault on those.)
+          const int r_first = tc_.c_row + quarter * 32;
+          {
+            const int r = r_first + lane < p.tok_hw ? r_first + lane : p.tok_hw - 1;
+            const float* pos_row = p.tok_pos + (int64_t)(1 + r) * p.N;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
-            float* crow = reinterpret_cast<float*>(p.C) + out_row * p.ldc + n0;
+          }
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          const uint32_t srow = stg_u32 + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(srow + ((j ^ (lane & 7)) << 4), r4(v[4 * j]), r4(v[4 * j + 1]), r4(v[4 * j + 2]), r4(v[4 * j + 3]));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && r_first < p.tok_hw) {
+            tma_store_3d(&tmC, stg, n0, r_first, tc_.batch);
+            bulk_commit();
           }
         } else {
           const int row0 = m_blk * TC_BM + quarter * 32;
@@ -564,7 +579,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     w_all.end();
-    if (!kDirect && lane == 0) bulk_wait<0>();   // all tile stores complete before the CTA retires
+    if (lane == 0) bulk_wait<0>();   // all tile stores complete before the CTA retires
     if (tr_w) { trace[5] = w_tm.acc; trace[6] = w_stg.acc; trace[7] = w_all.acc; trace[8] = n_tiles_done; trace[9] = w_ld.acc; trace[10] = w_st.acc; }
   }
   tc_fence_before_sync();
@@ -859,12 +874,21 @@ static int gemm_tc_impl(const void* A, int64_t lda, const void* W, int64_t ldw, 
   const bool pair = tok_hw == 0 && use_cta_pair(M, K * tr.n);
   const int kc = pair ? 2 : 1;
   int BN = pick_bn(M, N, TC_BM * kc, num_sms() / kc);
-  if (tok_hw > 0 && !getenv("SMK_GEMM_BN")) BN = 128;   // direct-store epilogue (patch embed): per-thread row stores favour narrow tiles (78 vs 82 us)
+  if (tok_hw > 0) BN = pick_bn(((M / tok_hw) * ((tok_hw + TC_BM - 1) / TC_BM)) * TC_BM, N, TC_BM, num_sms());
   CUtensorMap ta, tb, tcm;
   SMK_PROPAGATE(make_tmap_bf16_2d(&ta, A, (uint64_t)a_cols, (uint64_t)M, (uint64_t)lda * 2, TC_BK, TC_BM));
   SMK_PROPAGATE(make_tmap_bf16_2d(&tb, W, (uint64_t)w_cols, (uint64_t)N, (uint64_t)ldw * 2, TC_BK, (uint32_t)(BN / kc)));
   if (tok_hw > 0) {
-    tcm = ta;   // unused by the direct-store epilogue
+    SMK_REQUIRE(M % tok_hw == 0, "gemm_tc: token assembly needs whole images (M %% hw == 0)");
+    // per-image tiles: ceil(hw / 128) m-blocks per image, A rows of image b from row b·hw (batched form, weights shared)
+    const int n_img = M / tok_hw, mb = (tok_hw + TC_BM - 1) / TC_BM;
+    p.mb_per_batch = mb; p.batch_a_rows = tok_hw; p.a_row0 = 0; p.batch_b_rows = 0; p.b_row0 = 0;
+    p.M = n_img * mb * TC_BM;
+    p.credit_flops = 2.0 * M * N * p.credit_k;
+    const uint64_t dims[3] = {(uint64_t)N, (uint64_t)tok_hw, (uint64_t)(M / tok_hw)};
+    const uint64_t strides[2] = {(uint64_t)ldc * 4, (uint64_t)(tok_hw + 1) * ldc * 4};
+    const uint32_t box[3] = {32u, 32u, 1u};
+    SMK_PROPAGATE(make_tmap_nd(&tcm, 4, (float*)C + ldc, 3, dims, strides, box, 128));     // based at token row 1 of image 0
     return launch_bn<true, 1, kF16>(BN, ta, tb, tcm, p, s);
   }
   // output tiles of 32 rows x 32 columns per epilogue warp: 128 B (fp32, 128-byte swizzle) or 64 B (16-bit, 64-byte swizzle) per row
@@ -967,6 +991,16 @@ extern "C" int smk_gemm_split(const void* A, int64_t lda, const void* W, int64_t
   smk::GemmTerms t{n_terms, {0, 0, 0}, {0, 0, 0}};
   for (int i = 0; i < n_terms; ++i) { t.a_off[i] = a_off[i]; t.w_off[i] = w_off[i]; }
   return smk::gemm_tc(A, lda, W, ldw, bias, C, ldc, M, N, K, epilogue, out_kind, 0, nullptr, f16, t, 0, (cudaStream_t)stream);
+}
+
+// Patch-embed form (vision_transformer.py:184-188 + prepare_tokens :269-287): C viewed as [n_img, hw + 1, N] token rows; GEMM row m = patch
+// m % hw of image m / hw lands on token row 1 + m % hw with pos[(1 + m % hw), :] added (row 0, the class token, is not written).
+// A [n_img*hw, lda], W [N, ldw]: bf16, fp16 (f16 = 1) or the q8 split rows (f16 = 2).
+extern "C" int smk_gemm_tokens(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* pos, float* C, int64_t ldc,
+                               int n_img, int hw, int N, int K, int f16, void* stream) {
+  SMK_REQUIRE(A && W && C && pos && n_img >= 0 && hw > 0 && N > 0 && K > 0, "smk_gemm_tokens: bad arguments");
+  return smk::gemm_tc(A, lda, W, ldw, bias, C, ldc, n_img * hw, N, K, SMK_EPI_NONE, 1, hw, pos, f16 != 0, f16 == 2 ? smk::terms_q8(K) : smk::terms_plain(), 0,
+                      (cudaStream_t)stream);
 }
 
 extern "C" int smk_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,

@@ -71,8 +71,21 @@ def qkv_case():
     print(f"qkv    M={M} N={N:5d} K={K:5d}: 2-term fp16 {t:7.1f} us ({2.0 * M * N * K / 1e6 / t:6.1f} TF/s algorithmic)")
 
 
+def pe_tokens_case():
+    """patch embed with token assembly (per-image tiles, position embedding, 3-D output map), fp8-corrected operands."""
+    n_img, hw, N, K, nbuf = args.batch, 196, 384, 768, 4
+    A = [torch.randn(n_img * hw, 2 * K, device=dev).to(torch.float16) * 0.01 for _ in range(nbuf)]
+    W = (torch.randn(N, 2 * K, device=dev) * 0.01).to(torch.float16)
+    bias, pos = torch.randn(N, device=dev), torch.randn(hw + 1, N, device=dev)
+    o = [torch.zeros(n_img, hw + 1, N, device=dev) for _ in range(nbuf)]
+    t = timeit(lambda i: check(lib().smk_gemm_tokens(ptr(A[i]), 2 * K, ptr(W), 2 * K, ptr(bias), ptr(pos), ptr(o[i]), N, n_img, hw, N, K, 2, stream_ptr()), "pe"), nbuf)
+    print(f"pe_tok M={n_img * hw} N={N:5d} K={K:5d}: fp8-corrected, token assembly {t:7.1f} us ({2.0 * n_img * hw * N * K / 1e6 / t:6.1f} TF/s algorithmic)")
+
+
 if not args.only or "qkv" in args.only.split(","):
     qkv_case()
+if not args.only or "pe_tok" in args.only.split(","):
+    pe_tokens_case()
 for nm, (N, K, epi, k3, k8, mr) in CASES.items():
     if not args.only or nm in args.only.split(","):
         case(nm, N, K, epi, k3, k8, mr)

@@ -543,6 +543,35 @@ def test_attention_tcgen05_multi_tile_decoder_cross_layout(f16, Lk):
     assert (got - ref).abs().max().item() <= (5e-3 if f16 else 0.04)
 
 
+@pytest.mark.parametrize("n_img,hw,f16", [(1, 64, 0), (2, 64, 1), (3, 196, 0), (8, 196, 2), (5, 156, 1), (40, 9, 0), (2, 576, 2), (256, 196, 2)])
+def test_gemm_token_assembly(n_img, hw, f16):
+    """Patch-embed form: rows re-indexed around the class-token rows (3-D output map, chunks that cross image boundaries are stored once
+    per image), position embedding + bias added, class-token rows untouched.  bf16 / fp16 / fp8-corrected operands; hw smaller than a
+    32-row chunk (several images per chunk), multiples of 32 (no crossing) and the 224 / 384 geometries."""
+    torch.manual_seed(48)
+    N, K = 384, 192
+    A32 = torch.randn(n_img * hw, K, device=DEV)
+    W32 = torch.randn(N, K, device=DEV) * 0.05
+    bias = torch.randn(N, device=DEV)
+    pos = torch.randn(hw + 1, N, device=DEV)
+    if f16 == 2:
+        A = torch.zeros(n_img * hw, 2 * K, dtype=torch.float16, device=DEV)
+        W = torch.zeros(N, 2 * K, dtype=torch.float16, device=DEV)
+        check(lib().smk_split_q8(ptr(A32), K, ptr(A), n_img * hw, K, 0, stream_ptr()))
+        check(lib().smk_split_q8(ptr(W32), K, ptr(W), N, K, 1, stream_ptr()))
+        ld, Aeff, Weff = 2 * K, A32.double(), W32.double()
+    else:
+        dt = torch.float16 if f16 else torch.bfloat16
+        A, W = A32.to(dt), W32.to(dt)
+        ld, Aeff, Weff = K, A.double(), W.double()
+    Cc = torch.full((n_img, hw + 1, N), 7.0, device=DEV)
+    check(lib().smk_gemm_tokens(ptr(A), ld, ptr(W), ld, ptr(bias), ptr(pos), ptr(Cc), N, n_img, hw, N, K, f16, stream_ptr()), "smk_gemm_tokens")
+    torch.cuda.synchronize()
+    ref = (Aeff @ Weff.t() + bias.double()).view(n_img, hw, N) + pos[1:].double()[None]
+    assert torch.equal(Cc[:, 0], torch.full((n_img, N), 7.0, device=DEV))            # class-token rows untouched
+    assert (Cc[:, 1:].double() - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def _q8(t):
     return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).double()
 
