@@ -565,40 +565,54 @@ im2col_split_kernel(const TIn* __restrict__ x, __half* __restrict__ cols, int H,
   const int Wp = wp * P, ws = Wp + 4;
   const TIn* src = x + (int64_t)b * 3 * H * W;
   const int Wq = Wp >> 2;
-  for (int i = threadIdx.x; i < 3 * P * Wq; i += 256) {
-    const int r = i / Wq, xx = (i - r * Wq) << 2, c = r / P, ky = r - c * P, yy = py * P + ky;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (yy < H) {
-      const TIn* row = src + ((int64_t)c * H + yy) * W;
-      if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, lut, v);
-      else {
+  // index arithmetic is incremental (one division per thread, not per element): the kernel is instruction-bound, not HBM-bound
+  {
+    int r = threadIdx.x / Wq, xq = threadIdx.x - r * Wq;
+    const int rstep = 256 / Wq, xstep = 256 - rstep * Wq;
+    while (r < 3 * P) {
+      const int xx = xq << 2, c = r / P, ky = r - c * P, yy = py * P + ky;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (yy < H) {
+        const TIn* row = src + ((int64_t)c * H + yy) * W;
+        if (vec_ok && xx + 3 < W) load_pixels4<TIn>(row + xx, c, lut, v);
+        else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, lut);
+          for (int e = 0; e < 4; ++e)
+            if (xx + e < W) v[e] = load_pixel<TIn>(row + xx + e, c, lut);
+        }
       }
+      store4(strip + r * ws + xx, v);
+      xq += xstep; r += rstep;
+      if (xq >= Wq) { xq -= Wq; ++r; }
     }
-    store4(strip + r * ws + xx, v);
   }
   __syncthreads();
   const int K = 3 * P * P, vec_per_row = P / 4, vec_per_patch = K / 4;
+  const bool vpow2 = (vec_per_row & (vec_per_row - 1)) == 0;
+  const int vshift = __popc(vec_per_row - 1);
   __half* dst = cols + ((int64_t)b * hp + py) * wp * 2 * K;
-  for (int i = threadIdx.x; i < wp * vec_per_patch; i += 256) {
-    const int px = i / vec_per_patch, j = i - px * vec_per_patch;     // j = (c*P + ky) * vec_per_row + kxv
-    const int r = j / vec_per_row, kxv = j - r * vec_per_row;
-    const float4 v = *reinterpret_cast<const float4*>(strip + r * ws + px * P + kxv * 4);
-    uint2 hi, lo;
-    __half* o = dst + (int64_t)px * 2 * K;
-    if (q8) {
-      split_q8x4<false>(v.x, v.y, v.z, v.w, hi, lo.x, lo.y);
-      uint8_t* q = reinterpret_cast<uint8_t*>(o + K) + q8_byte_off(j * 4);
-      *reinterpret_cast<uint2*>(o + j * 4) = hi;
-      *reinterpret_cast<uint32_t*>(q) = lo.x;
-      *reinterpret_cast<uint32_t*>(q + 32) = lo.y;
-    } else {
-      split16x2<__half>(v.x, v.y, hi.x, lo.x);
-      split16x2<__half>(v.z, v.w, hi.y, lo.y);
-      *reinterpret_cast<uint2*>(o + j * 4) = hi;
-      *reinterpret_cast<uint2*>(o + K + j * 4) = lo;
+  {
+    int px = threadIdx.x / vec_per_patch, j = threadIdx.x - px * vec_per_patch;      // j = (c*P + ky) * vec_per_row + kxv
+    const int pstep = 256 / vec_per_patch, jstep = 256 - pstep * vec_per_patch;
+    while (px < wp) {
+      const int r = vpow2 ? j >> vshift : j / vec_per_row, kxv = j - r * vec_per_row;
+      const float4 v = *reinterpret_cast<const float4*>(strip + r * ws + px * P + kxv * 4);
+      uint2 hi, lo;
+      __half* o = dst + (int64_t)px * 2 * K;
+      if (q8) {
+        split_q8x4<false>(v.x, v.y, v.z, v.w, hi, lo.x, lo.y);
+        uint8_t* q = reinterpret_cast<uint8_t*>(o + K) + q8_byte_off(j * 4);
+        *reinterpret_cast<uint2*>(o + j * 4) = hi;
+        *reinterpret_cast<uint32_t*>(q) = lo.x;
+        *reinterpret_cast<uint32_t*>(q + 32) = lo.y;
+      } else {
+        split16x2<__half>(v.x, v.y, hi.x, lo.x);
+        split16x2<__half>(v.z, v.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(o + j * 4) = hi;
+        *reinterpret_cast<uint2*>(o + K + j * 4) = lo;
+      }
+      j += jstep; px += pstep;
+      if (j >= vec_per_patch) { j -= vec_per_patch; ++px; }
     }
   }
 }
