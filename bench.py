@@ -218,7 +218,7 @@ def workload_config(args, **extra):
 
 TAG_NAMES = ["other", "patch_embed", "qkv", "attention", "proj", "fc1", "fc2", "layernorm", "memory_kv", "decoder_gemm", "decoder_attention",
              "decoder_layernorm", "mask_logits", "mask_upsample", "objectness", "eval_query_iou", "eval_mask_metrics", "im2col"]
-TENSOR_TAGS = {1, 2, 3, 4, 5, 6, 8, 9, 10, 14}      # rows whose yardstick is the tensor pipe; the rest are HBM rows
+TENSOR_TAGS = {1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 14}  # rows whose yardstick is the tensor pipe (12: the mask-logit contraction, a batched tcgen05 GEMM since round 2); the rest are HBM rows
 
 
 def per_kernel_rows(lib, C, step, n_prof, pk, ms_plain):
