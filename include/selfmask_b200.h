@@ -31,7 +31,9 @@
  *   smk_upsample_sigmoid / smk_hist_metrics / smk_smeasure → fused in smk_eval_batch (x4 upsample + every metric reduction in two
  *                                                     launches) and, for one full-resolution mask, smk_mask_metrics; the upsample alone
  *                                                     is smk_upsample_bilinear
- *   smk_layernorm, smk_gemm_*, smk_attention*       → exported as sketched
+ *   smk_layernorm, smk_gemm_*, smk_attention*       → exported as sketched (smk_gemm_tokens = the patch-embed form with token assembly,
+ *                                                     smk_gemm_q8 / smk_split_q8 = the fp8-corrected split form and its operand layout,
+ *                                                     smk_attention_tc_multi = attention beyond one key tile)
  *
  * Threading contract: one host thread drives a device at a time.  Per-device one-time state (kernel attributes, SM count, the
  * persisting-L2 carve-out) is keyed by the CUDA device ordinal, so one process may use several GPUs in turn; two host threads on
@@ -61,9 +63,10 @@ enum { SMK_MODE_FP32 = 0,  /* validation: every contraction in fp32 on CUDA core
        SMK_MODE_BF16X3 = 2,/* parity on tensor cores: every GEMM as a 3-term bf16 split (hi·hi + hi·lo + lo·hi, K' = 3K) on
                               tcgen05 with fp32 accumulate; LayerNorm / softmax attention / residual in fp32 */
        SMK_MODE_FP16S = 3  /* parity AND throughput (the benchmarked mode): fp16 tcgen05 operands with as many split terms per
-                              contraction as the 2e-2 logit budget needs (patch embed / proj / fc1 / fc2: 3 terms on [hi | lo] operands;
-                              qkv, memory K/V: A_hi·(W_hi + W_lo); encoder attention: single-pass fp16 on tcgen05; decoder self-attention
-                              fp32; decoder tail as in SMK_MODE_BF16), fp32 accumulate / residual / LayerNorm / softmax */ };
+                              contraction as the 2e-2 logit budget needs (patch embed / proj / fc1 / fc2: hi·hi in fp16 + the two correction
+                              products hi·lo + lo·hi on e4m3 operands at the fp8 tensor rate, smk_gemm_q8; qkv, memory K/V: A_hi·(W_hi + W_lo);
+                              encoder attention: single-pass fp16 on tcgen05; decoder self-attention fp32; decoder tail as in
+                              SMK_MODE_BF16), fp32 accumulate / residual / LayerNorm / softmax */ };
 
 typedef struct {
   int32_t patch;        /* 16 (or 8)                                    */
