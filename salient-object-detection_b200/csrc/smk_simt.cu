@@ -14,10 +14,11 @@ namespace smk {
 // One warp per row; the row lives in registers (D <= 1024, D % 128 == 0); optional residual input and
 // optional second (fp32) output so that bf16-mode callers get both copies in one pass.
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_ROWS = 2;   // rows per warp, all loads issued before the first reduction (bytes in flight: the kernel is HBM-bound)
+constexpr int LN_ROWS = 1;   // rows per warp.  Measured in the fp16s step (us per launch, event-timed): 2 rows / 3 CTAs per SM 32.6, 2 / 4 31.3,
+                             // 4 / 3 35.0, 1 / 8 (32 registers, spills) 33.2, **1 / 6 (40 registers) 29.8**: latency-bound, not bandwidth-bound
 
 template <typename TOut, int kChunks>
-__global__ void __launch_bounds__(256, kChunks <= 3 ? 4 : 1)
+__global__ void __launch_bounds__(256, kChunks <= 3 ? 6 : 1)
 layernorm_kernel(const float* x /* may alias y: a row is fully read before it is written */, const float* __restrict__ res,
                  const float* __restrict__ gamma, const float* __restrict__ beta, TOut* y, float* __restrict__ y32, float* sum_out,
                  TOut* __restrict__ y_lo /* bf16 only: rounding residue of y, so that y + y_lo ≈ the fp32 row */,
