@@ -223,6 +223,15 @@ int smk_gemm_batched(const void* A, int64_t lda, int64_t a_total_rows, int batch
 /* y = LN(x) * gamma + beta over the last dim D (fp32 statistics).  out_bf16 selects the output type. */
 int smk_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int D, float eps,
                   int out_bf16, void* stream);
+/* The fp16s mode's LayerNorm (vision_transformer.py:150-163 norm1 / norm2, 1e-6): y [rows, ldy] fp16 = fp16(LN(x)) in columns [0, D);
+ * lo_kind 1 adds the fp16 rounding residue in columns [D, 2D) ([hi | lo] operand rows), lo_kind 2 the e4m3 correction operands of
+ * smk_split_q8 in the same 2D bytes (the A operand of smk_gemm_q8); y32 (optional) receives the fp32 normalised rows. */
+int smk_layernorm_f16(const float* x, const float* gamma, const float* beta, void* y, int64_t ldy, float* y32, int64_t rows, int D,
+                      float eps, int lo_kind, void* stream);
+/* Patch im2col of the fp16s mode (vision_transformer.py:184-188 as a GEMM): x [B, 3, H, W] fp32, or raw uint8 pixels normalised on the
+ * fly with mean_std (host, 6 floats: ((u/255) - mean) / std in IEEE fp32, datasets/base_dataset.py:250) → cols [B*hp*wp, 2*3*P*P fp16
+ * columns]: [hi | lo] fp16, or [hi | e4m3 operands] when q8 != 0.  Images are zero-padded to multiples of P (:260-267). */
+int smk_im2col_f16(const void* x, int is_u8, void* cols, int B, int H, int W, int P, const float* mean_std, int q8, void* stream);
 /* softmax(scale * Q K^T) V for `batch` problems × `heads`, fp32 math.
  * Q row (b,i) at q + b*q_bstride + i*ldq, head h in columns [h*dh, h*dh+dh); same for k, v, o. */
 int smk_attention(const void* q, const void* k, const void* v, void* o, int batch, int heads, int dh, int Lq, int Lk,

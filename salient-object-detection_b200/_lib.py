@@ -51,6 +51,8 @@ SIGNATURES = {
     "smk_upsample_bilinear": (_I, [_P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_gemm_f32": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "smk_gemm_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "smk_layernorm_f16": (_I, [_P, _P, _P, _P, _L, _P, _L, _I, _F, _I, _P]),
+    "smk_im2col_f16": (_I, [_P, _I, _P, _I, _I, _I, _I, C.POINTER(C.c_float), _I, _P]),
     "smk_gemm_tokens": (_I, [_P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_gemm_q8": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "smk_split_q8": (_I, [_P, _L, _P, _L, _I, _I, _P]),

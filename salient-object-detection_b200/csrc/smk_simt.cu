@@ -1193,6 +1193,20 @@ extern "C" int smk_layernorm(const float* x, const float* gamma, const float* be
   return layernorm_f32(x, nullptr, gamma, beta, (float*)y, nullptr, rows, D, eps, (cudaStream_t)stream);
 }
 
+extern "C" int smk_layernorm_f16(const float* x, const float* gamma, const float* beta, void* y, int64_t ldy, float* y32, int64_t rows, int D,
+                                 float eps, int lo_kind, void* stream) {
+  SMK_REQUIRE(x && gamma && beta && y && rows >= 0 && lo_kind >= 0 && lo_kind <= 2 && ldy >= (lo_kind ? 2 : 1) * (int64_t)D, "smk_layernorm_f16: bad arguments");
+  return layernorm_f16(x, gamma, beta, (__half*)y, lo_kind ? (__half*)y + D : nullptr, ldy, y32, nullptr, nullptr, rows, D, eps, (cudaStream_t)stream, 0,
+                       lo_kind == 2);
+}
+
+extern "C" int smk_im2col_f16(const void* x, int is_u8, void* cols, int B, int H, int W, int P, const float* mean_std, int q8, void* stream) {
+  SMK_REQUIRE(x && cols && B >= 0 && H > 0 && W > 0 && P > 0, "smk_im2col_f16: bad arguments");
+  const int hp = (H + P - 1) / P, wp = (W + P - 1) / P;
+  if (is_u8) return im2col_split_f16<uint8_t>((const uint8_t*)x, (__half*)cols, B, H, W, P, hp, wp, mean_std, (cudaStream_t)stream, q8);
+  return im2col_split_f16<float>((const float*)x, (__half*)cols, B, H, W, P, hp, wp, nullptr, (cudaStream_t)stream, q8);
+}
+
 extern "C" int smk_attention(const void* q, const void* k, const void* v, void* o, int batch, int heads, int dh, int Lq, int Lk,
                              int64_t q_bstride, int64_t ldq, int64_t k_bstride, int64_t ldk, int64_t v_bstride, int64_t ldv,
                              int64_t o_bstride, int64_t ldo, float scale, int is_bf16, void* stream) {

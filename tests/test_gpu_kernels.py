@@ -605,6 +605,65 @@ def test_split_q8_layout_and_values():
             assert torch.equal(first, _q8(h.float())) and torch.equal(second, _q8(lo * 2.0 ** 11))
 
 
+@pytest.mark.parametrize("rows", [1, 37, 50432])
+def test_layernorm_fp16_operand_rows(rows):
+    """The fp16s LayerNorm writes its consumer GEMM's operand rows in the same pass as the fp32 result: [hi | lo] fp16 and [hi | e4m3]
+    must be exactly the splits of that fp32 row (bit for bit), and the fp32 row the reference LayerNorm within rounding."""
+    torch.manual_seed(49)
+    D = 384
+    x = torch.randn(rows, D, device=DEV) * 3.0 + 0.5
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    y32 = torch.empty(rows, D, device=DEV)
+    for lo_kind in (0, 1, 2):
+        y = torch.full((rows, 2 * D), 7.0, dtype=torch.float16, device=DEV)
+        check(lib().smk_layernorm_f16(ptr(x), ptr(g), ptr(b), ptr(y), 2 * D, ptr(y32), rows, D, 1e-6, lo_kind, stream_ptr()), "smk_layernorm_f16")
+        torch.cuda.synchronize()
+        hi = y32.to(torch.float16)
+        assert torch.equal(y[:, :D], hi)
+        if lo_kind == 0:
+            assert (y[:, D:] == 7.0).all()
+        elif lo_kind == 1:
+            assert torch.equal(y[:, D:], (y32 - hi.float()).to(torch.float16))
+        else:
+            want = torch.zeros(rows, 2 * D, dtype=torch.float16, device=DEV)
+            check(lib().smk_split_q8(ptr(y32), D, ptr(want), rows, D, 0, stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(y.view(torch.int16), want.view(torch.int16))
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-6)
+    assert (y32.double() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,P,is_u8", [(3, 224, 224, 16, 1), (2, 200, 180, 16, 0), (2, 224, 224, 8, 1), (1, 40, 56, 16, 1)])
+def test_im2col_fp16_operand_rows(B, H, W, P, is_u8):
+    """Patch im2col of the fp16s mode: the [hi | e4m3] rows are the smk_split_q8 form of the [hi | lo] rows' values (hi + lo carries the
+    normalised pixel to ~2^-22), uint8 pixels normalised with the reference's IEEE expression, zero padding to multiples of P."""
+    torch.manual_seed(50)
+    mean_std = (C.c_float * 6)(0.485, 0.456, 0.406, 0.229, 0.224, 0.225)
+    if is_u8:
+        x = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device=DEV)
+        xn = ((x.float() / 255.0) - torch.tensor([0.485, 0.456, 0.406], device=DEV).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225], device=DEV).view(1, 3, 1, 1)
+    else:
+        x = torch.randn(B, 3, H, W, device=DEV)
+        xn = x
+    hp, wp, K = -(-H // P), -(-W // P), 3 * P * P
+    outs = []
+    for q8 in (0, 1):
+        cols = torch.full((B * hp * wp, 2 * K), 7.0, dtype=torch.float16, device=DEV)
+        check(lib().smk_im2col_f16(ptr(x), is_u8, ptr(cols), B, H, W, P, mean_std, q8, stream_ptr()), "smk_im2col_f16")
+        torch.cuda.synchronize()
+        outs.append(cols)
+    xp = torch.nn.functional.pad(xn, (0, wp * P - W, 0, hp * P - H))
+    ref = xp.view(B, 3, hp, P, wp, P).permute(0, 2, 4, 1, 3, 5).reshape(B * hp * wp, K)
+    split, q = outs
+    assert torch.equal(split[:, :K], ref.to(torch.float16))
+    val = split[:, :K].float() + split[:, K:].float()                  # hi + lo
+    assert (val - ref).abs().max().item() <= 1e-6
+    hi, first, second = _unpack_q8(q, K)
+    assert torch.equal(hi, split[:, :K].double()) and torch.equal(first, _q8(split[:, :K].float()))
+    lo = split[:, K:].double()
+    assert ((second * 2.0 ** -11 - lo).abs() <= lo.abs() * (2.0 ** -4 + 2.0 ** -9) + 2.0 ** -21).all()
+
+
 @pytest.mark.parametrize("M_,N,K,epi,out_kind", [
     (300, 384, 384, 0, 1), (50432, 1536, 384, 1, 4), (50432, 384, 1536, 4, 1), (50176, 384, 768, 0, 1), (50432, 384, 384, 4, 1),
     (20000, 512, 1024, 0, 0), (130, 128, 64, 2, 3), (5000, 256, 192, 0, 4)])
