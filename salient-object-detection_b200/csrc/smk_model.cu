@@ -675,23 +675,33 @@ static int model_forward_impl(smk_model* m, const float* x, const uint8_t* x_u8,
                             terms(m->t_pe, Kpe), 0, s));
       SMK_PROPAGATE(assemble_tokens(nullptr, w + m->o_cls, m->pos, m->X, B, hw, D, true, s));
     }
-    for (int i = 0; i < c.depth; ++i) {
+    // one encoder block for the images [b0, b0 + nb) on stream st (every buffer is row-sliceable: tokens of an image are contiguous rows)
+    auto enc_block = [&](int i, int b0, int nb, cudaStream_t st) -> int {
       const BlockW& b = m->blk[i];
-      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + b.n1w, w + b.n1b, Xn, m->t_qkv >= 3 ? Xn + D : nullptr, m->t_qkv >= 3 ? 2 * D : D, nullptr, nullptr, nullptr, M, D, 1e-6f, s)); }
-      { TagScope tg(TAG_QKV); SMK_PROPAGATE(gemm_tc(Xn, m->t_qkv >= 3 ? 2 * D : D, wh + 2 * b.qkvw, 2 * D, w + b.qkvb, QKV, 3 * D, M, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_qkv, D), 0, s)); }
+      const int64_t r0 = (int64_t)b0 * N;
+      const int Mh = nb * N;
+      float* Xh = m->X + r0 * D;
+      __half *Xnh = Xn + r0 * 2 * D, *QKVh = QKV + r0 * 3 * D, *AOh = AO + r0 * 2 * D, *Hmh = Hm + r0 * F2;
+      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(Xh, w + b.n1w, w + b.n1b, Xnh, m->t_qkv >= 3 ? Xnh + D : nullptr, m->t_qkv >= 3 ? 2 * D : D, nullptr, nullptr, nullptr, Mh, D, 1e-6f, st)); }
+      { TagScope tg(TAG_QKV); SMK_PROPAGATE(gemm_tc(Xnh, m->t_qkv >= 3 ? 2 * D : D, wh + 2 * b.qkvw, 2 * D, w + b.qkvb, QKVh, 3 * D, Mh, 3 * D, D, SMK_EPI_NONE, 0, 0, nullptr, 1, terms(m->t_qkv, D), 0, st)); }
       {
         TagScope tg(TAG_ATTN);
         const int ao_mode = m->t_proj == 4 ? 4 : 3;
-        if (N <= 256) SMK_PROPAGATE(attention_tc_f16(QKV, AO, 2 * D, ao_mode, B, N, c.heads, scale, s));
-        else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(QKV, 3 * D, QKV + D, 3 * D, QKV + 2 * D, 3 * D, M, M, N, N, 0, AO, 2 * D, ao_mode, B, N, N, c.heads, scale, 1, s));
-        else SMK_PROPAGATE(attention_fa((const __nv_bfloat16*)QKV, nullptr, 3 * D, (const __nv_bfloat16*)QKV + D, nullptr, 3 * D, (const __nv_bfloat16*)QKV + 2 * D, nullptr, 3 * D, N, N, 0,
-                                        AO, 2 * D, 3, B, N, N, c.heads, scale, s, 1));
+        if (N <= 256) SMK_PROPAGATE(attention_tc_f16(QKVh, AOh, 2 * D, ao_mode, nb, N, c.heads, scale, st));
+        else if (multi_attn) SMK_PROPAGATE(attention_tc_multi(QKVh, 3 * D, QKVh + D, 3 * D, QKVh + 2 * D, 3 * D, Mh, Mh, N, N, 0, AOh, 2 * D, ao_mode, nb, N, N, c.heads, scale, 1, st));
+        else SMK_PROPAGATE(attention_fa((const __nv_bfloat16*)QKVh, nullptr, 3 * D, (const __nv_bfloat16*)QKVh + D, nullptr, 3 * D, (const __nv_bfloat16*)QKVh + 2 * D, nullptr, 3 * D, N, N, 0,
+                                        AOh, 2 * D, 3, nb, N, N, c.heads, scale, st, 1));
       }
-      { TagScope tg(TAG_PROJ); SMK_PROPAGATE(gemm_tc(AO, 2 * D, wh + 2 * b.pw, 2 * D, w + b.pb, m->X, D, M, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_proj, D), 0, s)); }
-      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + b.n2w, w + b.n2b, Xn, Xn + D, 2 * D, nullptr, nullptr, nullptr, M, D, 1e-6f, s, 0, m->t_fc1 == 4)); }
-      { TagScope tg(TAG_FC1); SMK_PROPAGATE(gemm_tc(Xn, 2 * D, wh + 2 * b.f1w, 2 * D, w + b.f1b, Hm, F2, M, F, D, SMK_EPI_GELU, m->t_fc2 == 4 ? 4 : 3, 0, nullptr, 1, terms(m->t_fc1, D), 0, s)); }
-      { TagScope tg(TAG_FC2); SMK_PROPAGATE(gemm_tc(Hm, F2, wh + 2 * b.f2w, F2, w + b.f2b, m->X, D, M, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_fc2, F), 0, s)); }
-    }
+      { TagScope tg(TAG_PROJ); SMK_PROPAGATE(gemm_tc(AOh, 2 * D, wh + 2 * b.pw, 2 * D, w + b.pb, Xh, D, Mh, D, D, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_proj, D), 0, st)); }
+      { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(Xh, w + b.n2w, w + b.n2b, Xnh, Xnh + D, 2 * D, nullptr, nullptr, nullptr, Mh, D, 1e-6f, st, 0, m->t_fc1 == 4)); }
+      { TagScope tg(TAG_FC1); SMK_PROPAGATE(gemm_tc(Xnh, 2 * D, wh + 2 * b.f1w, 2 * D, w + b.f1b, Hmh, F2, Mh, F, D, SMK_EPI_GELU, m->t_fc2 == 4 ? 4 : 3, 0, nullptr, 1, terms(m->t_fc1, D), 0, st)); }
+      { TagScope tg(TAG_FC2); SMK_PROPAGATE(gemm_tc(Hmh, F2, wh + 2 * b.f2w, F2, w + b.f2b, Xh, D, Mh, D, F, SMK_EPI_RESIDUAL, 1, 0, nullptr, 1, terms(m->t_fc2, F), 0, st)); }
+      return SMK_OK;
+    };
+    // (Two half-batches on two streams — LayerNorms and kernel tails of one half under the shared-memory-bound GEMMs of the other — were
+    // measured SLOWER: 8.39 ms against 8.24 ms per step; the half-size persistent kernels lose more to wave quantisation than the
+    // overlap returns.  profiles/r02_step_experiments.md)
+    for (int i = 0; i < c.depth; ++i) SMK_PROPAGATE(enc_block(i, 0, B, s));
     // final norm: fp32 tokens (mask head reference copy), bf16 hi / lo (mask-logit contraction), fp16 (decoder memory)
     { TagScope tg(TAG_LN); SMK_PROPAGATE(layernorm_f16(m->X, w + m->o_enw, w + m->o_enb, m->tokh, nullptr, D, m->tok32, m->tok16, m->tok16 + D, M, D, 1e-6f, s, 2 * D)); }
     // memory K/V projection: only for geometries the restructured cross-attention does not cover (it attends the tokens directly)
