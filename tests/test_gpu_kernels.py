@@ -461,7 +461,7 @@ def _split16(x, dt):
 
 @pytest.mark.parametrize("f16", [1, 0])
 @pytest.mark.parametrize("M_,N,K,epi,terms,out_kind", [
-    (50432, 1152, 384, 0, 2, 0),      # qkv: A_hi·(W_hi + W_lo), 16-bit output (16-warp epilogue)
+    (50432, 1152, 384, 0, 2, 0),      # qkv: A_hi·(W_hi + W_lo), 16-bit output (swap-AB form: transposed 16-bit epilogue)
     (50432, 384, 384, 4, 3, 1),       # proj: 3 terms, fp32 residual
     (50432, 1536, 384, 1, 3, 3),      # fc1: 3 terms, GELU, [hi | lo] output
     (50432, 384, 1536, 4, 3, 1),      # fc2: 3 terms over K = 1536 (swap-AB form), fp32 residual
