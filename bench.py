@@ -507,6 +507,9 @@ def main():
                               "(the e4m3 correction products of the fp16s GEMMs count as 2·M·N·2K issued at the fp8 rate, i.e. twice the peak this fraction is taken against)",
                 "kernels": rows, "event_timed_ms_per_step": prof_ms, "plain_ms_per_step": ms / K,
                 "note": "event pairs around every launch defeat the PDL overlap, so the per-kernel rows sum to more than the plain step",
+                "limiter": ("the split GEMMs (fc1 / fc2 / proj / patch embed) are shared-memory-bandwidth bound, not MMA bound: with K = 384 every operand "
+                            "byte of a 128 x 256 tile is written once by TMA and read once by the tensor core, 4 bytes per split element "
+                            "(profiles/r02_gemm_q8.md: MMA only 79.5 us, + operand stream 101.7 us, + epilogue 133 us for fc1)") if args.mode == "fp16s" else None,
                 "whole_step": ({"algorithmic_gflop_per_image": gflop_img, "achieved_tflops": value / world * gflop_img / 1e3,
                                 "frac_of_sustained_bf16_peak": value / world * gflop_img / 1e3 / pk["tensor"]} if gflop_img else None)}
 
